@@ -1,0 +1,43 @@
+// Device-resident state of a clpp_ctx (HBM layout, see DESIGN.md "Data layout in HBM").
+#ifndef CLPP_DEVICE_H
+#define CLPP_DEVICE_H
+
+#include <cuda_runtime.h>
+
+#include "clpp_internal.h"
+
+struct clpp_ctx::Dev {
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+
+  // upstream tables: row-major [n_lines][n_cols] + second derivatives, L2-resident (~6 MB)
+  double *bg_tau = nullptr, *bg_y = nullptr, *bg_dd = nullptr;
+  double *th_z = nullptr, *th_y = nullptr, *th_dd = nullptr;
+
+  // stage 1
+  double *k = nullptr, *tau = nullptr;
+  double* sources = nullptr;  // [tp][k][tau], tau fastest (one k-mode writes contiguous rows)
+  clpp_kstat* kstat = nullptr;
+  int* k_order = nullptr;     // work queue: mode indices sorted by decreasing expected cost
+  int* queue_head = nullptr;  // atomic cursor into k_order
+  double* jac_scratch = nullptr;  // per-slot global workspace (Jacobian for large systems)
+  size_t sources_count = 0;
+
+  // stage 2
+  double *q = nullptr, *kq = nullptr;
+  int *l = nullptr;
+  double *bessel_x = nullptr, *bessel_phi = nullptr, *bessel_dphi = nullptr, *chi_at_phimin = nullptr;
+  int bessel_nx = 0;
+  double bessel_dx = 0., bessel_xmin = 0.;
+  double* src_tr = nullptr;   // sources seen by the transfer stage (after nl correction) [tp][k][tau]
+  double* src_ddk = nullptr;  // d2S/dk2 for the cubic spline in k, same layout
+  double* nl_corr = nullptr;
+  double* transfer = nullptr;  // [tt][l][q], q fastest (= reference layout)
+  size_t transfer_count = 0;
+  unsigned long long* tr_counters = nullptr;
+
+  // stage 3
+  double *pk = nullptr, *wq = nullptr, *cl = nullptr;
+};
+
+#endif
