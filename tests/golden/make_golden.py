@@ -1,0 +1,60 @@
+"""Generate the golden fixtures of tests/golden/ from the UNMODIFIED reference (oracle/_ref).
+
+Run here (container with /root/reference, after `make -C oracle`):
+    python tests/golden/make_golden.py
+Each <config>.npz holds
+  * the upstream inputs of the hot path (scalars in `meta`, background/thermodynamics tables,
+    ncdm momentum grids, primordial spectrum on the transfer k grid, halofit correction), and
+  * reference outputs: the k/tau/q/l grids (bit-exact targets), the full C_l table, the lensed
+    C_l's, and sub-sampled columns of S(k,tau) and rows of Delta_l(q).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle.refprobe import RefCosmology  # noqa: E402
+from classpp_public_b200.configs import CONFIGS  # noqa: E402
+from refutil import inputs_from_reference, reference_sources  # noqa: E402
+
+
+def make(name, n_k_cols=9, n_l_rows=8):
+    ref = RefCosmology(CONFIGS[name], threads=os.cpu_count()).compute("lensing")
+    inp = inputs_from_reference(ref)
+    nk, nt, ntp = ref.iscalar("pt.k_size"), ref.iscalar("pt.tau_size"), ref.iscalar("pt.tp_size")
+    ntt, nl, nq = ref.iscalar("tr.tt_size"), ref.iscalar("tr.l_size"), ref.iscalar("tr.q_size")
+    src = reference_sources(ref).reshape(ntp, nt, nk)
+    k_cols = np.unique(np.linspace(0, nk - 1, n_k_cols).astype(int))
+    tr = ref.get("tr.transfer").reshape(ntt, nl, nq)
+    l_rows = np.unique(np.linspace(0, nl - 1, n_l_rows).astype(int))
+    extra = {
+        "ref.k": ref.get("pt.k"), "ref.tau": ref.get("pt.tau_sampling"),
+        "ref.q": ref.get("tr.q"), "ref.kq": ref.get("tr.k"), "ref.l": ref.get("tr.l"),
+        "ref.l_size_tt": ref.get("tr.l_size_tt"),
+        "ref.sizes": np.array([nk, ref.iscalar("pt.k_size_cl"), ref.iscalar("pt.k_size_cmb"), nt, ntp, ntt, nl, nq,
+                               ref.iscalar("sp.ct_size")], dtype=np.float64),
+        "ref.tp_index": np.array([ref.iscalar("pt.index_tp_" + n) if ref.iscalar("pt.has_source_" + f) else -1
+                                  for n, f in (("t0", "t"), ("t1", "t"), ("t2", "t"), ("p", "p"),
+                                               ("delta_m", "delta_m"), ("delta_cb", "delta_cb"),
+                                               ("phi_plus_psi", "phi_plus_psi"))], dtype=np.float64),
+        "ref.k_cols": k_cols.astype(np.float64), "ref.sources_cols": src[:, :, k_cols],
+        "ref.l_rows": l_rows.astype(np.float64), "ref.transfer_rows": tr[:, l_rows, :],
+        "ref.cl": ref.get("sp.cl"),
+        "ref.cl_lensed": ref.get("le.cl_lensed"),
+        "pm.pk_at_transfer_k": ref.get("pm.pk_at_transfer_k"),
+    }
+    if int(inp.meta["nl.method"]) != 0:
+        extra["nl.nl_corr_density_m"] = ref.get("nl.nl_corr_density_m").astype(np.float64)
+    out = os.path.join(HERE, name + ".npz")
+    inp.save(out, extra)
+    print(name, "->", out, "%.2f MB" % (os.path.getsize(out) / 1e6))
+
+
+if __name__ == "__main__":
+    for name in (sys.argv[1:] or ["lcdm_coarse", "lcdm", "planck18"]):
+        make(name)
