@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native CLASS++ hot path.
+
+Metric (BASELINE.json): lensed-C_l spectra / s for the Planck-2018 LambdaCDM configuration
+(base_2018_plikHM_TTTEEE_lowl_lowE_lensing.ini: 1 massive neutrino species, halofit,
+l_max_scalars=2500, P(k) to 1 h/Mpc), measured on the hot path this repository replaces:
+PerturbationsModule -> TransferModule -> SpectraModule.
+
+A "step" = one pass of the hot path over one batch of `--batch` cosmologies per GPU.  Upstream
+inputs (background/thermodynamics tables, ncdm grids, halofit correction, primordial spectrum)
+are synthetic-by-construction: they were generated once from the reference for the named
+configuration and are stored in tests/golden/planck18.npz.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU)
+  python bench.py --impl reference --steps K --warmup W    the reference's CPU implementation
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "lensed C_l spectra/sec (Planck-18 LCDM hot path: perturbations+transfer+spectra)"
+UNIT = "spectra/s"
+
+# Algorithmic FP64 work of stage 1 per cosmology (SURVEY.md 8d / BASELINE.md 2): oracle stepstat
+# counters x fixed per-RHS / per-solve costs -- NOT the GPU's own step count.
+ALGO_FLOP_STAGE1 = {"planck18": 3.6e9, "lcdm": 1.0e9, "lcdm_coarse": 1.0e8}
+# stage 2: integrand points x 40 flop
+ALGO_FLOP_PER_LOS_POINT = 40.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        def num(s):
+            try:
+                return float(s)
+            except Exception:
+                return None
+        sm = [num(r[0]) for r in self.rows if r and num(r[0]) is not None]
+        mx = [num(r[1]) for r in self.rows if len(r) > 1 and num(r[1]) is not None]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+class _NL:
+    def __init__(self, arr):
+        self.nl_corr_density_m = arr
+
+
+def hot_path(M, inp, ctx, bg, th, pk, nl, fetch_tables=False):
+    """One cosmology through the three stages on an existing context."""
+    pt = M.PerturbationsModule(inp, bg, th)
+    tr = M.TransferModule(inp, bg, th, pt, nl)
+    sp = M.SpectraModule(inp, pt, M.TabulatedPrimordial(pk), nl, tr)
+    out_bytes = sp.cl_[0].nbytes
+    if fetch_tables:  # what the reference-facing drop-in hands back as public members
+        out_bytes += sum(s.nbytes for s in pt.sources_[0]) + tr.transfer_[0].nbytes
+    return pt, tr, sp, out_bytes
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from classpp_public_b200 import modules as M
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    inp = M.Inputs.load(os.path.join(ROOT, "tests", "golden", args.config + ".npz"))
+    a = inp.arrays
+    pk = a["pm.pk_at_transfer_k"]
+    nl = _NL(a["nl.nl_corr_density_m"]) if "nl.nl_corr_density_m" in a else None
+    B = args.batch
+
+    # ---- device-resident inputs: one context (own stream) per cosmology of the batch
+    ctxs, mods = [], []
+    for b in range(B):
+        ctx = M.Context(local)
+        bg = M.BackgroundModule(inp, ctx)
+        th = M.ThermodynamicsModule(inp, bg)
+        ctxs.append(ctx)
+        mods.append((bg, th))
+
+    results = [None] * B
+
+    def one(b, fetch=False):
+        results[b] = hot_path(M, inp, ctxs[b], mods[b][0], mods[b][1], pk, nl, fetch)
+
+    def step(fetch=False):
+        if B == 1:
+            one(0, fetch)
+        else:
+            ths = [threading.Thread(target=one, args=(b, fetch)) for b in range(B)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    launches0 = sum(c.launch_count for c in ctxs)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    t0 = time.perf_counter()
+    kms = {"perturb": 0.0, "k_spline": 0.0, "bessel": 0.0, "los": 0.0, "spectra": 0.0}
+    for _ in range(args.steps):
+        step()
+        for c in ctxs:
+            for k_, v in c.kernel_ms().items():
+                kms[k_] += v
+    barrier()
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    elapsed = max(ev0.elapsed_time(ev1) * 1e-3, 1e-9)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    launches = sum(c.launch_count for c in ctxs) - launches0
+    if world > 1:
+        t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    n_cosmo = B * args.steps * world
+    value = n_cosmo / elapsed
+
+    # ---- end to end through the public (reference-facing) API from pinned HOST buffers
+    def pinned(x):
+        return torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()
+    inp_h = M.Inputs(inp.meta, {k: (pinned(v) if v.dtype == np.float64 and v.size > 64 else v) for k, v in a.items()})
+    pk_h = pinned(pk)
+    nl_h = _NL(pinned(nl.nl_corr_density_m)) if nl is not None else None
+    h2d = sum(inp_h.arrays[k].nbytes for k in ("bg.tau_table", "bg.background_table", "th.z_table",
+                                               "th.thermodynamics_table")) * 2  # tables + their spline tables
+    h2d += (nl_h.nl_corr_density_m.nbytes if nl_h is not None else 0) + pk_h.nbytes
+    e2e_steps = max(1, min(args.steps, 3))
+    d2h = 0
+    barrier()
+    te0 = time.perf_counter()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    for _ in range(e2e_steps):
+        ctx = M.Context(local)
+        bg = M.BackgroundModule(inp_h, ctx)       # host -> device copy of this step's inputs
+        th = M.ThermodynamicsModule(inp_h, bg)
+        _, _, sp, d2h = hot_path(M, inp_h, ctx, bg, th, pk_h, nl_h, fetch_tables=True)  # device -> host results
+        ctx.close()
+    barrier()
+    ee1.record()
+    torch.cuda.synchronize()
+    e2e_elapsed = max(ee0.elapsed_time(ee1) * 1e-3, time.perf_counter() - te0)
+    if world > 1:
+        t = torch.tensor([e2e_elapsed], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_elapsed = float(t.item())
+    e2e_value = e2e_steps * world / e2e_elapsed
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (perturb_kernel): FP64 vector pipe
+    peaks, peaks_kind = load_peaks()
+    fp64_peak = ctxs[0].fp64_peak_tflops()
+    n_launch = B * args.steps
+    t_perturb = max(kms["perturb"] * 1e-3 / n_launch, 1e-12)  # average duration of one perturb_kernel launch
+    algo = ALGO_FLOP_STAGE1.get(args.config, 1.0e9)
+    achieved = algo / t_perturb / 1e12
+    tr_info = results[0][1].info
+    t_los = max(kms["los"] * 1e-3 / n_launch, 1e-12)
+    sec_achieved = ALGO_FLOP_PER_LOS_POINT * 1.5e8 / t_los / 1e12
+    roofline = {"kernel": "perturb_kernel", "bound": "fp64-vector (latency-bound in practice; neither hbm nor tensor)",
+                "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                "peak_source": "DFMA microbenchmark run live in bench.py (MEASURED_PEAKS.json has no FP64 entry; "
+                               "its hbm_gbs=%s bf16_tflops=%s are %s)" % (peaks.get("hbm_gbs"), peaks.get("bf16_tflops"), peaks_kind),
+                "traffic": None,
+                "algorithmic_flop_per_launch": algo,
+                "kernel_ms_per_launch": {k_: v / n_launch for k_, v in kms.items()},
+                "kernel_share_of_step": {k_: v * 1e-3 / elapsed / max(B, 1) for k_, v in kms.items()},
+                "secondary": {"kernel": "los_kernel", "bound": "fp64-vector", "achieved": sec_achieved,
+                              "peak": fp64_peak, "unit": "TFLOP/s", "frac": sec_achieved / fp64_peak}}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": ("BASELINE configs[1]: base_2018_plikHM_TTTEEE_lowl_lowE_lensing.ini (Planck-2018 best fit, "
+                                "1 ncdm species, halofit, l_max_scalars=2500, P_k_max_h/Mpc=1)") if args.config == "planck18"
+                               else args.config,
+                   "fixture": "tests/golden/%s.npz" % args.config, "batch_per_gpu": B,
+                   "k_modes": int(results[0][0].info.k_size), "tau_samples": int(results[0][0].info.tau_size),
+                   "q_values": int(tr_info.q_size), "l_values": int(tr_info.l_size),
+                   "parallelism": "independent cosmologies per GPU (replicas, no data-path collective)",
+                   "l2_policy": "working set per step (sources 24 MB + source spline 48 MB + Bessel 17 MB + transfer 12 MB "
+                                "+ Jacobian scratch) is reallocated and rewritten every step; > L2 with the scratch",
+                   "timing": "torch.cuda.Event around K steps after device-wide synchronize, max over ranks; per-kernel "
+                             "times from cudaEvents on the launching stream inside libclpp.so"},
+        "k_modes_per_s": value * int(results[0][0].info.k_size),
+        "wall_s": wall,
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps,
+                "note": "Context create + table upload from pinned host + 3 stages + D2H of sources_, transfer_, cl_"},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.config, budget_s=20.0)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(config, budget_s=20.0, threads=None):
+    """The reference's own CPU implementation of the hot path (oracle/_ref = unmodified CLASS++ built
+    from /root/reference) on this box's host cores, timed per module constructor by the probe."""
+    from oracle import refprobe
+    from classpp_public_b200.configs import CONFIGS
+    if not refprobe.available():
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                "sample": "oracle/_ref not built on this box"}
+    cores = threads or os.cpu_count()
+    times = []
+    t_start = time.perf_counter()
+    n = 0
+    while True:
+        ref = refprobe.RefCosmology(CONFIGS[config], threads=cores)
+        ref.compute("spectra")
+        t = ref.scalar("time.perturb") + ref.scalar("time.transfer") + ref.scalar("time.spectra")
+        ref.close()
+        n += 1
+        if n > 1:  # the first run of a process is cold: discard
+            times.append(t)
+        if (time.perf_counter() - t_start > budget_s and len(times) >= 2) or len(times) >= 8:
+            break
+    best = min(times)
+    return {"value": 1.0 / best, "unit": UNIT, "cores": int(cores), "kind": "reference",
+            "hot_path_s_best": best, "hot_path_s_mean": float(np.mean(times)),
+            "sample": "%d full runs of the reference for this config (first discarded); value = 1 / best wall time of "
+                      "the PerturbationsModule+TransferModule+SpectraModule constructors (same scope as the GPU arm; "
+                      "background/thermodynamics/halofit/lensing excluded), thread pool = %d threads" % (n, cores)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import refprobe
+    from classpp_public_b200.configs import CONFIGS
+    if not refprobe.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (make -C oracle needs /root/reference)"}))
+        return
+    cores = os.cpu_count()
+    ts = []
+    for i in range(args.warmup + args.steps):
+        ref = refprobe.RefCosmology(CONFIGS[args.config], threads=cores).compute("spectra")
+        t = ref.scalar("time.perturb") + ref.scalar("time.transfer") + ref.scalar("time.spectra")
+        ref.close()
+        if i >= args.warmup:
+            ts.append(t)
+    total = float(np.sum(ts))
+    value = len(ts) / total
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(ts) * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": args.config, "note": "unmodified CLASS++ (oracle/_ref) on the host cores; each step = "
+                      "one cosmology, timed = PerturbationsModule+TransferModule+SpectraModule constructors"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(cores), "kind": "reference",
+                            "sample": "%d steps of 1 cosmology each, thread pool = %d" % (len(ts), cores)},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="planck18")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("CLPP_BENCH_BATCH", 1)))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

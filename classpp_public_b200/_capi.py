@@ -127,6 +127,7 @@ class SpectraInfo(C.Structure):
 # every symbol declared in include/clpp.h (tests check that the library exports all of them)
 SYMBOLS = [
     "clpp_ctx_create", "clpp_ctx_destroy", "clpp_ctx_launch_count", "clpp_version",
+    "clpp_ctx_get_stream", "clpp_ctx_get_kernel_ms", "clpp_measure_fp64_peak",
     "clpp_set_background", "clpp_set_thermo", "clpp_set_ncdm",
     "clpp_perturb_grids", "clpp_perturb_solve", "clpp_perturb_get_k", "clpp_perturb_get_tau",
     "clpp_perturb_get_sources", "clpp_perturb_get_kstat", "clpp_perturb_set_sources",
@@ -157,6 +158,9 @@ def lib():
         L.clpp_ctx_destroy.restype = None
         L.clpp_ctx_launch_count.argtypes = [vp]
         L.clpp_ctx_launch_count.restype = C.c_long
+        L.clpp_ctx_get_stream.argtypes = [vp, P(vp)]
+        L.clpp_ctx_get_kernel_ms.argtypes = [vp, dp]
+        L.clpp_measure_fp64_peak.argtypes = [vp, dp, cp]
         L.clpp_set_background.argtypes = [vp, P(BackgroundDesc), dp, dp, cp]
         L.clpp_set_thermo.argtypes = [vp, P(ThermoDesc), dp, dp, cp]
         L.clpp_set_ncdm.argtypes = [vp, C.c_int, ip, dp, dp, dp, dp, dp, cp]

@@ -52,6 +52,8 @@ int clpp_ctx_create(int device, clpp_ctx** out, char* err) {
       return clpp_fail(err, "cudaStreamCreate failed");
     }
     c->stream = c->dev->stream;
+    cudaEventCreate(&c->dev->ev[0]);
+    cudaEventCreate(&c->dev->ev[1]);
   }
   *out = c;
   return CLPP_SUCCESS;
@@ -69,6 +71,8 @@ void clpp_ctx_destroy(clpp_ctx* c) {
                     d->pk, d->wq, d->cl};
     for (void* p : ptrs)
       if (p) cudaFree(p);
+    cudaEventDestroy(d->ev[0]);
+    cudaEventDestroy(d->ev[1]);
     cudaStreamDestroy(d->stream);
     delete d;
   }
@@ -76,6 +80,53 @@ void clpp_ctx_destroy(clpp_ctx* c) {
 }
 
 long clpp_ctx_launch_count(const clpp_ctx* c) { return c ? c->launches : 0; }
+
+int clpp_ctx_get_stream(clpp_ctx* c, void** stream) {
+  if (!c || !c->dev || !stream) return CLPP_FAILURE;
+  *stream = (void*)c->dev->stream;
+  return CLPP_SUCCESS;
+}
+
+int clpp_ctx_get_kernel_ms(const clpp_ctx* c, double out[5]) {
+  if (!c || !c->dev) return CLPP_FAILURE;
+  out[0] = c->dev->t_perturb_ms; out[1] = c->dev->t_kspline_ms; out[2] = c->dev->t_bessel_ms;
+  out[3] = c->dev->t_los_ms; out[4] = c->dev->t_spectra_ms;
+  return CLPP_SUCCESS;
+}
+
+__global__ void dfma_peak_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3., a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6.,
+         a7 = a0 + 7.;
+  const double b = 1.0000001, cc = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, cc); a1 = fma(a1, b, cc); a2 = fma(a2, b, cc); a3 = fma(a3, b, cc);
+    a4 = fma(a4, b, cc); a5 = fma(a5, b, cc); a6 = fma(a6, b, cc); a7 = fma(a7, b, cc);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int clpp_measure_fp64_peak(clpp_ctx* c, double* tflops, char* err) {
+  CLPP_CHECK(c && c->dev && tflops, err, "no CUDA device");
+  cudaSetDevice(c->device);
+  clpp_ctx::Dev* d = c->dev;
+  const int blocks = d->sm_count * 8, threads = 256, iters = 20000;
+  double* out = nullptr;
+  CLPP_CUDA(cudaMalloc((void**)&out, (size_t)blocks * threads * sizeof(double)), err);
+  double best = 0.;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(d->ev[0], d->stream);
+    dfma_peak_kernel<<<blocks, threads, 0, d->stream>>>(out, iters);
+    cudaEventRecord(d->ev[1], d->stream);
+    CLPP_CUDA(cudaStreamSynchronize(d->stream), err);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]);
+    const double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaFree(out);
+  *tflops = best;
+  return CLPP_SUCCESS;
+}
 
 int clpp_set_background(clpp_ctx* c, const clpp_background_desc* desc, const double* tau_table,
                         const double* background_table, char* err) {

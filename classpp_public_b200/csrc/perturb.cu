@@ -1443,14 +1443,21 @@ int clpp_dev_perturb_solve(clpp_ctx* c, int k_begin, int k_end, char* err) {
   P.order = d->k_order; P.n_modes = n_modes; P.kstat = d->kstat; P.jac = d->jac_scratch;
 
   CLPP_CUDA(cudaFuncSetAttribute(perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
+  cudaEventRecord(d->ev[0], st);
   if (n_modes > 0) {
     perturb_kernel<<<n_modes, 32, smem, st>>>(P);
     c->launches++;
   }
+  cudaEventRecord(d->ev[1], st);
   CLPP_CUDA(cudaGetLastError(), err);
   c->kstat.assign(nk, clpp_kstat{});
   CLPP_CUDA(cudaMemcpyAsync(c->kstat.data(), d->kstat, nk * sizeof(clpp_kstat), cudaMemcpyDeviceToHost, st), err);
   CLPP_CUDA(cudaStreamSynchronize(st), err);
+  {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]);
+    d->t_perturb_ms = ms;
+  }
   if (d_q) cudaFree(d_q);
   for (int ik = k_begin; ik < k_end; ik++) {
     const int s = c->kstat[ik].status;

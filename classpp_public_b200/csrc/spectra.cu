@@ -196,12 +196,15 @@ int clpp_dev_spectra(clpp_ctx* c, const double* primordial_pk, int q_begin, int 
             err);
   double* partial = d->cl + (size_t)T.l_size * I.ct_size;
   dim3 grid(T.l_size, P.n_chunk);
+  cudaEventRecord(d->ev[0], d->stream);
   spectra_partial_kernel<<<grid, SPECTRA_THREADS, 0, d->stream>>>(P, d->transfer, d->wq, partial);
   spectra_final_kernel<<<(T.l_size + 127) / 128, 128, 0, d->stream>>>(P, partial, d->cl);
+  cudaEventRecord(d->ev[1], d->stream);
   c->launches += 2;
   CLPP_CUDA(cudaGetLastError(), err);
   CLPP_CUDA(cudaMemcpyAsync(cl_out, d->cl, (size_t)T.l_size * I.ct_size * sizeof(double), cudaMemcpyDeviceToHost,
                             d->stream), err);
   CLPP_CUDA(cudaStreamSynchronize(d->stream), err);
+  { float ms = 0; cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); d->t_spectra_ms = ms; }
   return CLPP_SUCCESS;
 }

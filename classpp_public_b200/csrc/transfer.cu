@@ -498,10 +498,13 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
     double* u = nullptr;
     CLPP_CUDA(cudaMalloc((void**)&u, nsrc * sizeof(double)), err);
     const int n = ntp * nt;
+    cudaEventRecord(d->ev[0], st);
     k_spline_kernel<<<(n + 127) / 128, 128, 0, st>>>(ntp, nk, nt, d->k, d->src_tr, d->src_ddk, u);
+    cudaEventRecord(d->ev[1], st);
     c->launches++;
     CLPP_CUDA(cudaGetLastError(), err);
     CLPP_CUDA(cudaStreamSynchronize(st), err);
+    { float ms = 0; cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); d->t_kspline_ms = ms; }
     cudaFree(u);
   }
 
@@ -528,8 +531,10 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
       return CLPP_FAILURE;
     int* scale_count = nullptr;
     CLPP_CUDA(cudaMalloc((void**)&scale_count, nb * sizeof(int)), err);
+    cudaEventRecord(d->ev[0], st);
     bessel_table_kernel<<<(nx + 63) / 64, 64, 0, st>>>(nx, xmin, dx, std::min(nx, xfwdidx), lmax + 1, TI.l_size_max, d->l,
                                                       d->bessel_x, d->bessel_phi, d->bessel_dphi, scale_count);
+    cudaEventRecord(d->ev[1], st);
     c->launches++;
     CLPP_CUDA(cudaGetLastError(), err);
     // chi_at_phimin (hyperspherical_get_xmin_from_approx, hyperspherical.c:1419-1457, K=0, nu=1)
@@ -542,6 +547,7 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
     }
     CLPP_CUDA(cudaMemcpyAsync(d->chi_at_phimin, chi.data(), chi.size() * sizeof(double), cudaMemcpyHostToDevice, st), err);
     CLPP_CUDA(cudaStreamSynchronize(st), err);
+    { float ms = 0; cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); d->t_bessel_ms = ms; }
     cudaFree(scale_count);
   }
 
@@ -581,16 +587,19 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
   const size_t smem = (size_t)(3 + TI.tt_size) * nt * sizeof(double);
   CLPP_CHECK(smem <= 200 * 1024, err, "tau_size=%d too large for the shared-memory staging of the LOS kernel", nt);
   CLPP_CUDA(cudaFuncSetAttribute(los_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
+  cudaEventRecord(d->ev[0], st);
   if (q_end > q_begin) {
     los_kernel<<<q_end - q_begin, LOS_THREADS, smem, st>>>(P, d->k, d->tau, d->q, d->kq, d->l, d->chi_at_phimin, d->src_tr,
                                                           d->src_ddk, d->bessel_phi, d->bessel_dphi, d->transfer,
                                                           d->tr_counters);
     c->launches++;
   }
+  cudaEventRecord(d->ev[1], st);
   CLPP_CUDA(cudaGetLastError(), err);
   unsigned long long cnt[2];
   CLPP_CUDA(cudaMemcpyAsync(cnt, d->tr_counters, sizeof(cnt), cudaMemcpyDeviceToHost, st), err);
   CLPP_CUDA(cudaStreamSynchronize(st), err);
+  { float ms = 0; cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); d->t_los_ms = ms; }
   c->tinfo.n_integrals = (long)cnt[0];
   c->tinfo.n_points = (long)cnt[1];
   c->has_transfer = true;

@@ -129,6 +129,22 @@ class Context:
     def launch_count(self):
         return int(self._lib.clpp_ctx_launch_count(self._h))
 
+    @property
+    def stream_ptr(self):
+        p = C.c_void_p()
+        self._lib.clpp_ctx_get_stream(self._h, C.byref(p))
+        return p.value or 0
+
+    def kernel_ms(self):
+        out = np.zeros(5)
+        self._lib.clpp_ctx_get_kernel_ms(self._h, capi.dptr(out))
+        return dict(zip(("perturb", "k_spline", "bessel", "los", "spectra"), out.tolist()))
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        self.check(self._lib.clpp_measure_fp64_peak(self._h, C.byref(v), self._err))
+        return v.value
+
     def close(self):
         if self._h:
             self._lib.clpp_ctx_destroy(self._h)
