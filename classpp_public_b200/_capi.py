@@ -91,7 +91,7 @@ class KStat(C.Structure):
     int: steps, failed, fevals, jacobians, factorizations, solves
     int: intervals, status
     double: tau_ini
-    """)
+    """) + [("iv_neq", C.c_int * 6), ("iv_steps", C.c_int * 6), ("iv_cycles", C.c_longlong * 6), ("prof", C.c_longlong * 72)]
 
 
 class TransferDesc(C.Structure):
@@ -129,7 +129,7 @@ SYMBOLS = [
     "clpp_ctx_create", "clpp_ctx_destroy", "clpp_ctx_launch_count", "clpp_version",
     "clpp_ctx_get_stream", "clpp_ctx_get_kernel_ms", "clpp_measure_fp64_peak",
     "clpp_set_background", "clpp_set_thermo", "clpp_set_ncdm",
-    "clpp_perturb_grids", "clpp_perturb_solve", "clpp_perturb_get_k", "clpp_perturb_get_tau",
+    "clpp_perturb_grids", "clpp_perturb_solve", "clpp_perturb_solve_batch", "clpp_perturb_get_k", "clpp_perturb_get_tau",
     "clpp_perturb_get_sources", "clpp_perturb_get_kstat", "clpp_perturb_set_sources",
     "clpp_perturb_device_sources",
     "clpp_transfer_grids", "clpp_transfer_compute", "clpp_transfer_get_l", "clpp_transfer_get_q",
@@ -166,6 +166,7 @@ def lib():
         L.clpp_set_ncdm.argtypes = [vp, C.c_int, ip, dp, dp, dp, dp, dp, cp]
         L.clpp_perturb_grids.argtypes = [vp, P(PerturbDesc), P(PerturbInfo), cp]
         L.clpp_perturb_solve.argtypes = [vp, C.c_int, C.c_int, cp]
+        L.clpp_perturb_solve_batch.argtypes = [P(vp), C.c_int, cp]
         L.clpp_perturb_get_k.argtypes = [vp, dp]
         L.clpp_perturb_get_tau.argtypes = [vp, dp]
         L.clpp_perturb_get_sources.argtypes = [vp, dp, cp]

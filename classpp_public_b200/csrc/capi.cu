@@ -10,6 +10,7 @@
 
 // implemented in the stage files
 int clpp_dev_perturb_solve(clpp_ctx* c, int k_begin, int k_end, char* err);
+int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, const int* k_end, char* err);
 int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_begin, int q_end, char* err);
 int clpp_dev_spectra(clpp_ctx* c, const double* primordial_pk, int q_begin, int q_end, clpp_spectra_info* info,
                      double* cl_out, char* err);
@@ -68,7 +69,7 @@ void clpp_ctx_destroy(clpp_ctx* c) {
     void* ptrs[] = {d->bg_tau, d->bg_y, d->bg_dd, d->th_z, d->th_y, d->th_dd, d->k, d->tau, d->sources, d->kstat,
                     d->k_order, d->queue_head, d->jac_scratch, d->q, d->kq, d->l, d->bessel_x, d->bessel_phi,
                     d->bessel_dphi, d->chi_at_phimin, d->src_tr, d->src_ddk, d->nl_corr, d->transfer, d->tr_counters,
-                    d->pk, d->wq, d->cl};
+                    d->pk, d->wq, d->cl, d->ncdm, d->pt_cosmo, d->pt_modes};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     cudaEventDestroy(d->ev[0]);
@@ -207,6 +208,19 @@ int clpp_perturb_solve(clpp_ctx* c, int k_begin, int k_end, char* err) {
   CLPP_CHECK(0 <= k_begin && k_begin <= k_end && k_end <= c->pinfo.k_size, err, "bad k range [%d,%d)", k_begin, k_end);
   cudaSetDevice(c->device);
   return clpp_dev_perturb_solve(c, k_begin, k_end, err);
+}
+
+int clpp_perturb_solve_batch(clpp_ctx** ctxs, int n_ctx, char* err) {
+  CLPP_CHECK(ctxs && n_ctx >= 1, err, "empty batch");
+  std::vector<int> kb(n_ctx, 0), ke(n_ctx, 0);
+  for (int b = 0; b < n_ctx; b++) {
+    clpp_ctx* c = ctxs[b];
+    CLPP_CHECK(c && c->has_pgrids, err, "clpp_perturb_grids must be called first (cosmology %d of the batch)", b);
+    CLPP_CHECK(c->dev, err, "this context has no CUDA device: the B200 path has no CPU fallback");
+    ke[b] = c->pinfo.k_size;
+  }
+  cudaSetDevice(ctxs[0]->device);
+  return clpp_dev_perturb_solve_batch(ctxs, n_ctx, kb.data(), ke.data(), err);
 }
 
 int clpp_perturb_get_k(const clpp_ctx* c, double* k) {

@@ -23,8 +23,11 @@ struct clpp_ctx::Dev {
   clpp_kstat* kstat = nullptr;
   int* k_order = nullptr;     // work queue: mode indices sorted by decreasing expected cost
   int* queue_head = nullptr;  // atomic cursor into k_order
-  double* jac_scratch = nullptr;  // per-slot global workspace (Jacobian for large systems)
+  double* jac_scratch = nullptr;  // per-CTA global workspace: hub block of the Jacobian
+  double* ncdm = nullptr;         // [3][nq_tot]: q, w, dlnf0/dlnq
+  unsigned char *pt_cosmo = nullptr, *pt_modes = nullptr;  // batch descriptors of the last solve (PtCosmo[], int2[])
   size_t sources_count = 0;
+  size_t k_cap = 0, tau_cap = 0, kstat_cap = 0, jac_cap = 0, ncdm_cap = 0, pt_cosmo_cap = 0, pt_modes_cap = 0;
 
   // stage 2
   double *q = nullptr, *kq = nullptr;

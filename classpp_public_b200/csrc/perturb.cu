@@ -1,9 +1,10 @@
 // Stage 1: per-wavenumber Einstein-Boltzmann integration on the device.
 //
-// One WARP integrates one k-mode from its initial time to today (one CTA = one warp, so the
-// hardware block scheduler is the work queue; modes are issued in decreasing-k order like the
-// reference's task loop, perturbations_module.cpp:685).  Everything of a mode lives in shared
-// memory: state vector, the NDF backward-difference array, the LU factors of (I - h/(G(1-alpha)) J).
+// One WARP integrates one (cosmology, k) mode from its initial time to today.  One CTA = one
+// warp, so the hardware block scheduler is the work queue; modes of all cosmologies of a batch
+// are issued in decreasing-cost order (longest chains first).  Everything of a mode lives in
+// shared memory (~190 B per equation + the hub inverse): the state vector, the NDF
+// backward-difference array and the factors of the Newton matrix (I - h/(G(1-alpha)) J).
 // Error norms / step control use warp-shuffle reductions; the approximation state machine
 // (tight coupling -> full hierarchy -> ur fluid / ncdm fluid -> radiation streaming) is per-mode
 // device state: switch times are bisected on the device and the state vector is re-laid-out in
@@ -17,39 +18,63 @@
 //   perturb_derivs_member :7861-9218, perturb_tca_slip_and_shear :9229-9516,
 //   perturb_rsa_delta_and_theta :9530-9636,
 //   evolver_ndf15 (tools/evolver_ndf15.cpp:62-705), adjust_stepsize :907-943,
-//   interp_from_dif :860-905, new_linearisation :945-998, ludcmp/lubksb :1001-1064.
+//   interp_from_dif :860-905, new_linearisation :945-998.
 //
-// Differences of method (not of result): the Jacobian is assembled column by column from
-// f(t, e_j) -- the system is linear and homogeneous in y, so this equals the reference's
-// finite-difference numjac (:1213-1539) up to its O(1e-8) truncation noise -- and the linear
-// algebra is a dense warp-parallel LU in shared memory instead of the CPU's sparse LU.
+// Differences of METHOD (not of result) from the reference:
+//  * Linear algebra.  The reference discovers the sparsity of J numerically and runs a generic
+//    sparse LU (tools/sparse.c).  Here the structure of the Boltzmann hierarchy is used directly:
+//    every multipole l >= 3 of a hierarchy (photon temperature, photon polarisation, ur, each
+//    ncdm momentum bin) couples only to l-1 and l+1, so the state splits into CHAINS
+//    (tridiagonal, rooted at their l = 2 moment) and a small dense HUB block (everything else:
+//    densities, velocities, shears, eta; 7..28 variables).  (I - cJ) is factorised exactly as
+//    chains -> Schur complement on the hub -> explicit hub inverse (Gauss-Jordan with partial
+//    pivoting); the chain eliminations need no pivoting (all pivots >= 1).
+//    A solve is two chain sweeps (one lane per chain) + one hub mat-vec (one lane per row).
+//  * Jacobian.  The system is linear and homogeneous in y, so J's columns are f(t, e_j) exactly;
+//    hub columns are probed one by one and all chain entries with 3 grouped probes
+//    (l mod 3), instead of the reference's finite-difference numjac (:1213-1539).
+//  * Background/thermodynamics lookups keep the current table interval in registers (one
+//    column per lane) and only touch memory when the interval changes.
+#include <algorithm>
 #include <cmath>
+#include <vector>
 
 #include "device.h"
 
 #define PT_MAX_NCDM 3
 #define PT_MAX_INTERVALS 6
+#define PT_MAX_CHAINS 32
 #define PT_FULL 0xffffffffu
 
 // ---------------------------------------------------------------------------------------------
-struct PtParams {
-  // tables
+// per-cosmology inputs (global memory, one entry per context of the batch)
+struct PtCosmo {
   const double *bg_tau, *bg_y, *bg_dd;
-  int bt_size, bg_size, bg_size_normal;
   const double *th_z, *th_y, *th_dd;
-  int tt_size, th_size;
+  const double *ncdm_q, *ncdm_w, *ncdm_dlnf0;
+  const double *k, *tau;
+  double* sources;  // [tp][k][tau]
+  clpp_kstat* kstat;
+  int bt_size, tt_size, k_size, tau_size;
+  double th_linear_below_z;  // < 0: never use linear interpolation
+  double n_e, YHe, T_cmb, tau_free_streaming, a_today;
+  double ncdm_M[PT_MAX_NCDM], ncdm_factor[PT_MAX_NCDM];
+};
+
+// settings common to every cosmology of a batch (kernel parameter -> constant bank)
+struct PtParams {
+  const PtCosmo* cosmo;
+  const int2* modes;  // (cosmology index, k index), decreasing expected cost
+  int n_modes;
+  double* hub_jac;  // per-CTA global scratch [nh_max*nh_max]: hub block of the Jacobian
+  int bg_size, bg_size_normal, th_size;
   // background column indices
   int ia, iH, iHp, irho_g, irho_b, irho_cdm, irho_ur, irho_ncdm1, ip_ncdm1, ipseudo_p_ncdm1;
   // thermo column indices
   int ixe, idkappa, iddkappa, idddkappa, iexp_m_kappa, ig, idg, iddg, icb2, iwb, iTb, itau_d, irate, ir_d, idcb2, iddcb2;
   int compute_cb2_derivatives, compute_damping_scale;
-  double th_linear_below_z;  // < 0: never use linear interpolation
-  double n_e, YHe, T_cmb, tau_free_streaming;
   int has_ur, has_ncdm, N_ncdm;
-  int ncdm_q_size[PT_MAX_NCDM], ncdm_q_off[PT_MAX_NCDM];
-  double ncdm_M[PT_MAX_NCDM], ncdm_factor[PT_MAX_NCDM];
-  const double *ncdm_q, *ncdm_w, *ncdm_dlnf0;
-  double a_today;
+  int ncdm_q_size[PT_MAX_NCDM], ncdm_q_off[PT_MAX_NCDM], nq_tot;
   // precision
   double start_small_k_at_tau_c_over_tau_h, start_large_k_at_tau_h_over_tau_k;
   double tca_trigger_tau_c_over_tau_h, tca_trigger_tau_c_over_tau_k;
@@ -60,20 +85,38 @@ struct PtParams {
   double curvature_ini, three_ceff2_ur, three_cvis2_ur;
   int switch_sw, switch_eisw, switch_lisw, switch_dop, switch_pol;
   double eisw_lisw_split_z;
-  // grids / output
-  const double* k;
-  int k_size;
-  const double* tau;
-  int tau_size;
-  double* sources;  // [tp][k][tau]
   int tp_t0, tp_t1, tp_t2, tp_p, tp_delta_m, tp_delta_cb, tp_phi_plus_psi;
-  const int* order;
-  int n_modes;
-  clpp_kstat* kstat;
-  // per-slot scratch in global memory (Jacobian), indexed by blockIdx
-  double* jac;
-  int neq_max, ld;  // ld: odd leading dimension of the LU matrix in shared memory
+  // shared-memory geometry (offsets in doubles into the CTA's dynamic shared memory)
+  int neq_max, np, nh_max, ldh;
+  int o_mode, o_hubtmp, o_nw, o_i2l1, n_i2l1, o_vec, o_sinv, o_int;
 };
+
+extern __shared__ double smem[];
+// every shared-memory access goes through these, so that the compiler sees the shared address
+// space (LDS/STS with 32-bit addresses) instead of generic pointers
+#define s_pvb(P) (smem)
+#define s_pvt(P) (smem + 32)
+#define s_hubtmp(P) (smem + (P).o_hubtmp)
+#define s_nw(P) (smem + (P).o_nw)
+#define s_vec(P, slot) (smem + ((P).o_vec + (slot) * (P).np))
+#define s_sinv(P) (smem + (P).o_sinv)
+#define s_i2l1(P) (smem + (P).o_i2l1)
+#define s_hub_idx(P) ((int*)(smem + (P).o_int))
+#define s_piv(P) ((int*)(smem + (P).o_int) + (P).nh_max)
+#define s_ch_start(P) ((int*)(smem + (P).o_int) + 2 * (P).nh_max)
+#define s_ch_len(P) ((int*)(smem + (P).o_int) + 2 * (P).nh_max + PT_MAX_CHAINS)
+#define s_ch_rootslot(P) ((int*)(smem + (P).o_int) + 2 * (P).nh_max + 2 * PT_MAX_CHAINS)
+
+// NDF constants (evolver_ndf15.cpp:86-100), indexed by order-1
+__constant__ double c_G[5] = {1.0, 3.0 / 2.0, 11.0 / 6.0, 25.0 / 12.0, 137.0 / 60.0};
+__constant__ double c_invGa[5] = {1.0 / (1.0 * (1.0 + 37.0 / 200)), 1.0 / (1.5 * (1.0 + 1.0 / 9.0)),
+                                  1.0 / (11.0 / 6.0 * (1.0 + 8.23e-2)), 1.0 / (25.0 / 12.0 * (1.0 + 4.15e-2)),
+                                  1.0 / (137.0 / 60.0)};
+__constant__ double c_erconst[5] = {-37.0 / 200 * 1.0 + 1.0 / 2.0, -1.0 / 9.0 * 1.5 + 1.0 / 3.0,
+                                    -8.23e-2 * (11.0 / 6.0) + 1.0 / 4.0, -4.15e-2 * (25.0 / 12.0) + 1.0 / 5.0,
+                                    1.0 / 6.0};
+// difference-array rescaling matrix U (evolver_ndf15.cpp:907-943)
+__constant__ double c_U[5][5] = {{-1, -2, -3, -4, -5}, {0, 1, 3, 6, 10}, {0, 0, -1, -4, -10}, {0, 0, 0, 1, 5}, {0, 0, 0, 0, -1}};
 
 struct Approx {
   int tca_off, rsa_on, ufa_on, ncdmfa_on;  // monotone flags (0 -> 1 in time)
@@ -86,23 +129,31 @@ struct Layout {
   int delta_ur, theta_ur, shear_ur, l3_ur;
   int psi0_ncdm1;
   int eta;
-  int l_max_g, l_max_pol_g, l_max_ur;
   int l_max_ncdm, q_size_ncdm[PT_MAX_NCDM], ncdm_off[PT_MAX_NCDM];
 };
 
-// background + thermodynamics + derived metric quantities at the current time; identical in
-// all lanes (kept in registers)
+// background + thermodynamics at the current time; identical in all lanes
 struct Env {
   double tau, a, H, Hp, rho_g, rho_b, rho_cdm, rho_ur;
   double dkappa, ddkappa, exp_m_kappa, g, dg, cb2;
+  // derived, hoisted out of the RHS: a^2, aH, R = 4 rho_g / 3 rho_b, reciprocals, (a_today/a)^4
+  double a2, aH, R, inv_R, inv_1pR, inv_half_aH, inv_tau, tau_c, fac_ncdm;
 };
 
 struct Metric {
-  double h_prime, eta_prime, alpha, alpha_prime, h_prime_prime;
-  double delta_rho, rho_plus_p_theta, rho_plus_p_shear, delta_p;
-  double rsa_delta_g, rsa_theta_g, rsa_delta_ur, rsa_theta_ur;
-  double delta_m, theta_m, delta_cb, theta_cb;
-  double tca_shear_g, tca_slip;
+  double h_prime, eta_prime, alpha, alpha_prime;
+  double rsa_delta_g, rsa_theta_g;
+  double delta_m, delta_cb;
+  double tca_shear_g;
+};
+
+// vector slots in shared memory (each np doubles)
+enum {
+  V_Y = 0, V_YNEW, V_F0, V_PRED, V_PSI, V_DIFKP1, V_DEL, V_INVWT, V_TMP, V_YPI,
+  V_DIF0,  // 7 slots: dif[0..6]
+  V_JD = V_DIF0 + 7, V_JL, V_JU,  // chain rows of J: diagonal, sub-diagonal J[i,i-1], super-diagonal J[i,i+1]
+  V_IP, V_MU, V_LO,               // chain factors: 1/pivot, T[i,i+1]/p[i+1], T[i,i-1]
+  V_COUNT
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -116,88 +167,132 @@ __device__ __forceinline__ double wsum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PT_FULL, v, o);
   return v;
 }
+// x^(1/n), x > 0 (step-size heuristics; the reference calls pow)
+__device__ __forceinline__ double root_n(double x, double n) { return exp(log(x) / n); }
 
-// bracket x in a growing array: closeby (cursor) or bisection; returns inf with X[inf] <= x <= X[inf+1]
-__device__ __forceinline__ int table_locate(const double* __restrict__ X, int n, double x, int cursor, bool closeby) {
-  int inf, sup;
-  if (closeby) {
-    inf = min(max(cursor, 0), n - 2);
-    while (inf > 0 && x < X[inf]) inf--;
-    sup = inf + 1;
-    while (sup < n - 1 && x > X[sup]) sup++;
-    inf = sup - 1;
-  } else {
-    inf = 0;
-    sup = n - 1;
-    while (sup - inf > 1) {
-      const int mid = (int)(0.5 * (inf + sup));
-      if (x < X[mid]) sup = mid; else inf = mid;
-    }
+// largest index inf <= n-2 with X[inf] <= x (X growing): 32-ary search, one probe per lane
+__device__ __forceinline__ int locate_warp(const double* __restrict__ X, int n, double x, int lane) {
+  int lo = 0, hi = n - 1;
+  while (hi - lo > 1) {
+    const int step = (hi - lo + 31) >> 5;
+    const int idx = lo + (lane + 1) * step;
+    const bool ge = (idx < hi) && (x >= __ldg(X + idx));
+    const int c = __popc(__ballot_sync(PT_FULL, ge));
+    hi = min(lo + (c + 1) * step, hi);
+    lo = lo + c * step;
   }
-  return inf;
+  return lo;
+}
+// cursor walk (array_interpolate_spline_growing_closeby, arrays.c:2173-2232), falling back to the
+// warp search when the target is far
+__device__ __forceinline__ int locate_closeby(const double* __restrict__ X, int n, double x, int cursor, int lane) {
+  int inf = min(max(cursor, 0), n - 2);
+  int guard = 0;
+  while (inf > 0 && x < __ldg(X + inf)) {
+    inf--;
+    if (++guard > 6) return locate_warp(X, n, x, lane);
+  }
+  int sup = inf + 1;
+  while (sup < n - 1 && x > __ldg(X + sup)) {
+    sup++;
+    if (++guard > 6) return locate_warp(X, n, x, lane);
+  }
+  return sup - 1;
 }
 
+// optional section profiler (cycles per code section, summed over the mode's lifetime)
+#ifdef PT_PROF
+#define PROF_DECL long long prof_t0_
+#define PROF_BEGIN() (prof_t0_ = clock64())
+#define PROF_END(slot) do { if (threadIdx.x == 0) M.prof[slot] += clock64() - prof_t0_; } while (0)
+#else
+#define PROF_DECL
+#define PROF_BEGIN()
+#define PROF_END(slot)
+#endif
+enum { PF_ENV = 0, PF_RHS, PF_SOLVE, PF_PREDICT, PF_UPDATE, PF_CONTROL, PF_FACTOR, PF_ADJUST, PF_OUTPUT, PF_JAC, PF_DIFUPD, PF_COUNT };
+
+// per-mode statistics (copied to the public clpp_kstat at the end)
+struct Stat {
+  int steps, failed, fevals, jacobians, factorizations, solves, intervals, status;
+  double tau_ini;
+};
+
+// State of the mode a warp integrates.  It lives in SHARED memory (one per CTA = warp): every
+// field is warp-uniform except the table caches, which hold one column per lane.  Keeping it out
+// of local memory matters: with several warps per SM the per-thread stack frames thrash the L1.
 struct Mode {
-  // shared-memory views of this warp
-  double *pvb, *pvt;
-  double *y, *ynew, *f0, *pred, *psi, *difkp1, *del, *invwt, *tmp, *yi, *ypi;
-  double* dif;  // [7][neq_pad]
-  double* LU;   // [neq][ld] column-major: LU[i + j*ld]
-  int* piv;
-  double* J;    // global scratch [neq][neq] column-major
-  int neq_pad;
-  // mode state
-  double k, k2;
-  int ik, lane;
-  int cur_bg, cur_th;
-  Approx ap;
-  Layout L;
+  const PtCosmo* C;
+  double* Jhh;  // global scratch [nh][nh], column-major: Jhh[i + j*nh] = J[hub i, hub j]
+  double k, k2, inv_k, inv_k2;
+  double nf[PT_MAX_NCDM][8];  // ncdm fluid constants at the current time (env_at)
+  // cached table intervals: entry [.][c] holds column c of the two bracketing rows (y0, y1, dd0, dd1)
+  double bx0, bx1, tx0, tx1;
+  double bc[4][32], tc[4][32];
   Env e;
   Metric m;
   double tca_shear_last;  // photon shear of the last Newton-iteration RHS call (used by the sources while TCA is on)
-  clpp_kstat st;
-  int status;
+  double limit[PT_MAX_INTERVALS + 1];
+  double sw[4];
+  long long prof[PF_COUNT];
+  Approx sched[PT_MAX_INTERVALS];
+  Approx ap, apprev;
+  Layout L, Lprev;
+  Stat st;
+  int ik, cur_bg, cur_th, need_nw, nh, nch, status, next;
 };
+#define MODE(P) (*(Mode*)(smem + (P).o_mode))
 
 // ---------------------------------------------------------------------------------------------
 // background_at_tau (normal_info columns) + thermodynamics_at_z, cooperative over lanes
-__device__ void env_at(const PtParams& P, Mode& M, double tau, bool closeby) {
-  const int lane = M.lane;
+__device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby) {
+  Mode& M = MODE(P);
+  const PtCosmo* __restrict__ C = M.C;
+  const int lane = (int)threadIdx.x;
   // background
-  {
-    const int inf = table_locate(P.bg_tau, P.bt_size, tau, M.cur_bg, closeby);
+  if (!(tau >= M.bx0 && tau <= M.bx1)) {
+    const double* X = C->bg_tau;
+    const int n = C->bt_size;
+    const int inf = closeby ? locate_closeby(X, n, tau, M.cur_bg, lane) : locate_warp(X, n, tau, lane);
     M.cur_bg = inf;
-    const double x0 = P.bg_tau[inf], x1 = P.bg_tau[inf + 1];
-    const double h = x1 - x0, b = (tau - x0) / h, a = 1 - b;
+    M.bx0 = __ldg(X + inf);
+    M.bx1 = __ldg(X + inf + 1);
     if (lane < P.bg_size_normal) {
       const size_t r0 = (size_t)inf * P.bg_size + lane, r1 = r0 + P.bg_size;
-      M.pvb[lane] = a * P.bg_y[r0] + b * P.bg_y[r1] +
-                    ((a * a * a - a) * P.bg_dd[r0] + (b * b * b - b) * P.bg_dd[r1]) * h * h / 6.;
+      M.bc[0][lane] = __ldg(C->bg_y + r0); M.bc[1][lane] = __ldg(C->bg_y + r1);
+      M.bc[2][lane] = __ldg(C->bg_dd + r0); M.bc[3][lane] = __ldg(C->bg_dd + r1);
     }
   }
+  {
+    const double h = M.bx1 - M.bx0, b = (tau - M.bx0) / h, a = 1 - b;
+    if (lane < P.bg_size_normal)
+      s_pvb(P)[lane] = a * M.bc[0][lane] + b * M.bc[1][lane] + ((a * a * a - a) * M.bc[2][lane] + (b * b * b - b) * M.bc[3][lane]) * h * h / 6.;
+  }
   __syncwarp();
-  const double av = M.pvb[P.ia], Hv = M.pvb[P.iH], Hp = M.pvb[P.iHp];
+  const double av = s_pvb(P)[P.ia], Hv = s_pvb(P)[P.iH], Hp = s_pvb(P)[P.iHp];
   const double z = 1. / av - 1.;
   // thermodynamics
-  const double z_last = P.th_z[P.tt_size - 1];
+  const int ntt = C->tt_size;
+  const double z_last = __ldg(C->th_z + ntt - 1);
   if (z >= z_last) {
     if (lane == 0) {
-      const double* row = P.th_y + (size_t)(P.tt_size - 1) * P.th_size;
+      const double* row = C->th_y + (size_t)(ntt - 1) * P.th_size;
       const double x0 = row[P.ixe];
-      double* pv = M.pvt;
+      double* pv = s_pvt(P);
+      const double r = (1. + z) / (1. + z_last);
       pv[P.ixe] = x0;
-      pv[P.idkappa] = (1. + z) * (1. + z) * P.n_e * x0 * CLPP_sigma * CLPP_Mpc_over_m;
-      pv[P.itau_d] = row[P.itau_d] * pow((1 + z) / (1. + z_last), 2);
-      if (P.compute_damping_scale) pv[P.ir_d] = row[P.ir_d] * pow((1 + z) / (1. + z_last), -1.5);
+      pv[P.idkappa] = (1. + z) * (1. + z) * C->n_e * x0 * CLPP_sigma * CLPP_Mpc_over_m;
+      pv[P.itau_d] = row[P.itau_d] * r * r;
+      if (P.compute_damping_scale) pv[P.ir_d] = row[P.ir_d] / (r * sqrt(r));
       pv[P.iddkappa] = -Hv * 2. / (1. + z) * pv[P.idkappa];
       pv[P.idddkappa] = (Hv * Hv / (1. + z) - Hp) * 2. / (1. + z) * pv[P.idkappa];
       pv[P.iexp_m_kappa] = 0.;
       pv[P.ig] = 0.;
       pv[P.idg] = 0.;
       pv[P.iddg] = 0.;
-      pv[P.iTb] = P.T_cmb * (1. + z);
-      pv[P.iwb] = CLPP_k_B / (CLPP_c * CLPP_c * CLPP_m_H) * (1. + (1. / CLPP_not4 - 1.) * P.YHe + x0 * (1. - P.YHe)) *
-                  P.T_cmb * (1. + z);
+      pv[P.iTb] = C->T_cmb * (1. + z);
+      pv[P.iwb] = CLPP_k_B / (CLPP_c * CLPP_c * CLPP_m_H) * (1. + (1. / CLPP_not4 - 1.) * C->YHe + x0 * (1. - C->YHe)) *
+                  C->T_cmb * (1. + z);
       pv[P.icb2] = pv[P.iwb] * 4. / 3.;
       if (P.compute_cb2_derivatives) {
         pv[P.idcb2] = -Hv * av * pv[P.icb2];
@@ -206,32 +301,88 @@ __device__ void env_at(const PtParams& P, Mode& M, double tau, bool closeby) {
       pv[P.irate] = pv[P.idkappa];
     }
   } else {
-    const bool linear = (z < P.th_linear_below_z);
-    const int inf = table_locate(P.th_z, P.tt_size, z, M.cur_th, closeby && !linear);
-    M.cur_th = inf;
-    const double x0 = P.th_z[inf], x1 = P.th_z[inf + 1];
-    const double h = x1 - x0, b = (z - x0) / h, a = 1 - b;
+    const bool linear = (z < C->th_linear_below_z);
+    if (!(z >= M.tx0 && z <= M.tx1)) {
+      const double* X = C->th_z;
+      const int inf = (closeby && !linear) ? locate_closeby(X, ntt, z, M.cur_th, lane) : locate_warp(X, ntt, z, lane);
+      M.cur_th = inf;
+      M.tx0 = __ldg(X + inf);
+      M.tx1 = __ldg(X + inf + 1);
+      if (lane < P.th_size) {
+        const size_t r0 = (size_t)inf * P.th_size + lane, r1 = r0 + P.th_size;
+        M.tc[0][lane] = __ldg(C->th_y + r0); M.tc[1][lane] = __ldg(C->th_y + r1);
+        M.tc[2][lane] = __ldg(C->th_dd + r0); M.tc[3][lane] = __ldg(C->th_dd + r1);
+      }
+    }
+    const double h = M.tx1 - M.tx0, b = (z - M.tx0) / h, a = 1 - b;
     if (lane < P.th_size) {
-      const size_t r0 = (size_t)inf * P.th_size + lane, r1 = r0 + P.th_size;
-      double v = a * P.th_y[r0] + b * P.th_y[r1];
-      if (!linear) v += ((a * a * a - a) * P.th_dd[r0] + (b * b * b - b) * P.th_dd[r1]) * h * h / 6.;
-      M.pvt[lane] = v;
+      double v = a * M.tc[0][lane] + b * M.tc[1][lane];
+      if (!linear) v += ((a * a * a - a) * M.tc[2][lane] + (b * b * b - b) * M.tc[3][lane]) * h * h / 6.;
+      s_pvt(P)[lane] = v;
     }
   }
+  // momentum-dependent ncdm weights at this scale factor (used by the RHS while the ncdm hierarchy is integrated)
+  if (M.need_nw) {
+    const double a2 = av * av;
+    const int nq = P.nq_tot;
+    for (int j = lane; j < nq; j += 32) {
+      int s = 0;
+#pragma unroll
+      for (int t = 1; t < PT_MAX_NCDM; t++)
+        if (t < P.N_ncdm && j >= P.ncdm_q_off[t]) s = t;
+      const double Ms = C->ncdm_M[s];
+      const double q = __ldg(C->ncdm_q + j), w0 = __ldg(C->ncdm_w + j);
+      const double q2 = q * q, eps = sqrt(q2 + Ms * Ms * a2);
+      s_nw(P)[j] = q / eps;
+      s_nw(P)[nq + j] = q2 * eps * w0;
+      s_nw(P)[2 * nq + j] = q2 * q * w0;
+      s_nw(P)[3 * nq + j] = q2 * q2 / eps * w0;
+    }
+  }
+  // ncdm fluid constants (perturb_derivs_member :8800-8850, perturb_total_stress_energy :6380-6400)
+  if (P.has_ncdm && M.ap.ncdmfa_on && lane < P.N_ncdm) {
+    const int s = lane;
+    const double* pvb = s_pvb(P);
+    const double rho_n = pvb[P.irho_ncdm1 + s], p_n = pvb[P.ip_ncdm1 + s], pseudo_p = pvb[P.ipseudo_p_ncdm1 + s];
+    const double aH = Hv * av;
+    const double pseudo_p_over_p = pseudo_p / p_n;
+    const double w_n = p_n / rho_n;
+    const double cg2 = w_n * (1.0 - 1.0 / (3.0 + 3.0 * w_n) * (3.0 * w_n - 2.0 + pseudo_p_over_p));
+    const double ca2 = w_n / 3.0 / (1.0 + w_n) * (5.0 - pseudo_p_over_p);
+    const double cvis2 = (P.ncdmfa_method == CLPP_NCDMFA_HU) ? w_n : 3. * w_n * ca2;
+    double* nf = M.nf[s];
+    nf[0] = rho_n; nf[1] = rho_n + p_n; nf[2] = w_n; nf[3] = cg2 * rho_n; nf[4] = ca2;
+    nf[5] = ca2 / (1.0 + w_n);
+    nf[6] = 8.0 / 3.0 * cvis2 / (1.0 + w_n);
+    nf[7] = (P.ncdmfa_method == CLPP_NCDMFA_HU) ? 3.0 * aH * ca2 / w_n
+                                                : 3.0 * (aH * (2. / 3. - ca2 - pseudo_p_over_p / 3.) + 1. / tau);
+  }
+  if (lane == 0) {
+    Env& e = M.e;
+    const double* pvb = s_pvb(P);
+    const double* pvt = s_pvt(P);
+    e.tau = tau;
+    e.a = av; e.H = Hv; e.Hp = Hp;
+    const double rho_g = pvb[P.irho_g], rho_b = pvb[P.irho_b], dkappa = pvt[P.idkappa];
+    e.rho_g = rho_g; e.rho_b = rho_b; e.rho_cdm = pvb[P.irho_cdm];
+    e.rho_ur = P.has_ur ? pvb[P.irho_ur] : 0.;
+    e.dkappa = dkappa; e.ddkappa = pvt[P.iddkappa];
+    e.exp_m_kappa = pvt[P.iexp_m_kappa]; e.g = pvt[P.ig]; e.dg = pvt[P.idg];
+    e.cb2 = pvt[P.icb2];
+    const double aH = Hv * av, R = 4. / 3. * rho_g / rho_b;
+    e.a2 = av * av; e.aH = aH; e.R = R;
+    e.inv_R = 1.0 / R; e.inv_1pR = 1.0 / (1.0 + R); e.inv_half_aH = 1.0 / (0.5 * aH);
+    e.inv_tau = 1.0 / tau; e.tau_c = 1.0 / dkappa;
+    const double a_rel = C->a_today / av;
+    e.fac_ncdm = (a_rel * a_rel) * (a_rel * a_rel);
+  }
   __syncwarp();
-  Env& e = M.e;
-  e.tau = tau;
-  e.a = av; e.H = Hv; e.Hp = Hp;
-  e.rho_g = M.pvb[P.irho_g]; e.rho_b = M.pvb[P.irho_b]; e.rho_cdm = M.pvb[P.irho_cdm];
-  e.rho_ur = P.has_ur ? M.pvb[P.irho_ur] : 0.;
-  e.dkappa = M.pvt[P.idkappa]; e.ddkappa = M.pvt[P.iddkappa];
-  e.exp_m_kappa = M.pvt[P.iexp_m_kappa]; e.g = M.pvt[P.ig]; e.dg = M.pvt[P.idg];
-  e.cb2 = M.pvt[P.icb2];
 }
 
 // perturb_approximations: flags at time tau (uses bisection lookups, inter_normal)
-__device__ Approx approximations_at(const PtParams& P, Mode& M, double tau) {
-  env_at(P, M, tau, false);
+__device__ __noinline__ Approx approximations_at(const PtParams& P, double tau) {
+  Mode& M = MODE(P);
+  env_at(P, tau, false);
   const Env& e = M.e;
   Approx a;
   const double tau_k = 1. / M.k, tau_h = 1. / (e.H * e.a);
@@ -240,7 +391,7 @@ __device__ Approx approximations_at(const PtParams& P, Mode& M, double tau) {
     const double tau_c = 1. / e.dkappa;
     a.tca_off = ((tau_c / tau_h < P.tca_trigger_tau_c_over_tau_h) && (tau_c / tau_k < P.tca_trigger_tau_c_over_tau_k)) ? 0 : 1;
   }
-  a.rsa_on = ((tau / tau_k > P.rsa_trigger) && (tau > P.tau_free_streaming) && (P.rsa_method != CLPP_RSA_NONE)) ? 1 : 0;
+  a.rsa_on = ((tau / tau_k > P.rsa_trigger) && (tau > M.C->tau_free_streaming) && (P.rsa_method != CLPP_RSA_NONE)) ? 1 : 0;
   a.ufa_on = (P.has_ur && (tau / tau_k > P.ufa_trigger) && (P.ufa_method != CLPP_UFA_NONE)) ? 1 : 0;
   a.ncdmfa_on = (P.has_ncdm && (tau / tau_k > P.ncdmfa_trigger) && (P.ncdmfa_method != CLPP_NCDMFA_NONE)) ? 1 : 0;
   return a;
@@ -251,13 +402,11 @@ __device__ __forceinline__ int approx_flag(const Approx& a, int which) {
 }
 
 // perturb_vector_init (index part): layout of the state vector for a set of approximations
-__device__ Layout make_layout(const PtParams& P, const Approx& ap) {
-  Layout L;
+__device__ __forceinline__ void make_layout(const PtParams& P, const Approx& ap, Layout& L) {
   int n = 0;
   L.delta_g = L.theta_g = L.shear_g = L.l3_g = L.pol0_g = -1;
   L.delta_ur = L.theta_ur = L.shear_ur = L.l3_ur = -1;
   L.psi0_ncdm1 = -1;
-  L.l_max_g = P.l_max_g; L.l_max_pol_g = P.l_max_pol_g; L.l_max_ur = P.l_max_ur;
   if (!ap.rsa_on) {
     L.delta_g = n++;
     L.theta_g = n++;
@@ -277,129 +426,191 @@ __device__ Layout make_layout(const PtParams& P, const Approx& ap) {
     if (!ap.ufa_on) { L.l3_ur = n; n += P.l_max_ur - 2; }
   }
   L.l_max_ncdm = 0;
+#pragma unroll
+  for (int s = 0; s < PT_MAX_NCDM; s++) { L.q_size_ncdm[s] = 0; L.ncdm_off[s] = 0; }
   if (P.has_ncdm) {
     L.psi0_ncdm1 = n;
     L.l_max_ncdm = ap.ncdmfa_on ? 2 : P.l_max_ncdm;
-    for (int s = 0; s < P.N_ncdm; s++) {
-      L.q_size_ncdm[s] = ap.ncdmfa_on ? 1 : P.ncdm_q_size[s];
-      L.ncdm_off[s] = n;
-      n += (L.l_max_ncdm + 1) * L.q_size_ncdm[s];
+#pragma unroll
+    for (int s = 0; s < PT_MAX_NCDM; s++) {
+      if (s < P.N_ncdm) {
+        L.q_size_ncdm[s] = ap.ncdmfa_on ? 1 : P.ncdm_q_size[s];
+        L.ncdm_off[s] = n;
+        n += (L.l_max_ncdm + 1) * L.q_size_ncdm[s];
+      }
     }
   }
   L.eta = n++;
   L.neq = n;
-  return L;
+}
+
+// Split the state of the current layout into chains (multipoles l >= 3 of each hierarchy, rooted at
+// their l = 2 moment, which sits right before them in the state vector) and hub variables.
+__device__ __noinline__ void make_structure(const PtParams& P) {
+  Mode& M = MODE(P);
+  const Layout& L = M.L;
+  const Approx& ap = M.ap;
+  if ((int)threadIdx.x == 0) {
+    int nch = 0;
+    if (L.l3_g >= 0) {
+      s_ch_start(P)[nch] = L.l3_g; s_ch_len(P)[nch] = P.l_max_g - 2; nch++;
+      s_ch_start(P)[nch] = L.pol0_g + 3; s_ch_len(P)[nch] = P.l_max_pol_g - 2; nch++;
+    }
+    if (L.l3_ur >= 0) { s_ch_start(P)[nch] = L.l3_ur; s_ch_len(P)[nch] = P.l_max_ur - 2; nch++; }
+    if (P.has_ncdm && !ap.ncdmfa_on) {
+      const int stride = L.l_max_ncdm + 1;
+      const int nq = (L.eta - L.psi0_ncdm1) / stride;
+      for (int iq = 0; iq < nq; iq++) {
+        s_ch_start(P)[nch] = L.psi0_ncdm1 + iq * stride + 3; s_ch_len(P)[nch] = L.l_max_ncdm - 2; nch++;
+      }
+    }
+    // hub variables: everything that is not a chain interior (chains are sorted by start)
+    int nh = 0, c = 0;
+    for (int i = 0; i < L.neq; i++) {
+      while (c < nch && i >= s_ch_start(P)[c] + s_ch_len(P)[c]) c++;
+      if (c < nch && i >= s_ch_start(P)[c]) continue;
+      s_hub_idx(P)[nh++] = i;
+    }
+    // hub slot of each chain root
+    for (int cc = 0, s = 0; cc < nch; cc++) {
+      while (s_hub_idx(P)[s] != s_ch_start(P)[cc] - 1) s++;
+      s_ch_rootslot(P)[cc] = s;
+    }
+    s_piv(P)[0] = nh;
+    s_piv(P)[1] = nch;
+  }
+  __syncwarp();
+  M.nh = s_piv(P)[0];
+  M.nch = s_piv(P)[1];
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
-// Right-hand side f(tau, y) for the environment currently stored in M.e/M.pvb/M.pvt.
-// Also fills M.m (metric and derived quantities) for the caller.
-template <bool WANT_MATTER>
-__device__ void rhs_apply(const PtParams& P, Mode& M, const double* __restrict__ y, double* __restrict__ dy) {
+// Right-hand side f(tau, y) for the environment currently stored in M.e/pvb/pvt (one out-of-line
+// copy shared by the Newton loop, the Jacobian probes and the source output: the instruction
+// cache is the scarce resource of this kernel).  Also fills M.m (metric and derived quantities).
+// All lanes evaluate the scalar (hub) equations redundantly from broadcast shared-memory loads --
+// straight-line code without lane-divergent sections -- and the multipole chains are evaluated one
+// element per lane.  Every division by a quantity that only depends on time or on k is hoisted into
+// env_at / the mode set-up (reciprocals in M.e, M.ik2).
+__device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_dy, int want_matter) {
+  Mode& M = MODE(P);
+  const double* __restrict__ y = s_vec(P, slot_y);
+  double* __restrict__ dy = slot_dy >= 0 ? s_vec(P, slot_dy) : nullptr;
   const Layout& L = M.L;
-  const Approx& ap = M.ap;
+  const Approx ap = M.ap;
   const Env& e = M.e;
-  const int lane = M.lane;
-  const double k = M.k, k2 = M.k2;
-  const double a = e.a, a2 = a * a, aH = e.H * a;
-  const double R = 4. / 3. * e.rho_g / e.rho_b;
+  const int lane = threadIdx.x;
+  const double k = M.k, k2 = M.k2, ik2 = M.inv_k2;
+  const double a2 = e.a2, aH = e.aH, R = e.R;
   Metric& m = M.m;
+  const bool has_g = !ap.rsa_on;
+  const bool has_ur = P.has_ur && !ap.rsa_on;
+  const bool full_g = has_g && ap.tca_off;
+  const double* pvb = s_pvb(P);
 
-  // ---- perturb_total_stress_energy
+  // ---- loads of every hub value (independent, issued up front)
   double delta_g = 0., theta_g = 0., shear_g = 0.;
-  if (ap.tca_off) {
-    if (!ap.rsa_on) { delta_g = y[L.delta_g]; theta_g = y[L.theta_g]; shear_g = y[L.shear_g]; }
-  } else {
-    delta_g = y[L.delta_g]; theta_g = y[L.theta_g]; shear_g = 0.;
+  if (has_g) { delta_g = y[L.delta_g]; theta_g = y[L.theta_g]; }
+  double g3 = 0., g4 = 0., p0 = 0., p1 = 0., p2 = 0., p3 = 0.;
+  if (full_g) {
+    shear_g = y[L.shear_g]; g3 = y[L.l3_g]; g4 = y[L.l3_g + 1];
+    p0 = y[L.pol0_g]; p1 = y[L.pol0_g + 1]; p2 = y[L.pol0_g + 2]; p3 = y[L.pol0_g + 3];
   }
-  double delta_ur = 0., theta_ur = 0., shear_ur = 0.;
-  if (P.has_ur && !ap.rsa_on) { delta_ur = y[L.delta_ur]; theta_ur = y[L.theta_ur]; shear_ur = y[L.shear_ur]; }
+  double delta_ur = 0., theta_ur = 0., shear_ur = 0., u3 = 0., u4 = 0.;
+  if (has_ur) {
+    delta_ur = y[L.delta_ur]; theta_ur = y[L.theta_ur]; shear_ur = y[L.shear_ur];
+    if (!ap.ufa_on) { u3 = y[L.l3_ur]; u4 = y[L.l3_ur + 1]; }
+  }
   const double delta_b = y[L.delta_b], theta_b = y[L.theta_b], delta_cdm = y[L.delta_cdm], eta = y[L.eta];
   const double delta_p_b_over_rho_b = e.cb2 * delta_b;
 
+  // ---- perturb_total_stress_energy
   double delta_rho = e.rho_g * delta_g + e.rho_b * delta_b;
   double rpt = 4. / 3. * e.rho_g * theta_g + e.rho_b * theta_b;
   double rps = 4. / 3. * e.rho_g * shear_g;
   double delta_p = 1. / 3. * e.rho_g * delta_g + e.rho_b * delta_p_b_over_rho_b;
-  double delta_rho_m = 0., rho_m = 0., rpt_m = 0., rpm = 0.;
-  if (WANT_MATTER) {
-    delta_rho_m = e.rho_b * delta_b; rho_m = e.rho_b;
-    rpt_m = e.rho_b * theta_b; rpm = e.rho_b;
-  }
+  double delta_rho_m = e.rho_b * delta_b, rho_m = e.rho_b, rpt_m = e.rho_b * theta_b, rpm = e.rho_b;
   delta_rho += e.rho_cdm * delta_cdm;
-  if (WANT_MATTER) { delta_rho_m += e.rho_cdm * delta_cdm; rho_m += e.rho_cdm; rpm += e.rho_cdm; }
+  delta_rho_m += e.rho_cdm * delta_cdm; rho_m += e.rho_cdm; rpm += e.rho_cdm;
   if (P.has_ur) {
     delta_rho = delta_rho + e.rho_ur * delta_ur;
     rpt = rpt + 4. / 3. * e.rho_ur * theta_ur;
     rps = rps + 4. / 3. * e.rho_ur * shear_ur;
     delta_p += 1. / 3. * e.rho_ur * delta_ur;
   }
-  if (WANT_MATTER) {
-    m.delta_cb = delta_rho_m / rho_m;
-    m.theta_cb = rpt_m / rpm;
-  }
+  if (want_matter) m.delta_cb = delta_rho_m / rho_m + 3. * aH * (rpt_m / rpm) * ik2;
   if (P.has_ncdm) {
-    for (int s = 0; s < P.N_ncdm; s++) {
-      const double rho_n = M.pvb[P.irho_ncdm1 + s], p_n = M.pvb[P.ip_ncdm1 + s];
-      double d_n, t_n;
-      if (ap.ncdmfa_on) {
-        const double pseudo_p = M.pvb[P.ipseudo_p_ncdm1 + s];
-        const double w_n = p_n / rho_n;
-        const double cg2 = w_n * (1.0 - 1.0 / (3.0 + 3.0 * w_n) * (3.0 * w_n - 2.0 + pseudo_p / p_n));
-        const int idx = L.ncdm_off[s];
-        d_n = y[idx]; t_n = y[idx + 1];
-        delta_rho += rho_n * y[idx];
-        rpt += (rho_n + p_n) * y[idx + 1];
-        rps += (rho_n + p_n) * y[idx + 2];
-        delta_p += cg2 * rho_n * y[idx];
-      } else {
-        const double factor = P.ncdm_factor[s] * pow(P.a_today / a, 4);
-        double s_rho = 0., s_theta = 0., s_shear = 0., s_p = 0.;
-        const int nq = L.q_size_ncdm[s], stride = L.l_max_ncdm + 1;
-        const double Ms = P.ncdm_M[s];
-        for (int iq = lane; iq < nq; iq += 32) {
-          const int idx = L.ncdm_off[s] + iq * stride;
-          const double q = P.ncdm_q[P.ncdm_q_off[s] + iq], w0 = P.ncdm_w[P.ncdm_q_off[s] + iq];
-          const double q2 = q * q, eps = sqrt(q2 + Ms * Ms * a2);
-          s_rho += q2 * eps * w0 * y[idx];
-          s_theta += q2 * q * w0 * y[idx + 1];
-          s_shear += q2 * q2 / eps * w0 * y[idx + 2];
-          s_p += q2 * q2 / eps * w0 * y[idx];
-        }
-        s_rho = wsum(s_rho) * factor;
-        s_theta = wsum(s_theta) * k * factor;
-        s_shear = wsum(s_shear) * 2.0 / 3.0 * factor;
-        s_p = wsum(s_p) * factor / 3.;
-        d_n = s_rho / rho_n;
-        t_n = s_theta / (rho_n + p_n);
-        delta_rho += s_rho; rpt += s_theta; rps += s_shear; delta_p += s_p;
+    if (ap.ncdmfa_on) {
+      for (int s = 0; s < P.N_ncdm; s++) {
+        const double* nf = M.nf[s];  // rho, rho+p, w, cg2*rho, ...
+        const int idx = L.psi0_ncdm1 + 3 * s;
+        const double y0 = y[idx], y1 = y[idx + 1], y2 = y[idx + 2];
+        delta_rho += nf[0] * y0;
+        rpt += nf[1] * y1;
+        rps += nf[1] * y2;
+        delta_p += nf[3] * y0;
+        delta_rho_m += nf[0] * y0; rho_m += nf[0];
+        rpt_m += nf[1] * y1; rpm += nf[1];
       }
-      if (WANT_MATTER) {
-        delta_rho_m += rho_n * d_n; rho_m += rho_n;
-        rpt_m += (rho_n + p_n) * t_n; rpm += (rho_n + p_n);
+    } else {
+      const int stride = L.l_max_ncdm + 1, nqt = P.nq_tot;
+      const double* w = s_nw(P);
+      for (int s = 0; s < P.N_ncdm; s++) {
+        const double rho_n = pvb[P.irho_ncdm1 + s], p_n = pvb[P.ip_ncdm1 + s];
+        const double factor = M.C->ncdm_factor[s] * e.fac_ncdm;
+        double s_rho = 0., s_theta = 0., s_shear = 0., s_p = 0.;
+        const int nq = P.ncdm_q_size[s], q0 = P.ncdm_q_off[s];
+        const int base = L.psi0_ncdm1 + q0 * stride;
+        if (nq <= 8) {  // few bins: every lane sums them all (no shuffles)
+          for (int iq = 0; iq < nq; iq++) {
+            const int idx = base + iq * stride;
+            const double y0 = y[idx], y1 = y[idx + 1], y2 = y[idx + 2];
+            s_rho += w[nqt + q0 + iq] * y0;
+            s_theta += w[2 * nqt + q0 + iq] * y1;
+            s_shear += w[3 * nqt + q0 + iq] * y2;
+            s_p += w[3 * nqt + q0 + iq] * y0;
+          }
+        } else {
+          for (int iq = lane; iq < nq; iq += 32) {
+            const int idx = base + iq * stride;
+            const double y0 = y[idx], y1 = y[idx + 1], y2 = y[idx + 2];
+            s_rho += w[nqt + q0 + iq] * y0;
+            s_theta += w[2 * nqt + q0 + iq] * y1;
+            s_shear += w[3 * nqt + q0 + iq] * y2;
+            s_p += w[3 * nqt + q0 + iq] * y0;
+          }
+          s_rho = wsum(s_rho); s_theta = wsum(s_theta); s_shear = wsum(s_shear); s_p = wsum(s_p);
+        }
+        s_rho *= factor;
+        s_theta *= k * factor;
+        s_shear *= 2.0 / 3.0 * factor;
+        s_p *= factor / 3.;
+        delta_rho += s_rho; rpt += s_theta; rps += s_shear; delta_p += s_p;
+        // delta_ncdm = s_rho / rho_n, theta_ncdm = s_theta / (rho_n + p_n)
+        delta_rho_m += s_rho; rho_m += rho_n;
+        rpt_m += s_theta; rpm += (rho_n + p_n);
       }
     }
   }
-  if (WANT_MATTER) {
-    m.delta_m = delta_rho_m / rho_m;
-    m.theta_m = rpt_m / rpm;
-  }
+  if (want_matter) m.delta_m = delta_rho_m / rho_m + 3. * aH * (rpt_m / rpm) * ik2;
 
   // ---- perturb_einstein (synchronous gauge, K = 0)
-  const double h_prime = (k2 * eta + 1.5 * a2 * delta_rho) / (0.5 * aH);
-  double rsa_delta_g = 0., rsa_theta_g = 0., rsa_delta_ur = 0., rsa_theta_ur = 0.;
+  const double h_prime = (k2 * eta + 1.5 * a2 * delta_rho) * e.inv_half_aH;
+  double rsa_delta_g = 0., rsa_theta_g = 0.;
   if (ap.rsa_on) {
+    double rsa_delta_ur = 0., rsa_theta_ur = 0.;
     if (P.rsa_method != CLPP_RSA_NULL) {
-      rsa_delta_g = 4. / k2 * (aH * h_prime - k2 * eta);
+      rsa_delta_g = 4. * ik2 * (aH * h_prime - k2 * eta);
       rsa_theta_g = -0.5 * h_prime;
     }
     if (P.rsa_method == CLPP_RSA_MD_WITH_REIO) {
-      rsa_delta_g += -4. / k2 * e.dkappa * (theta_b + 0.5 * h_prime);
-      rsa_theta_g += 3. / k2 * (e.ddkappa * (theta_b + 0.5 * h_prime) +
-                                e.dkappa * (-aH * theta_b + e.cb2 * k2 * delta_b - aH * h_prime + k2 * eta));
+      rsa_delta_g += -4. * ik2 * e.dkappa * (theta_b + 0.5 * h_prime);
+      rsa_theta_g += 3. * ik2 * (e.ddkappa * (theta_b + 0.5 * h_prime) +
+                                 e.dkappa * (-aH * theta_b + e.cb2 * k2 * delta_b - aH * h_prime + k2 * eta));
     }
     if (P.has_ur && P.rsa_method != CLPP_RSA_NULL) {
-      rsa_delta_ur = 4. / k2 * (aH * h_prime - k2 * eta);
+      rsa_delta_ur = 4. * ik2 * (aH * h_prime - k2 * eta);
       rsa_theta_ur = -0.5 * h_prime;
     }
     delta_rho += e.rho_g * rsa_delta_g;
@@ -409,55 +620,54 @@ __device__ void rhs_apply(const PtParams& P, Mode& M, const double* __restrict__
       rpt += 4. / 3. * e.rho_ur * rsa_theta_ur;
     }
   }
-  const double eta_prime = (1.5 * a2 * rpt) / k2;
-  const double h_prime_prime = -2. * aH * h_prime + 2. * k2 * eta - 9. * a2 * delta_p;
-  const double alpha = (h_prime + 6. * eta_prime) / 2. / k2;
+  const double eta_prime = (1.5 * a2 * rpt) * ik2;
+  const double alpha = (h_prime + 6. * eta_prime) * 0.5 * ik2;
   if (!ap.tca_off) {
-    const double sg = 16. / 45. / e.dkappa * (theta_g + k2 * alpha);
+    const double sg = 16. / 45. * e.tau_c * (theta_g + k2 * alpha);
     rps += 4. / 3. * e.rho_g * sg;
   }
-  const double alpha_prime = -2. * aH * alpha + eta - 4.5 * (a2 / k2) * rps;
-  if (WANT_MATTER) {
-    m.delta_m += 3. * a * e.H * m.theta_m / k2;
-    m.delta_cb += 3. * a * e.H * m.theta_cb / k2;
-  }
+  const double alpha_prime = -2. * aH * alpha + eta - 4.5 * (a2 * ik2) * rps;
   m.h_prime = h_prime; m.eta_prime = eta_prime; m.alpha = alpha; m.alpha_prime = alpha_prime;
-  m.h_prime_prime = h_prime_prime;
-  m.delta_rho = delta_rho; m.rho_plus_p_theta = rpt; m.rho_plus_p_shear = rps; m.delta_p = delta_p;
-  m.rsa_delta_g = rsa_delta_g; m.rsa_theta_g = rsa_theta_g; m.rsa_delta_ur = rsa_delta_ur; m.rsa_theta_ur = rsa_theta_ur;
+  m.rsa_delta_g = rsa_delta_g; m.rsa_theta_g = rsa_theta_g;
   if (dy == nullptr) return;
 
-  // ---- perturb_derivs
-  const double cotKgen = 1.0 / (k * e.tau);
-  const double metric_continuity = h_prime / 2.;
+  // ---- perturb_derivs: hub equations (uniform)
+  const double cotKgen = e.inv_tau * M.inv_k;
+  const double metric_continuity = h_prime * 0.5;
   const double metric_shear = k2 * alpha;
-  const double metric_ufa_class = h_prime / 2.;
+  const double metric_ufa_class = h_prime * 0.5;
   if (ap.rsa_on) { delta_g = rsa_delta_g; theta_g = rsa_theta_g; }
 
-  double dtheta_b;
+  double dtheta_b, dtheta_g = 0., dshear_g = 0., dl3_g = 0., dp0 = 0., dp1 = 0., dp2 = 0.;
   if (ap.tca_off) {
     dtheta_b = -aH * theta_b + k2 * delta_p_b_over_rho_b + R * e.dkappa * (theta_g - theta_b);
+    if (full_g) {
+      const double P0 = (p0 + p2 + 2. * shear_g) * 0.125;
+      dtheta_g = k2 * (delta_g * 0.25 - shear_g) + e.dkappa * (theta_b - theta_g);
+      dshear_g = 0.5 * (8. / 15. * (theta_g + metric_shear) - 3. / 5. * k * g3 - e.dkappa * (2. * shear_g - 4. / 5. * P0));
+      dl3_g = k * (1. / 7.0) * (3. * 2. * shear_g - 4. * g4) - e.dkappa * g3;
+      dp0 = -k * p1 - e.dkappa * (p0 - 4. * P0);
+      dp1 = k * (1. / 3.) * (p0 - 2. * p2) - e.dkappa * p1;
+      dp2 = k * (1. / 5.) * (2. * p1 - 3. * p3) - e.dkappa * (p2 - 4. / 5. * P0);
+    }
   } else {
     // ---- perturb_tca_slip_and_shear
-    const double a_primeprime_over_a = e.Hp * a + 2. * aH * aH;
-    const double tau_c = 1. / e.dkappa;
+    const double a_primeprime_over_a = e.Hp * e.a + 2. * aH * aH;
+    const double tau_c = e.tau_c;
     const double dtau_c = -e.ddkappa * tau_c * tau_c;
-    const double F = tau_c / (1 + R);
+    const double i1pR = e.inv_1pR;
+    const double F = tau_c * i1pR;
     double F_prime = 0.;
-    if (P.tca_method >= CLPP_TCA_SECOND_ORDER_CLASS) F_prime = dtau_c / (1 + R) + tau_c * aH * R / (1 + R) / (1 + R);
+    if (P.tca_method >= CLPP_TCA_SECOND_ORDER_CLASS) F_prime = dtau_c * i1pR + tau_c * aH * R * i1pR * i1pR;
     const double metric_shear_prime = k2 * alpha_prime;
+    const double common = F * (-a_primeprime_over_a * theta_b +
+                               k2 * (-aH * delta_g * 0.5 + e.cb2 * (-theta_b - metric_continuity) -
+                                     4. / 3. * (-theta_g - metric_continuity) * 0.25));
     double slip;
-    if (P.tca_method == CLPP_TCA_FIRST_ORDER_MB) {
-      slip = 2. * R / (1. + R) * aH * (theta_b - theta_g) +
-             F * (-a_primeprime_over_a * theta_b +
-                  k2 * (-aH * delta_g / 2. + e.cb2 * (-theta_b - metric_continuity) - 4. / 3. * (-theta_g - metric_continuity) / 4.));
-    } else {
-      slip = (dtau_c / tau_c - 2. * aH / (1. + R)) * (theta_b - theta_g) +
-             F * (-a_primeprime_over_a * theta_b +
-                  k2 * (-aH * delta_g / 2. + e.cb2 * (-theta_b - metric_continuity) - 4. / 3. * (-theta_g - metric_continuity) / 4.));
-    }
+    if (P.tca_method == CLPP_TCA_FIRST_ORDER_MB) slip = 2. * R * i1pR * aH * (theta_b - theta_g) + common;
+    else slip = (dtau_c * e.dkappa - 2. * aH * i1pR) * (theta_b - theta_g) + common;
     double sg = 16. / 45. * tau_c * (theta_g + metric_shear);
-    const double theta_prime = (-aH * theta_b + k2 * (e.cb2 * delta_b + R / 4. * delta_g)) / (1. + R);
+    const double theta_prime = (-aH * theta_b + k2 * (e.cb2 * delta_b + R * 0.25 * delta_g)) * i1pR;
     const double shear_g_prime = 16. / 45. * (tau_c * (theta_prime + metric_shear_prime) + dtau_c * (theta_g + metric_shear));
     if (P.tca_method == CLPP_TCA_COMPROMISE_CLASS) {
       slip = (1. - 2. * aH * F) * slip +
@@ -465,111 +675,99 @@ __device__ void rhs_apply(const PtParams& P, Mode& M, const double* __restrict__
       sg = (1. - 11. / 6. * dtau_c) * sg - 11. / 6. * tau_c * 16. / 45. * tau_c * (theta_prime + metric_shear_prime);
     }
     m.tca_shear_g = sg;
-    m.tca_slip = slip;
-    dtheta_b = (-aH * theta_b + k2 * (delta_p_b_over_rho_b + R * (delta_g / 4. - sg)) + R * slip) / (1. + R);
+    dtheta_b = (-aH * theta_b + k2 * (delta_p_b_over_rho_b + R * (delta_g * 0.25 - sg)) + R * slip) * i1pR;
+    dtheta_g = -(dtheta_b + aH * theta_b - k2 * delta_p_b_over_rho_b) * e.inv_R + k2 * (0.25 * delta_g - sg);
   }
-
+  double ddelta_ur = 0., dtheta_ur = 0., dshear_ur = 0., dl3_ur = 0.;
+  if (has_ur) {
+    ddelta_ur = -4. / 3. * (theta_ur + metric_continuity) +
+                (1. - P.three_ceff2_ur) * aH * (delta_ur + 4. * aH * theta_ur * ik2);
+    dtheta_ur = k2 * (P.three_ceff2_ur * delta_ur * 0.25 - shear_ur) - (1. - P.three_ceff2_ur) * aH * theta_ur;
+    if (!ap.ufa_on) {
+      dshear_ur = 0.5 * (8. / 15. * (theta_ur + metric_shear) - 3. / 5. * k * u3 -
+                         (1. - P.three_cvis2_ur) * (8. / 15. * (theta_ur + metric_shear)));
+      dl3_ur = k * (1. / 7.) * (3. * 2. * shear_ur - 4. * u4);
+    } else {
+      if (P.ufa_method == CLPP_UFA_MB) dshear_ur = -3. * e.inv_tau * shear_ur + 2. / 3. * (theta_ur + metric_shear);
+      else if (P.ufa_method == CLPP_UFA_HU) dshear_ur = -3. * aH * shear_ur + 2. / 3. * (theta_ur + metric_shear);
+      else dshear_ur = -3. * e.inv_tau * shear_ur + 2. / 3. * (theta_ur + metric_ufa_class);
+    }
+  }
+  // ---- stores of the hub equations (lane 0) ...
   if (lane == 0) {
-    if (!ap.rsa_on) dy[L.delta_g] = -4. / 3. * (theta_g + metric_continuity);
+    if (has_g) {
+      dy[L.delta_g] = -4. / 3. * (theta_g + metric_continuity);
+      dy[L.theta_g] = dtheta_g;
+      if (full_g) {
+        dy[L.shear_g] = dshear_g;
+        dy[L.l3_g] = dl3_g;
+        dy[L.pol0_g] = dp0;
+        dy[L.pol0_g + 1] = dp1;
+        dy[L.pol0_g + 2] = dp2;
+      }
+    }
     dy[L.delta_b] = -(theta_b + metric_continuity);
     dy[L.theta_b] = dtheta_b;
     dy[L.delta_cdm] = -metric_continuity;
     dy[L.eta] = eta_prime;
-  }
-  if (!ap.rsa_on) {
-    if (ap.tca_off) {
-      const int lg = L.l_max_g, lp = L.l_max_pol_g;
-      const double* yg = y + L.delta_g;  // yg[l] = F_l (l>=3), yg[2] = shear
-      const double* yp = y + L.pol0_g;
-      const double P0 = (yp[0] + yp[2] + 2. * yg[2]) / 8.;
-      if (lane == 1) {
-        dy[L.theta_g] = k2 * (delta_g / 4. - yg[2]) + e.dkappa * (theta_b - theta_g);
-        dy[L.shear_g] = 0.5 * (8. / 15. * (theta_g + metric_shear) - 3. / 5. * k * yg[3] - e.dkappa * (2. * yg[2] - 4. / 5. * P0));
-        dy[L.l3_g] = k / 7.0 * (3. * 2. * yg[2] - 4. * yg[4]) - e.dkappa * yg[3];
-      }
-      if (lane == 2) {
-        dy[L.pol0_g] = -k * yp[1] - e.dkappa * (yp[0] - 4. * P0);
-        dy[L.pol0_g + 1] = k / 3. * (yp[0] - 2. * yp[2]) - e.dkappa * yp[1];
-        dy[L.pol0_g + 2] = k / 5. * (2. * yp[1] - 3. * yp[3]) - e.dkappa * (yp[2] - 4. / 5. * P0);
-      }
-      for (int l = 4 + lane; l <= lg; l += 32) {
-        if (l < lg) dy[L.delta_g + l] = k / (2.0 * l + 1.0) * (l * yg[l - 1] - (l + 1) * yg[l + 1]) - e.dkappa * yg[l];
-        else dy[L.delta_g + l] = k * (yg[l - 1] - (1. + l) * cotKgen * yg[l]) - e.dkappa * yg[l];
-      }
-      for (int l = 3 + lane; l <= lp; l += 32) {
-        if (l < lp) dy[L.pol0_g + l] = k / (2. * l + 1) * (l * yp[l - 1] - (l + 1.) * yp[l + 1]) - e.dkappa * yp[l];
-        else dy[L.pol0_g + l] = k * (yp[l - 1] - (l + 1) * cotKgen * yp[l]) - e.dkappa * yp[l];
-      }
-    } else if (lane == 1) {
-      dy[L.theta_g] = -(dtheta_b + aH * theta_b - k2 * delta_p_b_over_rho_b) / R + k2 * (0.25 * delta_g - m.tca_shear_g);
+    if (has_ur) {
+      dy[L.delta_ur] = ddelta_ur;
+      dy[L.theta_ur] = dtheta_ur;
+      dy[L.shear_ur] = dshear_ur;
+      if (!ap.ufa_on) dy[L.l3_ur] = dl3_ur;
     }
   }
-  if (P.has_ur && !ap.rsa_on) {
+  // ---- ... and the multipole chains, one element per lane (1/(2l+1) from a shared-memory table)
+  const double* i2l1 = s_i2l1(P);
+  if (full_g) {
+    const int lg = P.l_max_g, lp = P.l_max_pol_g;
+    const double* yg = y + L.delta_g;  // yg[l] = F_l (l>=3), yg[2] = shear
+    const double* yp = y + L.pol0_g;
+    for (int l = 4 + lane; l <= lg; l += 32) {
+      if (l < lg) dy[L.delta_g + l] = k * i2l1[l] * (l * yg[l - 1] - (l + 1) * yg[l + 1]) - e.dkappa * yg[l];
+      else dy[L.delta_g + l] = k * (yg[l - 1] - (1. + l) * cotKgen * yg[l]) - e.dkappa * yg[l];
+    }
+    for (int l = 3 + lane; l <= lp; l += 32) {
+      if (l < lp) dy[L.pol0_g + l] = k * i2l1[l] * (l * yp[l - 1] - (l + 1.) * yp[l + 1]) - e.dkappa * yp[l];
+      else dy[L.pol0_g + l] = k * (yp[l - 1] - (l + 1) * cotKgen * yp[l]) - e.dkappa * yp[l];
+    }
+  }
+  if (has_ur && !ap.ufa_on) {
     const double* yu = y + L.delta_ur;
-    if (lane == 3) {
-      dy[L.delta_ur] = -4. / 3. * (yu[1] + metric_continuity) +
-                       (1. - P.three_ceff2_ur) * aH * (yu[0] + 4. * aH * yu[1] / k / k);
-      dy[L.theta_ur] = k2 * (P.three_ceff2_ur * yu[0] / 4. - yu[2]) - (1. - P.three_ceff2_ur) * aH * yu[1];
-      if (!ap.ufa_on) {
-        dy[L.shear_ur] = 0.5 * (8. / 15. * (yu[1] + metric_shear) - 3. / 5. * k * yu[3] -
-                                (1. - P.three_cvis2_ur) * (8. / 15. * (yu[1] + metric_shear)));
-        dy[L.l3_ur] = k / 7. * (3. * 2. * yu[2] - 4. * yu[4]);
-      } else {
-        if (P.ufa_method == CLPP_UFA_MB) dy[L.shear_ur] = -3. / e.tau * yu[2] + 2. / 3. * (yu[1] + metric_shear);
-        else if (P.ufa_method == CLPP_UFA_HU) dy[L.shear_ur] = -3. * aH * yu[2] + 2. / 3. * (yu[1] + metric_shear);
-        else dy[L.shear_ur] = -3. / e.tau * yu[2] + 2. / 3. * (yu[1] + metric_ufa_class);
-      }
-    }
-    if (!ap.ufa_on) {
-      const int lu = L.l_max_ur;
-      for (int l = 4 + lane; l <= lu; l += 32) {
-        if (l < lu) dy[L.delta_ur + l] = k / (2. * l + 1) * (l * yu[l - 1] - (l + 1.) * yu[l + 1]);
-        else dy[L.delta_ur + l] = k * (yu[l - 1] - (1. + l) * cotKgen * yu[l]);
-      }
+    const int lu = P.l_max_ur;
+    for (int l = 4 + lane; l <= lu; l += 32) {
+      if (l < lu) dy[L.delta_ur + l] = k * i2l1[l] * (l * yu[l - 1] - (l + 1.) * yu[l + 1]);
+      else dy[L.delta_ur + l] = k * (yu[l - 1] - (1. + l) * cotKgen * yu[l]);
     }
   }
   if (P.has_ncdm) {
     if (ap.ncdmfa_on) {
       if (lane < P.N_ncdm) {
         const int s = lane;
-        const double rho_n = M.pvb[P.irho_ncdm1 + s], p_n = M.pvb[P.ip_ncdm1 + s], pseudo_p = M.pvb[P.ipseudo_p_ncdm1 + s];
-        const double pseudo_p_over_p = pseudo_p / p_n;
-        const double w_n = p_n / rho_n;
-        const double ca2 = w_n / 3.0 / (1.0 + w_n) * (5.0 - pseudo_p / p_n);
-        const double ceff2 = ca2;
-        const double cvis2 = (P.ncdmfa_method == CLPP_NCDMFA_HU) ? w_n : 3. * w_n * ca2;
-        const int idx = L.ncdm_off[s];
-        dy[idx] = -(1.0 + w_n) * (y[idx + 1] + metric_continuity) - 3.0 * aH * (ceff2 - w_n) * y[idx];
-        dy[idx + 1] = -aH * (1.0 - 3.0 * ca2) * y[idx + 1] + ceff2 / (1.0 + w_n) * k2 * y[idx] - k2 * y[idx + 2];
-        if (P.ncdmfa_method == CLPP_NCDMFA_MB)
-          dy[idx + 2] = -3.0 * (aH * (2. / 3. - ca2 - pseudo_p_over_p / 3.) + 1. / e.tau) * y[idx + 2] +
-                        8.0 / 3.0 * cvis2 / (1.0 + w_n) * (y[idx + 1] + metric_shear);
-        else if (P.ncdmfa_method == CLPP_NCDMFA_HU)
-          dy[idx + 2] = -3.0 * aH * ca2 / w_n * y[idx + 2] + 8.0 / 3.0 * cvis2 / (1.0 + w_n) * (y[idx + 1] + metric_shear);
-        else
-          dy[idx + 2] = -3.0 * (aH * (2. / 3. - ca2 - pseudo_p_over_p / 3.) + 1. / e.tau) * y[idx + 2] +
-                        8.0 / 3.0 * cvis2 / (1.0 + w_n) * (y[idx + 1] + metric_ufa_class);
+        const double* nf = M.nf[s];  // [2] w, [4] ca2, [5] ceff2/(1+w), [6] 8/3 cvis2/(1+w), [7] shear damping rate
+        const int idx = L.psi0_ncdm1 + 3 * s;
+        const double y0 = y[idx], y1 = y[idx + 1], y2 = y[idx + 2];
+        const double w_n = nf[2], ca2 = nf[4];
+        dy[idx] = -(1.0 + w_n) * (y1 + metric_continuity) - 3.0 * aH * (ca2 - w_n) * y0;
+        dy[idx + 1] = -aH * (1.0 - 3.0 * ca2) * y1 + nf[5] * k2 * y0 - k2 * y2;
+        const double ms = (P.ncdmfa_method == CLPP_NCDMFA_CLASS) ? metric_ufa_class : metric_shear;
+        dy[idx + 2] = -nf[7] * y2 + nf[6] * (y1 + ms);
       }
     } else {
       const int stride = L.l_max_ncdm + 1, lm = L.l_max_ncdm;
-      for (int s = 0; s < P.N_ncdm; s++) {
-        const int tot = L.q_size_ncdm[s] * stride;
-        const double Ms = P.ncdm_M[s];
-        for (int e_i = lane; e_i < tot; e_i += 32) {
-          const int iq = e_i / stride, l = e_i - iq * stride;
-          const int idx = L.ncdm_off[s] + iq * stride;
-          const double q = P.ncdm_q[P.ncdm_q_off[s] + iq];
-          const double dlnf0 = P.ncdm_dlnf0[P.ncdm_q_off[s] + iq];
-          const double eps = sqrt(q * q + a2 * Ms * Ms);
-          const double qk = k * q / eps;
-          double v;
-          if (l == 0) v = -qk * y[idx + 1] + metric_continuity * dlnf0 / 3.;
-          else if (l == 1) v = qk / 3.0 * (y[idx] - 2 * y[idx + 2]);
-          else if (l == 2) v = qk / 5.0 * (2 * y[idx + 1] - 3. * y[idx + 3]) - metric_shear * 2. / 15. * dlnf0;
-          else if (l < lm) v = qk / (2. * l + 1.0) * (l * y[idx + (l - 1)] - (l + 1.) * y[idx + (l + 1)]);
-          else v = qk * y[idx + l - 1] - (1. + l) * k * cotKgen * y[idx + l];
-          dy[idx + l] = v;
-        }
+      const int tot = L.eta - L.psi0_ncdm1;  // all species are contiguous, same stride
+      const double* w = s_nw(P);
+      for (int e_i = lane; e_i < tot; e_i += 32) {
+        const int jq = e_i / stride, l = e_i - jq * stride;  // jq = global momentum-bin index
+        const int idx = L.psi0_ncdm1 + jq * stride;
+        const double qk = k * w[jq];
+        double v;
+        if (l == 0) v = -qk * y[idx + 1] + metric_continuity * __ldg(M.C->ncdm_dlnf0 + jq) * (1. / 3.);
+        else if (l == 1) v = qk * (1. / 3.0) * (y[idx] - 2 * y[idx + 2]);
+        else if (l == 2) v = qk * (1. / 5.0) * (2 * y[idx + 1] - 3. * y[idx + 3]) - metric_shear * 2. / 15. * __ldg(M.C->ncdm_dlnf0 + jq);
+        else if (l < lm) v = qk * i2l1[l] * (l * y[idx + (l - 1)] - (l + 1.) * y[idx + (l + 1)]);
+        else v = qk * y[idx + l - 1] - (1. + l) * k * cotKgen * y[idx + l];
+        dy[idx + l] = v;
       }
     }
   }
@@ -578,18 +776,21 @@ __device__ void rhs_apply(const PtParams& P, Mode& M, const double* __restrict__
 
 // ---------------------------------------------------------------------------------------------
 // perturb_sources_member: source functions at sample index_tau from (y, dy)
-__device__ void write_sources(const PtParams& P, Mode& M, double tau, const double* y, const double* dy, int index_tau) {
-  env_at(P, M, tau, true);
-  rhs_apply<true>(P, M, y, nullptr);
-  if (M.lane != 0) return;
+__device__ __noinline__ void write_sources(const PtParams& P, double tau, int slot_y, int slot_dy, int index_tau) {
+  Mode& M = MODE(P);
+  const double* y = s_vec(P, slot_y);
+  const double* dy = s_vec(P, slot_dy);
+  env_at(P, tau, true);
+  rhs_apply(P, slot_y, -1, 1);
+  if ((int)threadIdx.x != 0) return;
   const Layout& L = M.L;
   const Approx& ap = M.ap;
   const Env& e = M.e;
   const Metric& m = M.m;
   const double k = M.k;
-  const double z = P.a_today / e.a - 1.;
+  const double z = M.C->a_today / e.a - 1.;
   const double aH = e.a * e.H;
-  const double aH_prime = e.Hp * e.a + pow(e.H * e.a, 2);
+  const double aH_prime = e.Hp * e.a + (e.H * e.a) * (e.H * e.a);
   double delta_g, Pi;
   if (ap.rsa_on) { delta_g = m.rsa_delta_g; Pi = 0.; }
   else {
@@ -597,8 +798,8 @@ __device__ void write_sources(const PtParams& P, Mode& M, double tau, const doub
     if (!ap.tca_off) Pi = 5. * M.tca_shear_last / 8.;
     else Pi = (y[L.pol0_g] + y[L.pol0_g + 2] + 2. * y[L.shear_g]) / 8.;
   }
-  const size_t stride_tp = (size_t)P.k_size * P.tau_size;
-  double* out = P.sources + (size_t)M.ik * P.tau_size + index_tau;
+  const size_t stride_tp = (size_t)M.C->k_size * M.C->tau_size;
+  double* out = M.C->sources + (size_t)M.ik * M.C->tau_size + index_tau;
   if (P.tp_t0 >= 0) {
     int switch_isw = 1;
     if ((P.switch_eisw == 0) && (z >= P.eisw_lisw_split_z)) switch_isw = 0;
@@ -619,20 +820,91 @@ __device__ void write_sources(const PtParams& P, Mode& M, double tau, const doub
 }
 
 // ---------------------------------------------------------------------------------------------
-// dense LU of A = I - c J with partial pivoting (Crout-free right-looking form, rows over lanes)
-__device__ bool lu_factor(Mode& M, int n, int ld, double c) {
-  const int lane = M.lane;
-  double* A = M.LU;
-  // build A from the global Jacobian (column-major, coalesced)
-  for (int j = 0; j < n; j++)
-    for (int i = lane; i < n; i += 32) A[i + j * ld] = (i == j ? 1.0 : 0.0) - c * M.J[i + (size_t)j * n];
+// Jacobian J = A(tau): hub columns f(tau, e_j) one by one, chain entries with 3 grouped probes
+// (the environment M.e must be set at tau)
+__device__ __noinline__ void jacobian(const PtParams& P) {
+  Mode& M = MODE(P);
+  const int n = M.L.neq, lane = (int)threadIdx.x, nh = M.nh, nch = M.nch;
+  double* e_j = s_vec(P, V_TMP);
+  double* col = s_vec(P, V_DEL);
+  double *Jd = s_vec(P, V_JD), *Jl = s_vec(P, V_JL), *Ju = s_vec(P, V_JU);
+  for (int i = lane; i < n; i += 32) { e_j[i] = 0.; Jd[i] = 0.; Jl[i] = 0.; Ju[i] = 0.; }
   __syncwarp();
-  for (int j = 0; j < n; j++) {
-    // pivot search in column j
+  for (int j = 0; j < nh; j++) {
+    const int hj = s_hub_idx(P)[j];
+    if (lane == 0) e_j[hj] = 1.;
+    __syncwarp();
+    rhs_apply(P, V_TMP, V_DEL, 0);
+    for (int s = lane; s < nh; s += 32) M.Jhh[s + (size_t)j * nh] = col[s_hub_idx(P)[s]];
+    if (lane < nch && s_ch_start(P)[lane] - 1 == hj) Jl[hj + 1] = col[hj + 1];  // chain start <- its root
+    if (lane == 0) e_j[hj] = 0.;
+    __syncwarp();
+  }
+  if (nch > 0) {
+    for (int r = 0; r < 3; r++) {
+      if (lane < nch) {
+        const int s = s_ch_start(P)[lane], len = s_ch_len(P)[lane];
+        for (int p = r; p < len; p += 3) e_j[s + p] = 1.;
+      }
+      __syncwarp();
+      rhs_apply(P, V_TMP, V_DEL, 0);
+      if (lane < nch) {
+        const int s = s_ch_start(P)[lane], len = s_ch_len(P)[lane];
+        for (int p = 0; p < len; p++) {
+          const int i = s + p, pm = p % 3;
+          if (pm == r) Jd[i] = col[i];
+          if ((pm + 1) % 3 == r && p + 1 < len) Ju[i] = col[i];
+          if ((pm + 2) % 3 == r && p >= 1) Jl[i] = col[i];
+        }
+        if (r == 0) Ju[s - 1] = col[s - 1];  // root <- chain start
+        for (int p = r; p < len; p += 3) e_j[s + p] = 0.;
+      }
+      __syncwarp();
+    }
+  }
+  if (threadIdx.x == 0) M.st.jacobians++;
+  if (threadIdx.x == 0) M.st.fevals += nh + (nch > 0 ? 3 : 0);
+}
+
+// Factorisation of A = I - c J: chains (backward elimination towards their root), Schur
+// complement on the hub block, explicit inverse of the hub block (Gauss-Jordan, partial pivoting).
+__device__ __noinline__ void factor(const PtParams& P, double c) {
+  Mode& M = MODE(P);
+  const int lane = (int)threadIdx.x, nh = M.nh, nch = M.nch, ldh = P.ldh;
+  const double *Jd = s_vec(P, V_JD), *Jl = s_vec(P, V_JL), *Ju = s_vec(P, V_JU);
+  double *ip = s_vec(P, V_IP), *mu = s_vec(P, V_MU), *lo = s_vec(P, V_LO);
+  double* W = s_sinv(P);
+  for (int i = lane; i < nh; i += 32) s_hubtmp(P)[i] = 0.;
+  __syncwarp();
+  if (lane < nch) {
+    const int s = s_ch_start(P)[lane], last = s + s_ch_len(P)[lane] - 1;
+    double ipn = 1.0 / (1.0 - c * Jd[last]);
+    ip[last] = ipn;
+    double lon = -c * Jl[last];
+    lo[last] = lon;
+    for (int i = last - 1; i >= s; i--) {
+      const double mui = -c * Ju[i] * ipn;
+      const double p = (1.0 - c * Jd[i]) - mui * lon;
+      ipn = 1.0 / p;
+      lon = -c * Jl[i];
+      ip[i] = ipn; mu[i] = mui; lo[i] = lon;
+    }
+    const double mur = -c * Ju[s - 1] * ipn;
+    mu[s - 1] = mur;
+    s_hubtmp(P)[s_ch_rootslot(P)[lane]] = -mur * lon;
+  }
+  __syncwarp();
+  // hub block W = I - c Jhh (+ Schur terms on the diagonal of the chain roots); lane i owns row i
+  for (int i = lane; i < nh; i += 32) {
+    for (int j = 0; j < nh; j++) W[i * ldh + j] = (i == j ? 1.0 + s_hubtmp(P)[i] : 0.0) - c * M.Jhh[i + (size_t)j * nh];
+  }
+  __syncwarp();
+  for (int j = 0; j < nh; j++) {
+    // pivot search in column j, rows >= j
     double best = -1.;
     int bi = j;
-    for (int i = j + lane; i < n; i += 32) {
-      const double v = fabs(A[i + j * ld]);
+    for (int i = j + lane; i < nh; i += 32) {
+      const double v = fabs(W[i * ldh + j]);
       if (v > best) { best = v; bi = i; }
     }
 #pragma unroll
@@ -641,156 +913,184 @@ __device__ bool lu_factor(Mode& M, int n, int ld, double c) {
       const int oi = __shfl_xor_sync(PT_FULL, bi, o);
       if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
-    if (lane == 0) M.piv[j] = bi;
-    if (best == 0.) {
-      if (lane == 0) A[j + j * ld] = 1e-50;  // TINY, as ludcmp does for a singular pivot
-    }
+    if (lane == 0) s_piv(P)[j] = bi;
     if (bi != j) {
-      for (int cc = lane; cc < n; cc += 32) {
-        const double t = A[j + cc * ld];
-        A[j + cc * ld] = A[bi + cc * ld];
-        A[bi + cc * ld] = t;
+      for (int cc = lane; cc < nh; cc += 32) {
+        const double t = W[j * ldh + cc];
+        W[j * ldh + cc] = W[bi * ldh + cc];
+        W[bi * ldh + cc] = t;
       }
+      __syncwarp();
     }
+    double pv = W[j * ldh + j];
+    if (pv == 0.) pv = 1e-50;  // TINY, as ludcmp does for a singular pivot
+    const double pinv = 1.0 / pv;
     __syncwarp();
-    const double pinv = 1.0 / A[j + j * ld];
-    for (int i = j + 1 + lane; i < n; i += 32) A[i + j * ld] *= pinv;
+    for (int cc = lane; cc < nh; cc += 32) W[j * ldh + cc] = (cc == j) ? pinv : W[j * ldh + cc] * pinv;
     __syncwarp();
-    // trailing update, flat over the (n-j-1)^2 block
-    const int mrem = n - j - 1;
-    if (mrem > 0) {
-      if (mrem >= 32) {
-        for (int cc = j + 1; cc < n; cc++) {
-          const double ajc = A[j + cc * ld];
-          if (ajc != 0.)
-            for (int i = j + 1 + lane; i < n; i += 32) A[i + cc * ld] -= A[i + j * ld] * ajc;
-        }
-      } else {
-        const int tot = mrem * mrem;
-        for (int t = lane; t < tot; t += 32) {
-          const int cc = j + 1 + t / mrem, i = j + 1 + t % mrem;
-          A[i + cc * ld] -= A[i + j * ld] * A[j + cc * ld];
+    for (int i = lane; i < nh; i += 32) {
+      if (i != j) {
+        const double f = W[i * ldh + j];
+        if (f != 0.) {
+          for (int cc = 0; cc < nh; cc++) {
+            const double wj = W[j * ldh + cc];
+            W[i * ldh + cc] = (cc == j) ? -f * wj : W[i * ldh + cc] - f * wj;
+          }
         }
       }
     }
     __syncwarp();
   }
-  return true;
+  for (int j = nh - 1; j >= 0; j--) {
+    const int p = s_piv(P)[j];
+    if (p != j) {
+      for (int i = lane; i < nh; i += 32) {
+        const double t = W[i * ldh + j];
+        W[i * ldh + j] = W[i * ldh + p];
+        W[i * ldh + p] = t;
+      }
+      __syncwarp();
+    }
+  }
+  if (threadIdx.x == 0) M.st.factorizations++;
 }
 
-// solve A x = b in place (b in shared memory)
-__device__ void lu_solve(Mode& M, int n, int ld, double* b) {
-  const int lane = M.lane;
-  const double* A = M.LU;
-  // apply the row permutation
-  if (lane == 0) {
-    for (int j = 0; j < n; j++) {
-      const int p = M.piv[j];
-      if (p != j) { const double t = b[j]; b[j] = b[p]; b[p] = t; }
+// solve A x = b in place (b in shared memory) with the factors of `factor`
+__device__ __forceinline__ void solve(const PtParams& P, double* __restrict__ b) {
+  Mode& M = MODE(P);
+  const int lane = (int)threadIdx.x, nh = M.nh, nch = M.nch, ldh = P.ldh;
+  const double *ip = s_vec(P, V_IP), *mu = s_vec(P, V_MU), *lo = s_vec(P, V_LO);
+  if (nch > 0) {
+    if (lane < nch) {
+      const int s = s_ch_start(P)[lane], last = s + s_ch_len(P)[lane] - 1;
+      double r = b[last];
+      for (int i = last - 1; i >= s; i--) {
+        r = b[i] - mu[i] * r;
+        b[i] = r;
+      }
+      b[s - 1] -= mu[s - 1] * r;
+    }
+    __syncwarp();
+  }
+  if (nh <= 32) {
+    double x = 0.;
+    if (lane < nh) {
+      const double* w = s_sinv(P) + lane * ldh;
+      double x0 = 0., x1 = 0.;
+      int j = 0;
+      for (; j + 1 < nh; j += 2) {
+        x0 += w[j] * b[s_hub_idx(P)[j]];
+        x1 += w[j + 1] * b[s_hub_idx(P)[j + 1]];
+      }
+      if (j < nh) x0 += w[j] * b[s_hub_idx(P)[j]];
+      x = x0 + x1;
+    }
+    __syncwarp();
+    if (lane < nh) b[s_hub_idx(P)[lane]] = x;
+  } else {
+    double xs[4];  // up to 128 hub variables
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int i = lane + 32 * t;
+      double x = 0.;
+      if (i < nh) {
+        const double* w = s_sinv(P) + i * ldh;
+        for (int j = 0; j < nh; j++) x += w[j] * b[s_hub_idx(P)[j]];
+      }
+      xs[t] = x;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int i = lane + 32 * t;
+      if (i < nh) b[s_hub_idx(P)[i]] = xs[t];
     }
   }
   __syncwarp();
-  // forward substitution (unit lower), column oriented
-  for (int j = 0; j < n - 1; j++) {
-    const double xj = b[j];
-    if (xj != 0.)
-      for (int i = j + 1 + lane; i < n; i += 32) b[i] -= A[i + j * ld] * xj;
+  if (nch > 0) {
+    if (lane < nch) {
+      const int s = s_ch_start(P)[lane], last = s + s_ch_len(P)[lane] - 1;
+      double xp = b[s - 1];
+      for (int i = s; i <= last; i++) {
+        xp = (b[i] - lo[i] * xp) * ip[i];
+        b[i] = xp;
+      }
+    }
     __syncwarp();
   }
-  // back substitution
-  for (int j = n - 1; j >= 0; j--) {
-    if (lane == 0) b[j] = b[j] / A[j + j * ld];
-    __syncwarp();
-    const double xj = b[j];
-    for (int i = lane; i < j; i += 32) b[i] -= A[i + j * ld] * xj;
-    __syncwarp();
-  }
-}
-
-// Jacobian J = A(tau): column j = f(tau, e_j) (the environment M.e must be set at tau)
-__device__ void jacobian(const PtParams& P, Mode& M) {
-  const int n = M.L.neq, lane = M.lane;
-  double* e_j = M.tmp;
-  double* col = M.del;
-  for (int i = lane; i < n; i += 32) e_j[i] = 0.;
-  __syncwarp();
-  for (int j = 0; j < n; j++) {
-    if (lane == 0) { e_j[j] = 1.; if (j > 0) e_j[j - 1] = 0.; }
-    __syncwarp();
-    rhs_apply<false>(P, M, e_j, col);
-    for (int i = lane; i < n; i += 32) M.J[i + (size_t)j * n] = col[i];
-    __syncwarp();
-  }
-  M.st.jacobians++;
-  M.st.fevals += n;
+  if (threadIdx.x == 0) M.st.solves++;
 }
 
 // rescale the backward differences when the step changes by the factor r (k = current order)
-__device__ void adjust_stepsize(Mode& M, double r, int k) {
-  const double U[5][5] = {{-1, -2, -3, -4, -5}, {0, 1, 3, 6, 10}, {0, 0, -1, -4, -10}, {0, 0, 0, 1, 5}, {0, 0, 0, 0, -1}};
-  double RU[5][5], tmpv[5];
-  for (int ii = 1; ii <= 5; ii++) RU[0][ii - 1] = -ii * r;
-  for (int jj = 2; jj <= 5; jj++)
-    for (int ii = 1; ii <= 5; ii++) RU[jj - 1][ii - 1] = RU[jj - 2][ii - 1] * (1.0 - (1.0 + ii * r) / jj);
-  for (int ii = 0; ii < 5; ii++) {
-    for (int kk = 0; kk < 5; kk++) tmpv[kk] = RU[ii][kk];
-    for (int jj = 0; jj < 5; jj++) {
-      double s = 0.0;
-      for (int kk = 0; kk < 5; kk++) s += tmpv[kk] * U[kk][jj];
-      RU[ii][jj] = s;
+__device__ __noinline__ void adjust_stepsize(const PtParams& P, double r, int k) {
+  Mode& M = MODE(P);
+  // RU = R(r) * U; lane t < 25 computes entry (t/5, t%5) and parks it in shared memory
+  double* RU = s_hubtmp(P);  // >= 32 doubles
+  if ((int)threadIdx.x < 25) {
+    const int ii = (int)threadIdx.x / 5, jj = (int)threadIdx.x % 5;
+    double s = 0.;
+#pragma unroll
+    for (int kk = 0; kk < 5; kk++) {
+      // R[ii][kk] = prod_{m=1..ii+1} (m - 1 - (kk+1) r) / m
+      double Rv = 1.;
+      for (int mm = 1; mm <= ii + 1; mm++) Rv *= ((mm - 1) - (kk + 1) * r) / mm;
+      s += Rv * c_U[kk][jj];
     }
+    RU[(int)threadIdx.x] = s;
   }
-  const int n = M.L.neq, np = M.neq_pad;
-  for (int i = M.lane; i < n; i += 32) {
+  __syncwarp();
+  const int n = M.L.neq, np = P.np;
+  double* dif = s_vec(P, V_DIF0);
+  for (int i = (int)threadIdx.x; i < n; i += 32) {
     double row[5];
-    for (int kk = 0; kk < k; kk++) row[kk] = M.dif[kk * np + i];
-    for (int jj = 0; jj < k; jj++) {
-      double s = 0.0;
-      for (int kk = 0; kk < k; kk++) s += row[kk] * RU[kk][jj];
-      M.dif[jj * np + i] = s;
+#pragma unroll
+    for (int kk = 0; kk < 5; kk++) row[kk] = (kk < k) ? dif[kk * np + i] : 0.;
+#pragma unroll
+    for (int jj = 0; jj < 5; jj++) {
+      if (jj < k) {
+        double s = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 5; kk++) s += row[kk] * RU[kk * 5 + jj];
+        dif[jj * np + i] = s;
+      }
     }
   }
   __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
-// NDF1-5 over [t0, tfinal] for the current layout; y in M.y (in/out). `next` = index of the next
+// NDF1-5 over [t0, tfinal] for the current layout; y in V_Y (in/out). `next` = index of the next
 // source sample time (carried across intervals). Returns false on failure.
-__device__ bool ndf15(const PtParams& P, Mode& M, double t0, double tfinal, int* next_io) {
-  const double G[5] = {1.0, 3.0 / 2.0, 11.0 / 6.0, 25.0 / 12.0, 137.0 / 60.0};
-  const double alpha[5] = {-37.0 / 200, -1.0 / 9.0, -8.23e-2, -4.15e-2, 0};
-  double invGa[5], erconst[5];
-  for (int i = 0; i < 5; i++) {
-    invGa[i] = 1.0 / (G[i] * (1.0 - alpha[i]));
-    erconst[i] = alpha[i] * G[i] + 1.0 / (2.0 + i);
-  }
+__device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) {
+  Mode& M = MODE(P);
+  PROF_DECL;
   const double abstol = 1e-15, eps = 1e-16, threshold = abstol;
   const int maxit = 4, maxk = 5;
   const double rtol = P.rtol;
-  const int n = M.L.neq, np = M.neq_pad, ld = P.ld, lane = M.lane;
-  double *y = M.y, *ynew = M.ynew, *f0 = M.f0, *pred = M.pred, *psi = M.psi, *difkp1 = M.difkp1, *del = M.del,
-         *invwt = M.invwt, *dif = M.dif;
-  const double* t_vec = P.tau;
-  const int tres = P.tau_size;
-  int next = *next_io;
-  while (next < tres && t_vec[next] < t0) next++;
+  const int n = M.L.neq, np = P.np, lane = (int)threadIdx.x;
+  double *y = s_vec(P, V_Y), *ynew = s_vec(P, V_YNEW), *f0 = s_vec(P, V_F0), *pred = s_vec(P, V_PRED), *psi = s_vec(P, V_PSI),
+         *difkp1 = s_vec(P, V_DIFKP1), *del = s_vec(P, V_DEL), *invwt = s_vec(P, V_INVWT), *dif = s_vec(P, V_DIF0);
+  const double* t_vec = M.C->tau;
+  const int tres = M.C->tau_size;
+  int next = M.next;
+  while (next < tres && __ldg(t_vec + next) < t0) next++;
+  double tnext = (next < tres) ? __ldg(t_vec + next) : 1e300;
 
   for (int j = 0; j < 7; j++)
     for (int i = lane; i < n; i += 32) dif[j * np + i] = 0.;
   const double htspan = fabs(tfinal - t0);
   double t = t0, tnew = t0;
-  env_at(P, M, t0, true);
-  rhs_apply<false>(P, M, y, f0);
-  M.st.fevals++;
+  env_at(P, t0, true);
+  rhs_apply(P, V_Y, V_F0, 0);
+  if (threadIdx.x == 0) M.st.fevals++;
   const double hmax = (tfinal - t0) / 10.0;
-  jacobian(P, M);
+  jacobian(P);
   bool Jcurrent = true;
   double hmin = 16.0 * eps * fabs(t);
   // initial step from |f0/wt| and the second derivative estimate
   double rh = 0.0;
   for (int i = lane; i < n; i += 32) {
     const double wt = fmax(fabs(y[i]), threshold);
-    M.tmp[i] = wt;
     rh = fmax(rh, 1.25 / sqrt(rtol) * fabs(f0[i] / wt));
   }
   rh = wmax(rh);
@@ -799,16 +1099,18 @@ __device__ bool ndf15(const PtParams& P, Mode& M, double t0, double tfinal, int*
   absh = fmax(absh, hmin);
   double h = absh;
   {
+    // J*f0 = f(t0, f0): the system is linear and homogeneous
+    rhs_apply(P, V_F0, V_PSI, 0);
+    if (threadIdx.x == 0) M.st.fevals++;
     const double tdel = (t + fmin(sqrt(eps) * fmax(fabs(t), fabs(t + h)), absh)) - t;
-    env_at(P, M, t + tdel, true);
-    rhs_apply<false>(P, M, y, del);  // f(t+tdel, y)
-    M.st.fevals++;
+    env_at(P, t + tdel, true);
+    rhs_apply(P, V_Y, V_DEL, 0);  // f(t+tdel, y)
+    if (threadIdx.x == 0) M.st.fevals++;
     rh = 0.0;
     for (int i = lane; i < n; i += 32) {
-      double s = 0.0;
-      for (int j = 0; j < n; j++) s += M.J[i + (size_t)j * n] * f0[j];
-      s += (del[i] - f0[i]) / tdel;
-      rh = fmax(rh, 1.25 * sqrt(0.5 * fabs(s / M.tmp[i]) / rtol));
+      const double wt = fmax(fabs(y[i]), threshold);
+      const double s = psi[i] + (del[i] - f0[i]) / tdel;
+      rh = fmax(rh, 1.25 * sqrt(0.5 * fabs(s / wt) / rtol));
     }
     rh = wmax(rh);
     absh = fmin(hmax, htspan);
@@ -820,10 +1122,9 @@ __device__ bool ndf15(const PtParams& P, Mode& M, double t0, double tfinal, int*
   double abshlast = absh;
   for (int i = lane; i < n; i += 32) dif[0 * np + i] = h * f0[i];
   __syncwarp();
-  double hinvGak = h * invGa[k - 1];
+  double hinvGak = h * c_invGa[k - 1];
   int nconhk = 0;
-  lu_factor(M, n, ld, hinvGak);
-  M.st.factorizations++;
+  factor(P, hinvGak);
   bool havrate = false;
   bool done = false, at_hmin = false;
   double rate = 0., oldnrm = 0., err = 0.;
@@ -844,11 +1145,14 @@ __device__ bool ndf15(const PtParams& P, Mode& M, double t0, double tfinal, int*
       done = true;
     }
     if (((fabs(absh - abshlast) / absh) > 1e-6) || (k != klast)) {
-      adjust_stepsize(M, absh / abshlast, k);
-      hinvGak = h * invGa[k - 1];
+      PROF_BEGIN();
+      adjust_stepsize(P, absh / abshlast, k);
+      PROF_END(PF_ADJUST);
+      hinvGak = h * c_invGa[k - 1];
       nconhk = 0;
-      lu_factor(M, n, ld, hinvGak);
-      M.st.factorizations++;
+      PROF_BEGIN();
+      factor(P, hinvGak);
+      PROF_END(PF_FACTOR);
       havrate = false;
     }
     bool nofailed = true;
@@ -859,41 +1163,55 @@ __device__ bool ndf15(const PtParams& P, Mode& M, double t0, double tfinal, int*
         if (done) tnew = tfinal;
         h = tnew - t;
         double minnrm = 0.0;
+        PROF_BEGIN();
+        const double invGak = c_invGa[k - 1];
         for (int i = lane; i < n; i += 32) {
-          double ps = 0.0, pr = y[i];
+          double ps = 0.0;
+          const double yi = y[i];
+          double pr = yi;
           for (int j = 0; j < k; j++) {
             const double d = dif[j * np + i];
-            ps += d * G[j] * invGa[k - 1];
+            ps += d * c_G[j] * invGak;
             pr += d;
           }
           psi[i] = ps;
           pred[i] = pr;
           ynew[i] = pr;
           difkp1[i] = 0.0;
-          const double iw = 1.0 / fmax(fmax(fabs(pr), fabs(y[i])), threshold);
+          const double iw = 1.0 / fmax(fmax(fabs(pr), fabs(yi)), threshold);
           invwt[i] = iw;
           minnrm = fmax(minnrm, 100 * eps * fabs(pr * iw));
         }
         minnrm = wmax(minnrm);
         __syncwarp();
-        env_at(P, M, tnew, true);
+        PROF_END(PF_PREDICT);
+        PROF_BEGIN();
+        env_at(P, tnew, true);
+        PROF_END(PF_ENV);
         bool tooslow = false;
         for (int iter = 1; iter <= maxit; iter++) {
-          rhs_apply<false>(P, M, ynew, f0);
+          PROF_BEGIN();
+          rhs_apply(P, V_YNEW, V_F0, 0);
+          PROF_END(PF_RHS);
           if (!M.ap.tca_off) M.tca_shear_last = M.m.tca_shear_g;
-          M.st.fevals++;
+          if (threadIdx.x == 0) M.st.fevals++;
+          PROF_BEGIN();
           for (int i = lane; i < n; i += 32) del[i] = hinvGak * f0[i] - (psi[i] + difkp1[i]);
           __syncwarp();
-          lu_solve(M, n, ld, del);
-          M.st.solves++;
+          solve(P, del);
+          PROF_END(PF_SOLVE);
+          PROF_BEGIN();
           double newnrm = 0.0;
           for (int i = lane; i < n; i += 32) {
-            newnrm = fmax(newnrm, fabs(del[i] * invwt[i]));
-            difkp1[i] += del[i];
-            ynew[i] = pred[i] + difkp1[i];
+            const double d = del[i];
+            newnrm = fmax(newnrm, fabs(d * invwt[i]));
+            const double dk = difkp1[i] + d;
+            difkp1[i] = dk;
+            ynew[i] = pred[i] + dk;
           }
           newnrm = wmax(newnrm);
           __syncwarp();
+          PROF_END(PF_UPDATE);
           if (newnrm <= minnrm) { gotynew = true; break; }
           else if (iter == 1) {
             if (havrate) {
@@ -916,12 +1234,12 @@ __device__ bool ndf15(const PtParams& P, Mode& M, double t0, double tfinal, int*
           oldnrm = newnrm;
         }
         if (tooslow) {
-          M.st.failed++;
+          if (threadIdx.x == 0) M.st.failed++;
           if (!Jcurrent) {
-            env_at(P, M, t, true);
-            rhs_apply<false>(P, M, y, f0);
-            M.st.fevals++;
-            jacobian(P, M);
+            env_at(P, t, true);
+            rhs_apply(P, V_Y, V_F0, 0);
+            if (threadIdx.x == 0) M.st.fevals++;
+            jacobian(P);
             Jcurrent = true;
           } else if (absh <= hmin) {
             M.status = 2;  // step size too small
@@ -931,21 +1249,20 @@ __device__ bool ndf15(const PtParams& P, Mode& M, double t0, double tfinal, int*
             absh = fmax(0.3 * absh, hmin);
             h = absh;
             done = false;
-            adjust_stepsize(M, absh / abshlast, k);
-            hinvGak = h * invGa[k - 1];
+            adjust_stepsize(P, absh / abshlast, k);
+            hinvGak = h * c_invGa[k - 1];
             nconhk = 0;
           }
-          lu_factor(M, n, ld, hinvGak);
-          M.st.factorizations++;
+          factor(P, hinvGak);
           havrate = false;
         }
       }
       // error estimate
       err = 0.0;
       for (int i = lane; i < n; i += 32) err = fmax(err, fabs(difkp1[i] * invwt[i]));
-      err = wmax(err) * erconst[k - 1];
+      err = wmax(err) * c_erconst[k - 1];
       if (err > rtol) {
-        M.st.failed++;
+        if (threadIdx.x == 0) M.st.failed++;
         if (absh <= hmin) {
           M.status = 2;
           return false;
@@ -953,12 +1270,12 @@ __device__ bool ndf15(const PtParams& P, Mode& M, double t0, double tfinal, int*
         abshlast = absh;
         if (nofailed) {
           nofailed = false;
-          double hopt = absh * fmax(0.1, 0.833 * pow((rtol / err), (1.0 / (k + 1))));
+          double hopt = absh * fmax(0.1, 0.833 * root_n(rtol / err, k + 1.0));
           if (k > 1) {
             double errkm1 = 0.0;
             for (int i = lane; i < n; i += 32) errkm1 = fmax(errkm1, fabs((dif[(k - 1) * np + i] + difkp1[i]) * invwt[i]));
-            errkm1 = wmax(errkm1) * erconst[k - 2];
-            const double hkm1 = absh * fmax(0.1, 0.769 * pow((rtol / errkm1), (1.0 / k)));
+            errkm1 = wmax(errkm1) * c_erconst[k - 2];
+            const double hkm1 = absh * fmax(0.1, 0.769 * root_n(rtol / errkm1, (double)k));
             if (hkm1 > hopt) {
               hopt = fmin(absh, hkm1);
               k = k - 1;
@@ -970,77 +1287,88 @@ __device__ bool ndf15(const PtParams& P, Mode& M, double t0, double tfinal, int*
         }
         h = absh;
         if (absh < abshlast) done = false;
-        adjust_stepsize(M, absh / abshlast, k);
-        hinvGak = h * invGa[k - 1];
+        adjust_stepsize(P, absh / abshlast, k);
+        hinvGak = h * c_invGa[k - 1];
         nconhk = 0;
-        lu_factor(M, n, ld, hinvGak);
-        M.st.factorizations++;
+        factor(P, hinvGak);
         havrate = false;
       } else {
         break;
       }
     }
-    M.st.steps++;
+    if (threadIdx.x == 0) M.st.steps++;
+    PROF_BEGIN();
     // update the difference array
     for (int i = lane; i < n; i += 32) {
-      dif[(k + 1) * np + i] = difkp1[i] - dif[k * np + i];
-      dif[k * np + i] = difkp1[i];
-      for (int j = k - 1; j >= 0; j--) dif[j * np + i] += dif[(j + 1) * np + i];
+      const double dk = difkp1[i];
+      dif[(k + 1) * np + i] = dk - dif[k * np + i];
+      double acc = dk;
+      dif[k * np + i] = acc;
+      for (int j = k - 1; j >= 0; j--) {
+        acc += dif[j * np + i];
+        dif[j * np + i] = acc;
+      }
     }
     __syncwarp();
+    PROF_END(PF_DIFUPD);
+    PROF_BEGIN();
     // ---- output at the sample times passed by this step
-    while ((next < tres) && ((tnew - t_vec[next]) >= 0.0)) {
-      if (tnew == t_vec[next]) {
-        write_sources(P, M, t_vec[next], ynew, f0, next);
+    while ((next < tres) && ((tnew - tnext) >= 0.0)) {
+      if (tnew == tnext) {
+        write_sources(P, tnext, V_YNEW, V_F0, next);
       } else {
-        const double s = (t_vec[next] - tnew) / h;
-        double vecy[5], vecdy[5];
-        double prod = 1.0, sumfrac = 0., fact = 1.0;
-        for (int j = 0; j < k; j++) {
-          prod *= (s + j);
-          fact *= (j + 1);
-          sumfrac += 1.0 / (s + j);
-          vecy[j] = prod / fact;
-          vecdy[j] = prod * sumfrac / (h * fact);
-        }
+        const double s = (tnext - tnew) / h;
+        double* yi = s_vec(P, V_TMP);
+        double* ypi = s_vec(P, V_YPI);
         for (int i = lane; i < n; i += 32) {
           double a1 = 0, a2 = 0;
+          double prod = 1.0, sumfrac = 0., fact = 1.0;
           for (int j = 0; j < k; j++) {
-            a1 += vecy[j] * dif[j * np + i];
-            a2 += vecdy[j] * dif[j * np + i];
+            prod *= (s + j);
+            fact *= (j + 1);
+            sumfrac += 1.0 / (s + j);
+            const double d = dif[j * np + i];
+            a1 += prod / fact * d;
+            a2 += prod * sumfrac / (h * fact) * d;
           }
-          M.yi[i] = ynew[i] + a1;
-          M.ypi[i] = a2;
+          yi[i] = ynew[i] + a1;
+          ypi[i] = a2;
         }
         __syncwarp();
-        write_sources(P, M, t_vec[next], M.yi, M.ypi, next);
+        write_sources(P, tnext, V_TMP, V_YPI, next);
       }
       next++;
+      tnext = (next < tres) ? __ldg(t_vec + next) : 1e300;
     }
+    PROF_END(PF_OUTPUT);
     if (done) break;
+    PROF_BEGIN();
     klast = k;
     abshlast = absh;
     nconhk = min(nconhk + 1, maxk + 2);
     if (nconhk >= k + 2) {
-      double temp = 1.2 * pow((err / rtol), (1.0 / (k + 1.0)));
-      double hopt = (temp > 0.1) ? absh / temp : 10 * absh;
-      int kopt = k;
+      // candidate steps at orders k, k-1, k+1: the three norms by warp reductions, the three
+      // roots evaluated side by side in lanes 0..2
+      double e_km1 = 0., e_kp1 = 0.;
       if (k > 1) {
-        double errkm1 = 0.0;
-        for (int i = lane; i < n; i += 32) errkm1 = fmax(errkm1, fabs(dif[(k - 1) * np + i] * invwt[i]));
-        errkm1 = wmax(errkm1) * erconst[k - 2];
-        temp = 1.3 * pow((errkm1 / rtol), (1.0 / k));
-        const double hkm1 = (temp > 0.1) ? absh / temp : 10 * absh;
-        if (hkm1 > hopt) { hopt = hkm1; kopt = k - 1; }
+        for (int i = lane; i < n; i += 32) e_km1 = fmax(e_km1, fabs(dif[(k - 1) * np + i] * invwt[i]));
+        e_km1 = wmax(e_km1) * c_erconst[k - 2];
       }
       if (k < maxk) {
-        double errkp1 = 0.0;
-        for (int i = lane; i < n; i += 32) errkp1 = fmax(errkp1, fabs(dif[(k + 1) * np + i] * invwt[i]));
-        errkp1 = wmax(errkp1) * erconst[k];
-        temp = 1.4 * pow((errkp1 / rtol), (1.0 / (k + 2.0)));
-        const double hkp1 = (temp > 0.1) ? absh / temp : 10 * absh;
-        if (hkp1 > hopt) { hopt = hkp1; kopt = k + 1; }
+        for (int i = lane; i < n; i += 32) e_kp1 = fmax(e_kp1, fabs(dif[(k + 1) * np + i] * invwt[i]));
+        e_kp1 = wmax(e_kp1) * c_erconst[k];
       }
+      const double my_e = lane == 0 ? err : lane == 1 ? e_km1 : e_kp1;
+      const double my_c = lane == 0 ? 1.2 : lane == 1 ? 1.3 : 1.4;
+      const double my_n = lane == 0 ? k + 1.0 : lane == 1 ? (double)k : k + 2.0;
+      double temp = 0.;
+      if (my_e > 0.) temp = my_c * root_n(my_e / rtol, my_n);
+      const double my_h = (temp > 0.1) ? absh / temp : 10 * absh;
+      double hopt = __shfl_sync(PT_FULL, my_h, 0);
+      const double hkm1 = __shfl_sync(PT_FULL, my_h, 1), hkp1 = __shfl_sync(PT_FULL, my_h, 2);
+      int kopt = k;
+      if (k > 1 && hkm1 > hopt) { hopt = hkm1; kopt = k - 1; }
+      if (k < maxk && hkp1 > hopt) { hopt = hkp1; kopt = k + 1; }
       if (hopt > absh) {
         absh = hopt;
         if (k != kopt) k = kopt;
@@ -1050,30 +1378,33 @@ __device__ bool ndf15(const PtParams& P, Mode& M, double t0, double tfinal, int*
     for (int i = lane; i < n; i += 32) y[i] = ynew[i];
     __syncwarp();
     Jcurrent = false;
+    PROF_END(PF_CONTROL);
   }
   // final state: y <- ynew, and a last RHS call so that the environment and the TCA/RSA
   // by-products are current at the end of the interval (evolver_ndf15.cpp:653-662)
   for (int i = lane; i < n; i += 32) y[i] = ynew[i];
   __syncwarp();
-  env_at(P, M, tnew, true);
-  rhs_apply<false>(P, M, y, f0);
+  env_at(P, tnew, true);
+  rhs_apply(P, V_Y, V_F0, 0);
   if (!M.ap.tca_off) M.tca_shear_last = M.m.tca_shear_g;
-  M.st.fevals++;
-  *next_io = next;
+  if (threadIdx.x == 0) M.st.fevals++;
+  M.next = next;
   return true;
 }
 
 // ---------------------------------------------------------------------------------------------
 // perturb_initial_conditions: adiabatic mode, synchronous gauge, flat space
-__device__ void initial_conditions(const PtParams& P, Mode& M, double tau) {
-  env_at(P, M, tau, false);
+__device__ __noinline__ void initial_conditions(const PtParams& P, double tau) {
+  Mode& M = MODE(P);
+  env_at(P, tau, false);
   const Env& e = M.e;
   const Layout& L = M.L;
-  const int lane = M.lane;
+  const int lane = (int)threadIdx.x;
   const double k = M.k, a = e.a;
+  double* y = s_vec(P, V_Y);
   double rho_r = e.rho_g, rho_m = e.rho_b + e.rho_cdm, rho_nu = 0.;
   if (P.has_ur) { rho_r += e.rho_ur; rho_nu += e.rho_ur; }
-  for (int s = 0; s < P.N_ncdm; s++) { rho_r += M.pvb[P.irho_ncdm1 + s]; rho_nu += M.pvb[P.irho_ncdm1 + s]; }
+  for (int s = 0; s < P.N_ncdm; s++) { rho_r += s_pvb(P)[P.irho_ncdm1 + s]; rho_nu += s_pvb(P)[P.irho_ncdm1 + s]; }
   const double fracnu = rho_nu / rho_r;
   const double fracb = e.rho_b / rho_m;
   const double om = a * rho_m / sqrt(rho_r);
@@ -1088,47 +1419,52 @@ __device__ void initial_conditions(const PtParams& P, Mode& M, double tau) {
   const double l3_ur = ktau_three * 2. / 7. / (12. * fracnu + 45.) * ci;
   const double eta = ci * (1. - ktau_two / 12. / (15. + 4. * fracnu) *
                                     (5. + 4. * fracnu - (16. * fracnu * fracnu + 280. * fracnu + 325) / 10. / (2. * fracnu + 15.) * tau * om));
-  for (int i = lane; i < L.neq; i += 32) M.y[i] = 0.;
+  for (int i = lane; i < L.neq; i += 32) y[i] = 0.;
   __syncwarp();
   if (lane == 0) {
-    M.y[L.delta_g] = delta_g;
-    M.y[L.theta_g] = theta_g;
-    M.y[L.delta_b] = 3. / 4. * delta_g;
-    M.y[L.theta_b] = theta_g;
-    M.y[L.delta_cdm] = 3. / 4. * delta_g;
-    M.y[L.eta] = eta;
+    y[L.delta_g] = delta_g;
+    y[L.theta_g] = theta_g;
+    y[L.delta_b] = 3. / 4. * delta_g;
+    y[L.theta_b] = theta_g;
+    y[L.delta_cdm] = 3. / 4. * delta_g;
+    y[L.eta] = eta;
     if (P.has_ur) {
-      M.y[L.delta_ur] = delta_ur;
-      M.y[L.theta_ur] = theta_ur;
-      M.y[L.shear_ur] = shear_ur;
-      M.y[L.l3_ur] = l3_ur;
+      y[L.delta_ur] = delta_ur;
+      y[L.theta_ur] = theta_ur;
+      y[L.shear_ur] = shear_ur;
+      y[L.l3_ur] = l3_ur;
     }
   }
   if (P.has_ncdm) {
     const int stride = L.l_max_ncdm + 1;
     for (int s = 0; s < P.N_ncdm; s++) {
-      const double Ms = P.ncdm_M[s];
-      for (int iq = lane; iq < L.q_size_ncdm[s]; iq += 32) {
-        const int idx = L.ncdm_off[s] + iq * stride;
-        const double q = P.ncdm_q[P.ncdm_q_off[s] + iq];
-        const double dlnf0 = P.ncdm_dlnf0[P.ncdm_q_off[s] + iq];
+      const double Ms = M.C->ncdm_M[s];
+      const int nq = P.ncdm_q_size[s], off = L.psi0_ncdm1 + P.ncdm_q_off[s] * stride;
+      for (int iq = lane; iq < nq; iq += 32) {
+        const int idx = off + iq * stride;
+        const double q = M.C->ncdm_q[P.ncdm_q_off[s] + iq];
+        const double dlnf0 = M.C->ncdm_dlnf0[P.ncdm_q_off[s] + iq];
         const double eps = sqrt(q * q + a * a * Ms * Ms);
-        M.y[idx + 0] = -0.25 * delta_ur * dlnf0;
-        M.y[idx + 1] = -eps / 3. / q / k * theta_ur * dlnf0;
-        M.y[idx + 2] = -0.5 * shear_ur * dlnf0;
-        M.y[idx + 3] = -0.25 * l3_ur * dlnf0;
+        y[idx + 0] = -0.25 * delta_ur * dlnf0;
+        y[idx + 1] = -eps / 3. / q / k * theta_ur * dlnf0;
+        y[idx + 2] = -0.5 * shear_ur * dlnf0;
+        y[idx + 3] = -0.25 * l3_ur * dlnf0;
       }
     }
   }
   __syncwarp();
 }
 
-// perturb_vector_init (switching part): move the state from the old layout (in M.y) to the new one
-__device__ void remap_state(const PtParams& P, Mode& M, const Layout& Lo, const Approx& apo, const Layout& Ln,
-                            const Approx& apn) {
-  const int lane = M.lane;
-  double* yo = M.y;
-  double* yn = M.ynew;
+// perturb_vector_init (switching part): move the state from the old layout (in V_Y) to the new one
+__device__ __noinline__ void remap_state(const PtParams& P) {
+  Mode& M = MODE(P);
+  const Layout& Lo = M.Lprev;
+  const Layout& Ln = M.L;
+  const Approx& apo = M.apprev;
+  const Approx& apn = M.ap;
+  const int lane = (int)threadIdx.x;
+  double* yo = s_vec(P, V_Y);
+  double* yn = s_vec(P, V_YNEW);
   const double k = M.k;
   for (int i = lane; i < Ln.neq; i += 32) yn[i] = 0.;
   __syncwarp();
@@ -1154,11 +1490,11 @@ __device__ void remap_state(const PtParams& P, Mode& M, const Layout& Lo, const 
     }
   }
   if (Ln.shear_g >= 0 && Lo.shear_g >= 0) {
-    for (int l = 2 + lane; l <= Ln.l_max_g; l += 32) yn[Ln.delta_g + l] = yo[Lo.delta_g + l];
-    for (int l = lane; l <= Ln.l_max_pol_g; l += 32) yn[Ln.pol0_g + l] = yo[Lo.pol0_g + l];
+    for (int l = 2 + lane; l <= P.l_max_g; l += 32) yn[Ln.delta_g + l] = yo[Lo.delta_g + l];
+    for (int l = lane; l <= P.l_max_pol_g; l += 32) yn[Ln.pol0_g + l] = yo[Lo.pol0_g + l];
   }
   if (Ln.l3_ur >= 0 && Lo.l3_ur >= 0)
-    for (int l = 3 + lane; l <= Ln.l_max_ur; l += 32) yn[Ln.delta_ur + l] = yo[Lo.delta_ur + l];
+    for (int l = 3 + lane; l <= P.l_max_ur; l += 32) yn[Ln.delta_ur + l] = yo[Lo.delta_ur + l];
   if (P.has_ncdm) {
     if (apn.ncdmfa_on == apo.ncdmfa_on) {
       const int tot = Ln.eta - Ln.psi0_ncdm1;
@@ -1166,27 +1502,29 @@ __device__ void remap_state(const PtParams& P, Mode& M, const Layout& Lo, const 
     } else {
       // ncdm fluid approximation switched on: integrate the momentum hierarchy (:4478-4518)
       const double a = M.e.a;
+      const double a_rel = M.C->a_today / a, a_rel4 = (a_rel * a_rel) * (a_rel * a_rel);
       const int stride = Lo.l_max_ncdm + 1;
       for (int s = 0; s < P.N_ncdm; s++) {
-        const double rho_n = M.pvb[P.irho_ncdm1 + s], p_n = M.pvb[P.ip_ncdm1 + s];
-        const double factor = P.ncdm_factor[s] * pow(P.a_today / a, 4);
-        const double Ms = P.ncdm_M[s];
+        const double rho_n = s_pvb(P)[P.irho_ncdm1 + s], p_n = s_pvb(P)[P.ip_ncdm1 + s];
+        const double factor = M.C->ncdm_factor[s] * a_rel4;
+        const double Ms = M.C->ncdm_M[s];
+        const int off = Lo.psi0_ncdm1 + P.ncdm_q_off[s] * stride;
         double d = 0., th = 0., sh = 0.;
-        for (int iq = lane; iq < Lo.q_size_ncdm[s]; iq += 32) {
-          const int idx = Lo.ncdm_off[s] + iq * stride;
-          const double q = P.ncdm_q[P.ncdm_q_off[s] + iq], w0 = P.ncdm_w[P.ncdm_q_off[s] + iq];
-          const double eps = sqrt(q * q + a * a * Ms * Ms);
-          d += w0 * pow(q, 2) * eps * yo[idx];
-          th += w0 * pow(q, 3) * yo[idx + 1];
-          sh += w0 * pow(q, 4) / eps * yo[idx + 2];
+        for (int iq = lane; iq < P.ncdm_q_size[s]; iq += 32) {
+          const int idx = off + iq * stride;
+          const double q = M.C->ncdm_q[P.ncdm_q_off[s] + iq], w0 = M.C->ncdm_w[P.ncdm_q_off[s] + iq];
+          const double q2 = q * q, eps = sqrt(q2 + a * a * Ms * Ms);
+          d += w0 * q2 * eps * yo[idx];
+          th += w0 * q2 * q * yo[idx + 1];
+          sh += w0 * q2 * q2 / eps * yo[idx + 2];
         }
         d = wsum(d) * factor / rho_n;
         th = wsum(th) * k * factor / (rho_n + p_n);
         sh = wsum(sh) * 2. / 3. * factor / (rho_n + p_n);
         if (lane == 0) {
-          yn[Ln.ncdm_off[s]] = d;
-          yn[Ln.ncdm_off[s] + 1] = th;
-          yn[Ln.ncdm_off[s] + 2] = sh;
+          yn[Ln.psi0_ncdm1 + 3 * s] = d;
+          yn[Ln.psi0_ncdm1 + 3 * s + 1] = th;
+          yn[Ln.psi0_ncdm1 + 3 * s + 2] = sh;
         }
       }
     }
@@ -1197,49 +1535,56 @@ __device__ void remap_state(const PtParams& P, Mode& M, const Layout& Lo, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) perturb_kernel(const PtParams P) {
-  extern __shared__ double smem[];
+__global__ void __launch_bounds__(32) perturb_kernel(const __grid_constant__ PtParams P) {
   if ((int)blockIdx.x >= P.n_modes) return;
-  Mode M;
-  M.lane = threadIdx.x;
-  const int np = (P.neq_max + 31) & ~31;
-  M.neq_pad = np;
-  double* p = smem;
-  M.pvb = p; p += 32;
-  M.pvt = p; p += 32;
-  M.y = p; p += np; M.ynew = p; p += np; M.f0 = p; p += np; M.pred = p; p += np; M.psi = p; p += np;
-  M.difkp1 = p; p += np; M.del = p; p += np; M.invwt = p; p += np; M.tmp = p; p += np; M.yi = p; p += np;
-  M.ypi = p; p += np;
-  M.dif = p; p += 7 * np;
-  M.LU = p; p += (size_t)P.ld * P.neq_max;
-  M.piv = (int*)p;
-  M.J = P.jac + (size_t)blockIdx.x * P.neq_max * P.neq_max;
-  M.ik = P.order[blockIdx.x];
-  M.k = P.k[M.ik];
-  M.k2 = M.k * M.k;
-  M.cur_bg = 0; M.cur_th = P.tt_size - 2;
-  M.status = 0;
-  M.tca_shear_last = 0.;
-  memset(&M.st, 0, sizeof(M.st));
-  memset(&M.m, 0, sizeof(M.m));
-  const int lane = M.lane;
+  Mode& M = MODE(P);
+  const int lane = (int)threadIdx.x;
+  const int2 md = P.modes[blockIdx.x];
+  const PtCosmo* C = P.cosmo + md.x;
+  if (lane == 0) {
+    M.Jhh = P.hub_jac + (size_t)blockIdx.x * P.nh_max * P.nh_max;
+    M.C = C;
+    M.ik = md.y;
+    M.k = C->k[md.y];
+    M.k2 = M.k * M.k;
+    M.inv_k = 1.0 / M.k;
+    M.inv_k2 = 1.0 / M.k2;
+    M.cur_bg = 0; M.cur_th = C->tt_size - 2;
+    M.bx0 = 1.; M.bx1 = 0.; M.tx0 = 1.; M.tx1 = 0.;
+    M.need_nw = 0;
+    M.nh = 0; M.nch = 0;
+    M.status = 0;
+    M.next = 0;
+    M.tca_shear_last = 0.;
+    M.st = Stat{};
+    M.m = Metric{};
+    M.ap.tca_off = M.ap.rsa_on = M.ap.ufa_on = M.ap.ncdmfa_on = 0;
+    for (int q = 0; q < PF_COUNT; q++) M.prof[q] = 0;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) { M.bc[q][lane] = 0.; M.tc[q][lane] = 0.; }
+  for (int l = lane; l < P.n_i2l1; l += 32) s_i2l1(P)[l] = 1.0 / (2.0 * l + 1.0);
+  __syncwarp();
+  const double tau_first = C->tau[0];
+  const int tau_size = C->tau_size;
 
   // ---- start time: bisection on (tau_c/tau_h, tau_h/tau_k, ncdm still relativistic)  (:2592-2635)
-  double tau_lower = P.bg_tau[0], tau_upper = P.tau[0];
+  double tau_lower = C->bg_tau[0], tau_upper = tau_first;
+  int status = 0;
   {
-    env_at(P, M, tau_lower, false);
-    if (M.e.a * M.e.H / M.e.dkappa > P.start_small_k_at_tau_c_over_tau_h) M.status = 3;
-    if (M.k / M.e.a / M.e.H > P.start_large_k_at_tau_h_over_tau_k) M.status = 4;
+    env_at(P, tau_lower, false);
+    if (M.e.a * M.e.H / M.e.dkappa > P.start_small_k_at_tau_c_over_tau_h) status = 3;
+    if (M.k / M.e.a / M.e.H > P.start_large_k_at_tau_h_over_tau_k) status = 4;
     for (int s = 0; s < P.N_ncdm; s++)
-      if (fabs(M.pvb[P.ip_ncdm1 + s] / M.pvb[P.irho_ncdm1 + s] - 1. / 3.) > P.tol_ncdm_initial_w) M.status = 5;
+      if (fabs(s_pvb(P)[P.ip_ncdm1 + s] / s_pvb(P)[P.irho_ncdm1 + s] - 1. / 3.) > P.tol_ncdm_initial_w) status = 5;
   }
   double tau_mid = 0.5 * (tau_lower + tau_upper);
-  if (M.status == 0) {
+  if (status == 0) {
     while ((tau_upper - tau_lower) / tau_lower > P.tol_tau_approx) {
-      env_at(P, M, tau_mid, false);
+      env_at(P, tau_mid, false);
       bool early = true;
       for (int s = 0; s < P.N_ncdm; s++)
-        if (fabs(M.pvb[P.ip_ncdm1 + s] / M.pvb[P.irho_ncdm1 + s] - 1. / 3.) > P.tol_ncdm_initial_w) early = false;
+        if (fabs(s_pvb(P)[P.ip_ncdm1 + s] / s_pvb(P)[P.irho_ncdm1 + s] - 1. / 3.) > P.tol_ncdm_initial_w) early = false;
       if (early) {
         if ((M.e.a * M.e.H / M.e.dkappa > P.start_small_k_at_tau_c_over_tau_h) ||
             (M.k / M.e.a / M.e.H > P.start_large_k_at_tau_h_over_tau_k))
@@ -1250,133 +1595,123 @@ __global__ void __launch_bounds__(32) perturb_kernel(const PtParams P) {
     }
   }
   const double tau_ini = tau_mid;
-  const double tau_end = P.tau[P.tau_size - 1];
-  M.st.tau_ini = tau_ini;
+  const double tau_end = C->tau[tau_size - 1];
 
-  // ---- schedule of approximation switches (:2940-3231)
-  double limit[PT_MAX_INTERVALS + 1];
-  Approx sched[PT_MAX_INTERVALS];
+  // ---- schedule of approximation switches (:2940-3231); every lane computes the same values
   int n_int = 1;
-  if (M.status == 0) {
-    const Approx a_ini = approximations_at(P, M, tau_ini);
-    const Approx a_end = approximations_at(P, M, tau_end);
-    double sw[4];
+  if (status == 0) {
+    const Approx a_ini = approximations_at(P, tau_ini);
+    const Approx a_end = approximations_at(P, tau_end);
     int nsw = 0;
     for (int w = 0; w < 4; w++) {
       const int f0 = approx_flag(a_ini, w), f1 = approx_flag(a_end, w);
-      if (f1 < f0) { M.status = 6; break; }
+      if (f1 < f0) { status = 6; break; }
       if (f1 > f0) {
         double lo = tau_ini, hi = tau_end, mid = 0.5 * (lo + hi);
         while (hi - lo > P.tol_tau_approx) {
-          const Approx am = approximations_at(P, M, mid);
+          const Approx am = approximations_at(P, mid);
           if (approx_flag(am, w) > f0) hi = mid; else lo = mid;
           mid = 0.5 * (lo + hi);
         }
-        sw[nsw++] = mid;
+        M.sw[nsw++] = mid;
       }
     }
+    __syncwarp();
     n_int = nsw + 1;
-    limit[0] = tau_ini;
+    M.limit[0] = tau_ini;
     for (int i = 1; i < n_int; i++) {
       double nxt = tau_end;
       for (int j = 0; j < nsw; j++)
-        if ((sw[j] > limit[i - 1]) && (sw[j] < nxt)) nxt = sw[j];
-      limit[i] = nxt;
+        if ((M.sw[j] > M.limit[i - 1]) && (M.sw[j] < nxt)) nxt = M.sw[j];
+      M.limit[i] = nxt;
     }
-    limit[n_int] = tau_end;
-    sched[0] = a_ini;
-    for (int i = 1; i < n_int && M.status == 0; i++) {
-      sched[i] = approximations_at(P, M, 0.5 * (limit[i] + limit[i + 1]));
+    M.limit[n_int] = tau_end;
+    M.sched[0] = a_ini;
+    for (int i = 1; i < n_int && status == 0; i++) {
+      const Approx ai = approximations_at(P, 0.5 * (M.limit[i] + M.limit[i + 1]));
+      const Approx ap = M.sched[i - 1];
+      M.sched[i] = ai;
       int nchange = 0;
       for (int w = 0; w < 4; w++) {
-        if (approx_flag(sched[i], w) < approx_flag(sched[i - 1], w)) M.status = 6;
-        if (approx_flag(sched[i], w) != approx_flag(sched[i - 1], w)) nchange++;
+        if (approx_flag(ai, w) < approx_flag(ap, w)) status = 6;
+        if (approx_flag(ai, w) != approx_flag(ap, w)) nchange++;
       }
-      if (nchange != 1) M.status = 7;
+      if (nchange != 1) status = 7;
     }
-    if (a_ini.tca_off || a_ini.rsa_on || a_ini.ufa_on || a_ini.ncdmfa_on) M.status = 8;
+    if (a_ini.tca_off || a_ini.rsa_on || a_ini.ufa_on || a_ini.ncdmfa_on) status = 8;
   }
-  M.st.intervals = n_int;
+  M.status = status;
+  __syncwarp();
+  clpp_kstat* ks = C->kstat + md.y;
 
   // ---- integrate interval by interval
-  int next = 0;
-  for (int iv = 0; iv < n_int && M.status == 0; iv++) {
-    const Approx apn = sched[iv];
-    const Layout Ln = make_layout(P, apn);
-    if (iv == 0) {
-      M.ap = apn;
-      M.L = Ln;
-      initial_conditions(P, M, limit[0]);
-    } else {
-      const Layout Lo = M.L;
-      const Approx apo = M.ap;
-      remap_state(P, M, Lo, apo, Ln, apn);
-      M.ap = apn;
-      M.L = Ln;
+  for (int iv = 0; iv < n_int && status == 0; iv++) {
+    const Approx apn = M.sched[iv];
+    __syncwarp();
+    M.Lprev = M.L;
+    M.apprev = M.ap;
+    __syncwarp();
+    M.ap = apn;
+    make_layout(P, apn, M.L);
+    __syncwarp();
+    if (iv == 0) initial_conditions(P, M.limit[0]);
+    else remap_state(P);
+    make_structure(P);
+    M.need_nw = P.has_ncdm && !apn.ncdmfa_on;
+    M.bx0 = 1.; M.bx1 = 0.;  // the first lookup of the interval refreshes everything
+    __syncwarp();
+    const long long c0 = clock64();
+    const int s0 = M.st.steps;
+    const bool ok = ndf15(P, M.limit[iv], M.limit[iv + 1]);
+    __syncwarp();
+    if (lane == 0) {
+      ks->iv_neq[iv] = M.L.neq;
+      ks->iv_steps[iv] = M.st.steps - s0;
+      ks->iv_cycles[iv] = clock64() - c0;
+#ifdef PT_PROF
+      for (int q = 0; q < PF_COUNT; q++) { ks->prof[iv * 12 + q] = M.prof[q]; M.prof[q] = 0; }
+#endif
     }
-    if (!ndf15(P, M, limit[iv], limit[iv + 1], &next)) break;
+    __syncwarp();
+    status = M.status;
+    if (!ok) break;
   }
   // zero-fill the samples that were not reached (failure only; normally next == tau_size)
   if (lane == 0) {
-    const size_t stride_tp = (size_t)P.k_size * P.tau_size;
-    double* out = P.sources + (size_t)M.ik * P.tau_size;
+    const size_t stride_tp = (size_t)C->k_size * tau_size;
+    double* out = C->sources + (size_t)md.y * tau_size;
     const int tps[7] = {P.tp_t0, P.tp_t1, P.tp_t2, P.tp_p, P.tp_delta_m, P.tp_delta_cb, P.tp_phi_plus_psi};
-    for (int it = next; it < P.tau_size; it++)
+    for (int it = M.next; it < tau_size; it++)
       for (int j = 0; j < 7; j++)
         if (tps[j] >= 0) out[tps[j] * stride_tp + it] = 0.;
-    M.st.status = M.status;
-    P.kstat[M.ik] = M.st;
+    ks->steps = M.st.steps; ks->failed = M.st.failed; ks->fevals = M.st.fevals; ks->jacobians = M.st.jacobians;
+    ks->factorizations = M.st.factorizations; ks->solves = M.st.solves;
+    ks->intervals = n_int; ks->status = status; ks->tau_ini = tau_ini;
   }
 }
 
-// ---------------------------------------------------------------------------------------------
+// =============================================================================================
+// host side
+// =============================================================================================
 template <typename T>
-static int dev_alloc(T** p, size_t n, char* err) {
-  if (*p) { cudaFree(*p); *p = nullptr; }
-  CLPP_CUDA(cudaMalloc((void**)p, n * sizeof(T)), err);
+static int dev_reserve(T** p, size_t* cap, size_t n, char* err) {
+  if (*p && *cap >= n) return CLPP_SUCCESS;
+  if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+  CLPP_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)), err);
+  *cap = n;
   return CLPP_SUCCESS;
 }
 
-int clpp_dev_perturb_solve(clpp_ctx* c, int k_begin, int k_end, char* err) {
-  clpp_ctx::Dev* d = c->dev;
+// settings shared by every cosmology of a batch (pointers and geometry are filled by the caller)
+static int fill_common(const clpp_ctx* c, PtParams& P, char* err) {
   const clpp_perturb_desc& pd = c->pd;
   const clpp_background_desc& bg = c->bg;
   const clpp_thermo_desc& th = c->th;
   const clpp_perturb_info& I = c->pinfo;
-  cudaStream_t st = d->stream;
+  memset(&P, 0, sizeof(P));
   CLPP_CHECK(c->N_ncdm <= PT_MAX_NCDM, err, "at most %d ncdm species are supported on the device", PT_MAX_NCDM);
   CLPP_CHECK(bg.bg_size_normal <= 32 && th.th_size <= 32, err, "background/thermo vectors wider than a warp");
-
-  const int nk = I.k_size, nt = I.tau_size, ntp = I.tp_size;
-  const size_t nsrc = (size_t)ntp * nk * nt;
-  if (!d->sources || d->sources_count != nsrc) {
-    if (dev_alloc(&d->sources, nsrc, err)) return CLPP_FAILURE;
-    d->sources_count = nsrc;
-    CLPP_CUDA(cudaMemsetAsync(d->sources, 0, nsrc * sizeof(double), st), err);
-  }
-  if (dev_alloc(&d->k, nk, err) || dev_alloc(&d->tau, nt, err) || dev_alloc(&d->kstat, nk, err)) return CLPP_FAILURE;
-  CLPP_CUDA(cudaMemcpyAsync(d->k, c->k.data(), nk * sizeof(double), cudaMemcpyHostToDevice, st), err);
-  CLPP_CUDA(cudaMemcpyAsync(d->tau, c->tau.data(), nt * sizeof(double), cudaMemcpyHostToDevice, st), err);
-  CLPP_CUDA(cudaMemsetAsync(d->kstat, 0, nk * sizeof(clpp_kstat), st), err);
-
-  // ncdm arrays
-  double *d_q = nullptr, *d_w = nullptr, *d_dl = nullptr;
-  if (c->N_ncdm > 0) {
-    const size_t tot = c->ncdm_q.size();
-    CLPP_CUDA(cudaMalloc((void**)&d_q, 3 * tot * sizeof(double)), err);
-    d_w = d_q + tot;
-    d_dl = d_w + tot;
-    CLPP_CUDA(cudaMemcpyAsync(d_q, c->ncdm_q.data(), tot * sizeof(double), cudaMemcpyHostToDevice, st), err);
-    CLPP_CUDA(cudaMemcpyAsync(d_w, c->ncdm_w.data(), tot * sizeof(double), cudaMemcpyHostToDevice, st), err);
-    CLPP_CUDA(cudaMemcpyAsync(d_dl, c->ncdm_dlnf0.data(), tot * sizeof(double), cudaMemcpyHostToDevice, st), err);
-  }
-
-  PtParams P;
-  memset(&P, 0, sizeof(P));
-  P.bg_tau = d->bg_tau; P.bg_y = d->bg_y; P.bg_dd = d->bg_dd;
-  P.bt_size = bg.bt_size; P.bg_size = bg.bg_size; P.bg_size_normal = bg.bg_size_normal;
-  P.th_z = d->th_z; P.th_y = d->th_y; P.th_dd = d->th_dd;
-  P.tt_size = th.tt_size; P.th_size = th.th_size;
+  P.bg_size = bg.bg_size; P.bg_size_normal = bg.bg_size_normal; P.th_size = th.th_size;
   P.ia = bg.index_bg_a; P.iH = bg.index_bg_H; P.iHp = bg.index_bg_H_prime;
   P.irho_g = bg.index_bg_rho_g; P.irho_b = bg.index_bg_rho_b; P.irho_cdm = bg.index_bg_rho_cdm;
   P.irho_ur = bg.index_bg_rho_ur; P.irho_ncdm1 = bg.index_bg_rho_ncdm1; P.ip_ncdm1 = bg.index_bg_p_ncdm1;
@@ -1387,22 +1722,14 @@ int clpp_dev_perturb_solve(clpp_ctx* c, int k_begin, int k_end, char* err) {
   P.iTb = th.index_th_Tb; P.itau_d = th.index_th_tau_d; P.irate = th.index_th_rate; P.ir_d = th.index_th_r_d;
   P.idcb2 = th.index_th_dcb2; P.iddcb2 = th.index_th_ddcb2;
   P.compute_cb2_derivatives = th.compute_cb2_derivatives; P.compute_damping_scale = th.compute_damping_scale;
-  P.th_linear_below_z = -1.;
-  if (th.reio_parametrization == CLPP_REIO_HALF_TANH) P.th_linear_below_z = 2 * th.z_reionization;
-  if (th.reio_parametrization == CLPP_REIO_INTER) P.th_linear_below_z = 50.;
-  P.n_e = th.n_e; P.YHe = th.YHe; P.T_cmb = bg.T_cmb; P.tau_free_streaming = th.tau_free_streaming;
   P.has_ur = bg.has_ur; P.has_ncdm = bg.has_ncdm; P.N_ncdm = bg.has_ncdm ? bg.N_ncdm : 0;
-  int off = 0, nq_tot_l = 0;
+  int off = 0;
   for (int s = 0; s < P.N_ncdm; s++) {
     P.ncdm_q_size[s] = c->ncdm_q_size[s];
     P.ncdm_q_off[s] = off;
     off += c->ncdm_q_size[s];
-    P.ncdm_M[s] = c->ncdm_M[s];
-    P.ncdm_factor[s] = c->ncdm_factor[s];
-    nq_tot_l += c->ncdm_q_size[s] * (pd.l_max_ncdm + 1);
   }
-  P.ncdm_q = d_q; P.ncdm_w = d_w; P.ncdm_dlnf0 = d_dl;
-  P.a_today = bg.a_today;
+  P.nq_tot = off;
   P.start_small_k_at_tau_c_over_tau_h = pd.start_small_k_at_tau_c_over_tau_h;
   P.start_large_k_at_tau_h_over_tau_k = pd.start_large_k_at_tau_h_over_tau_k;
   P.tca_trigger_tau_c_over_tau_h = pd.tight_coupling_trigger_tau_c_over_tau_h;
@@ -1417,62 +1744,172 @@ int clpp_dev_perturb_solve(clpp_ctx* c, int k_begin, int k_end, char* err) {
   P.curvature_ini = pd.curvature_ini; P.three_ceff2_ur = pd.three_ceff2_ur; P.three_cvis2_ur = pd.three_cvis2_ur;
   P.switch_sw = pd.switch_sw; P.switch_eisw = pd.switch_eisw; P.switch_lisw = pd.switch_lisw;
   P.switch_dop = pd.switch_dop; P.switch_pol = pd.switch_pol; P.eisw_lisw_split_z = pd.eisw_lisw_split_z;
-  P.k = d->k; P.k_size = nk; P.tau = d->tau; P.tau_size = nt; P.sources = d->sources;
   P.tp_t0 = I.index_tp_t0; P.tp_t1 = I.index_tp_t1; P.tp_t2 = I.index_tp_t2; P.tp_p = I.index_tp_p;
   P.tp_delta_m = I.index_tp_delta_m; P.tp_delta_cb = I.index_tp_delta_cb; P.tp_phi_plus_psi = I.index_tp_phi_plus_psi;
 
-  // largest state vector over the approximation phases (full hierarchy, everything off)
+  // largest state vector over the approximation phases (full hierarchy, everything off) and its hub block
   int neq_max = 2 + 1 + (pd.l_max_g - 2) + (pd.l_max_pol_g + 1) + 3 + 1;
-  if (bg.has_ur) neq_max += 3 + (pd.l_max_ur - 2);
-  neq_max += nq_tot_l;
+  int nh_max = 3 + 3 + 3 + 1;
+  int n_chains = 2;
+  if (bg.has_ur) { neq_max += 3 + (pd.l_max_ur - 2); nh_max += 3; n_chains++; }
+  neq_max += P.nq_tot * (pd.l_max_ncdm + 1);
+  nh_max += 3 * P.nq_tot;
+  n_chains += P.nq_tot;
+  CLPP_CHECK(n_chains <= PT_MAX_CHAINS, err,
+             "%d multipole hierarchies (photons, ur, ncdm momentum bins) exceed the %d chains a warp handles: reduce "
+             "the number of ncdm momentum bins", n_chains, PT_MAX_CHAINS);
+  CLPP_CHECK(nh_max <= 128, err, "%d hub variables exceed the 128 a warp handles: reduce the number of ncdm momentum bins",
+             nh_max);
   P.neq_max = neq_max;
-  P.ld = neq_max | 1;
-  const int np = (neq_max + 31) & ~31;
-  const size_t smem = (size_t)(64 + 18 * np + (size_t)P.ld * neq_max) * sizeof(double) + (size_t)np * sizeof(int);
+  P.np = (neq_max + 1) & ~1;
+  P.nh_max = nh_max;
+  P.ldh = nh_max | 1;
+  P.o_mode = 64;
+  P.o_hubtmp = P.o_mode + (int)((sizeof(Mode) + 7) / 8);
+  P.o_nw = P.o_hubtmp + std::max(nh_max, 32);
+  P.o_i2l1 = P.o_nw + 4 * ((P.nq_tot + 1) & ~1);
+  P.n_i2l1 = (std::max(std::max(pd.l_max_g, pd.l_max_pol_g), std::max(pd.l_max_ur, pd.l_max_ncdm)) + 2 + 1) & ~1;
+  P.o_vec = P.o_i2l1 + P.n_i2l1;
+  P.o_sinv = P.o_vec + V_COUNT * P.np;
+  P.o_int = P.o_sinv + ((P.nh_max * P.ldh + 1) & ~1);
+  return CLPP_SUCCESS;
+}
+
+static size_t perturb_smem_bytes(const PtParams& P) {
+  return (size_t)P.o_int * sizeof(double) + (size_t)(2 * P.nh_max + 3 * PT_MAX_CHAINS) * sizeof(int);
+}
+
+// Integrates modes [k_begin[i], k_end[i]) of every context in ONE kernel launch on the stream of
+// the first context (all contexts must live on the same device).
+int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, const int* k_end, char* err) {
+  CLPP_CHECK(n_ctx >= 1, err, "empty batch");
+  clpp_ctx* c0 = cs[0];
+  clpp_ctx::Dev* d0 = c0->dev;
+  cudaStream_t st = d0->stream;
+  PtParams P;
+  if (fill_common(c0, P, err)) return CLPP_FAILURE;
+  for (int b = 1; b < n_ctx; b++) {
+    CLPP_CHECK(cs[b]->dev && cs[b]->device == c0->device, err, "all contexts of a batch must live on the same CUDA device");
+    PtParams Q;
+    if (fill_common(cs[b], Q, err)) return CLPP_FAILURE;
+    CLPP_CHECK(memcmp(&P, &Q, sizeof(P)) == 0, err,
+               "cosmology %d of the batch differs from cosmology 0 in the precision settings / species content / "
+               "requested sources: such cosmologies must be solved in separate batches", b);
+  }
+
+  std::vector<PtCosmo> cosmo(n_ctx);
+  std::vector<int2> modes;
+  std::vector<double> cost;
+  for (int b = 0; b < n_ctx; b++) {
+    clpp_ctx* c = cs[b];
+    clpp_ctx::Dev* d = c->dev;
+    const clpp_perturb_info& I = c->pinfo;
+    const int nk = I.k_size, nt = I.tau_size, ntp = I.tp_size;
+    const size_t nsrc = (size_t)ntp * nk * nt;
+    cudaStream_t sb = d->stream;
+    if (!d->sources || d->sources_count != nsrc) {
+      if (d->sources) { cudaFree(d->sources); d->sources = nullptr; }
+      CLPP_CUDA(cudaMalloc((void**)&d->sources, nsrc * sizeof(double)), err);
+      d->sources_count = nsrc;
+      CLPP_CUDA(cudaMemsetAsync(d->sources, 0, nsrc * sizeof(double), sb), err);
+    }
+    if (dev_reserve(&d->k, &d->k_cap, nk, err) || dev_reserve(&d->tau, &d->tau_cap, nt, err) ||
+        dev_reserve(&d->kstat, &d->kstat_cap, nk, err))
+      return CLPP_FAILURE;
+    CLPP_CUDA(cudaMemcpyAsync(d->k, c->k.data(), nk * sizeof(double), cudaMemcpyHostToDevice, sb), err);
+    CLPP_CUDA(cudaMemcpyAsync(d->tau, c->tau.data(), nt * sizeof(double), cudaMemcpyHostToDevice, sb), err);
+    CLPP_CUDA(cudaMemsetAsync(d->kstat, 0, nk * sizeof(clpp_kstat), sb), err);
+    const size_t tot = c->ncdm_q.size();
+    if (c->N_ncdm > 0) {
+      if (dev_reserve(&d->ncdm, &d->ncdm_cap, 3 * tot, err)) return CLPP_FAILURE;
+      CLPP_CUDA(cudaMemcpyAsync(d->ncdm, c->ncdm_q.data(), tot * sizeof(double), cudaMemcpyHostToDevice, sb), err);
+      CLPP_CUDA(cudaMemcpyAsync(d->ncdm + tot, c->ncdm_w.data(), tot * sizeof(double), cudaMemcpyHostToDevice, sb), err);
+      CLPP_CUDA(cudaMemcpyAsync(d->ncdm + 2 * tot, c->ncdm_dlnf0.data(), tot * sizeof(double), cudaMemcpyHostToDevice, sb), err);
+    }
+    PtCosmo& Q = cosmo[b];
+    memset(&Q, 0, sizeof(Q));
+    Q.bg_tau = d->bg_tau; Q.bg_y = d->bg_y; Q.bg_dd = d->bg_dd;
+    Q.th_z = d->th_z; Q.th_y = d->th_y; Q.th_dd = d->th_dd;
+    Q.ncdm_q = d->ncdm; Q.ncdm_w = d->ncdm ? d->ncdm + tot : nullptr; Q.ncdm_dlnf0 = d->ncdm ? d->ncdm + 2 * tot : nullptr;
+    Q.k = d->k; Q.tau = d->tau; Q.sources = d->sources; Q.kstat = d->kstat;
+    Q.bt_size = c->bg.bt_size; Q.tt_size = c->th.tt_size; Q.k_size = nk; Q.tau_size = nt;
+    Q.th_linear_below_z = -1.;
+    if (c->th.reio_parametrization == CLPP_REIO_HALF_TANH) Q.th_linear_below_z = 2 * c->th.z_reionization;
+    if (c->th.reio_parametrization == CLPP_REIO_INTER) Q.th_linear_below_z = 50.;
+    Q.n_e = c->th.n_e; Q.YHe = c->th.YHe; Q.T_cmb = c->bg.T_cmb; Q.tau_free_streaming = c->th.tau_free_streaming;
+    Q.a_today = c->bg.a_today;
+    for (int s = 0; s < P.N_ncdm; s++) { Q.ncdm_M[s] = c->ncdm_M[s]; Q.ncdm_factor[s] = c->ncdm_factor[s]; }
+    for (int ik = k_begin[b]; ik < k_end[b]; ik++) {
+      modes.push_back(make_int2(b, ik));
+      cost.push_back(c->k[ik]);  // the number of steps of a mode grows with k tau_0
+    }
+    if (b > 0) CLPP_CUDA(cudaStreamSynchronize(sb), err);  // uploads of the other contexts' streams
+  }
+  // issue order: decreasing expected cost (longest chains first), across the whole batch
+  const int n_modes = (int)modes.size();
+  std::vector<int> perm(n_modes);
+  for (int i = 0; i < n_modes; i++) perm[i] = i;
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  std::vector<int2> sorted(n_modes);
+  for (int i = 0; i < n_modes; i++) sorted[i] = modes[perm[i]];
+
+  if (dev_reserve(&d0->pt_cosmo, &d0->pt_cosmo_cap, n_ctx * sizeof(PtCosmo), err)) return CLPP_FAILURE;
+  if (dev_reserve(&d0->pt_modes, &d0->pt_modes_cap, (size_t)std::max(n_modes, 1) * sizeof(int2), err)) return CLPP_FAILURE;
+  if (dev_reserve(&d0->jac_scratch, &d0->jac_cap, (size_t)std::max(n_modes, 1) * P.nh_max * P.nh_max, err))
+    return CLPP_FAILURE;
+  CLPP_CUDA(cudaMemcpyAsync(d0->pt_cosmo, cosmo.data(), n_ctx * sizeof(PtCosmo), cudaMemcpyHostToDevice, st), err);
+  CLPP_CUDA(cudaMemcpyAsync(d0->pt_modes, sorted.data(), n_modes * sizeof(int2), cudaMemcpyHostToDevice, st), err);
+  P.cosmo = (const PtCosmo*)d0->pt_cosmo;
+  P.modes = (const int2*)d0->pt_modes;
+  P.n_modes = n_modes;
+  P.hub_jac = d0->jac_scratch;
+
+  const size_t smem = perturb_smem_bytes(P);
   CLPP_CHECK(smem <= 227 * 1024, err,
              "state vector of %d equations needs %zu bytes of shared memory per k-mode (> 227 KB): reduce l_max_ncdm / "
-             "the number of ncdm momentum bins", neq_max, smem);
-
-  // mode order: decreasing k (the expensive modes first)
-  const int n_modes = k_end - k_begin;
-  std::vector<int> order(n_modes);
-  for (int i = 0; i < n_modes; i++) order[i] = k_end - 1 - i;
-  if (dev_alloc(&d->k_order, std::max(n_modes, 1), err)) return CLPP_FAILURE;
-  CLPP_CUDA(cudaMemcpyAsync(d->k_order, order.data(), n_modes * sizeof(int), cudaMemcpyHostToDevice, st), err);
-  if (dev_alloc(&d->jac_scratch, (size_t)std::max(n_modes, 1) * neq_max * neq_max, err)) return CLPP_FAILURE;
-  P.order = d->k_order; P.n_modes = n_modes; P.kstat = d->kstat; P.jac = d->jac_scratch;
-
+             "the number of ncdm momentum bins", P.neq_max, smem);
   CLPP_CUDA(cudaFuncSetAttribute(perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
-  cudaEventRecord(d->ev[0], st);
+  cudaEventRecord(d0->ev[0], st);
   if (n_modes > 0) {
     perturb_kernel<<<n_modes, 32, smem, st>>>(P);
-    c->launches++;
+    c0->launches++;
   }
-  cudaEventRecord(d->ev[1], st);
+  cudaEventRecord(d0->ev[1], st);
   CLPP_CUDA(cudaGetLastError(), err);
-  c->kstat.assign(nk, clpp_kstat{});
-  CLPP_CUDA(cudaMemcpyAsync(c->kstat.data(), d->kstat, nk * sizeof(clpp_kstat), cudaMemcpyDeviceToHost, st), err);
+  for (int b = 0; b < n_ctx; b++) {
+    clpp_ctx* c = cs[b];
+    const int nk = c->pinfo.k_size;
+    c->kstat.assign(nk, clpp_kstat{});
+    CLPP_CUDA(cudaMemcpyAsync(c->kstat.data(), c->dev->kstat, nk * sizeof(clpp_kstat), cudaMemcpyDeviceToHost, st), err);
+  }
   CLPP_CUDA(cudaStreamSynchronize(st), err);
   {
     float ms = 0;
-    cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]);
-    d->t_perturb_ms = ms;
+    cudaEventElapsedTime(&ms, d0->ev[0], d0->ev[1]);
+    for (int b = 0; b < n_ctx; b++) cs[b]->dev->t_perturb_ms = 0.;
+    d0->t_perturb_ms = ms;
   }
-  if (d_q) cudaFree(d_q);
-  for (int ik = k_begin; ik < k_end; ik++) {
-    const int s = c->kstat[ik].status;
-    if (s != 0) {
-      const char* what = s == 2 ? "Step size too small in the NDF15 evolver"
-                       : s == 3 ? "your choice of initial time for integrating wavenumbers is inappropriate: it corresponds to a time before that at which the background has been integrated. You should increase 'start_small_k_at_tau_c_over_tau_h'"
-                       : s == 4 ? "your choice of initial time for integrating wavenumbers is inappropriate: it corresponds to a time before that at which the background has been integrated. You should increase 'start_large_k_at_tau_h_over_tau_k'"
-                       : s == 5 ? "your choice of initial time for integrating wavenumbers is inappropriate: ncdm species not ultra-relativistic"
-                       : s == 6 ? "an approximation flag goes backward in time, this cannot be handled"
-                       : s == 7 ? "you switch several approximations at the same time, this cannot be handled"
-                       : s == 8 ? "scalar initial conditions assume tight coupling on and all other approximations off"
-                                : "unknown device error";
-      return clpp_fail(err, "perturb_solve failed for k=%e (index %d): %s", c->k[ik], ik, what);
+  for (int b = 0; b < n_ctx; b++) {
+    clpp_ctx* c = cs[b];
+    for (int ik = k_begin[b]; ik < k_end[b]; ik++) {
+      const int s = c->kstat[ik].status;
+      if (s != 0) {
+        const char* what = s == 2 ? "Step size too small in the NDF15 evolver"
+                         : s == 3 ? "your choice of initial time for integrating wavenumbers is inappropriate: it corresponds to a time before that at which the background has been integrated. You should increase 'start_small_k_at_tau_c_over_tau_h'"
+                         : s == 4 ? "your choice of initial time for integrating wavenumbers is inappropriate: it corresponds to a time before that at which the background has been integrated. You should increase 'start_large_k_at_tau_h_over_tau_k'"
+                         : s == 5 ? "your choice of initial time for integrating wavenumbers is inappropriate: ncdm species not ultra-relativistic"
+                         : s == 6 ? "an approximation flag goes backward in time, this cannot be handled"
+                         : s == 7 ? "you switch several approximations at the same time, this cannot be handled"
+                         : s == 8 ? "scalar initial conditions assume tight coupling on and all other approximations off"
+                                  : "unknown device error";
+        return clpp_fail(err, "perturb_solve failed for k=%e (index %d, cosmology %d of the batch): %s", c->k[ik], ik, b, what);
+      }
     }
+    c->has_sources = true;
   }
-  c->has_sources = true;
   return CLPP_SUCCESS;
+}
+
+int clpp_dev_perturb_solve(clpp_ctx* c, int k_begin, int k_end, char* err) {
+  return clpp_dev_perturb_solve_batch(&c, 1, &k_begin, &k_end, err);
 }

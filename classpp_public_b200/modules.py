@@ -234,10 +234,27 @@ class PerturbationsModule:
         if solve:
             lo, hi = k_range if k_range is not None else (0, i.k_size)
             ctx.check(L.clpp_perturb_solve(ctx.handle, int(lo), int(hi), ctx.err))
-            ks = (capi.KStat * i.k_size)()
-            L.clpp_perturb_get_kstat(ctx.handle, ks)
-            self.kstat_ = np.array([[s.steps, s.failed, s.fevals, s.jacobians, s.factorizations, s.solves,
-                                     s.intervals, s.status] for s in ks])
+            self._fetch_kstat()
+
+    def _fetch_kstat(self):
+        i = self.info
+        ks = (capi.KStat * i.k_size)()
+        self.ctx._lib.clpp_perturb_get_kstat(self.ctx.handle, ks)
+        self.kstat_ = np.array([[s.steps, s.failed, s.fevals, s.jacobians, s.factorizations, s.solves,
+                                 s.intervals, s.status] for s in ks])
+        self.kprofile_ = np.array([[list(s.iv_neq), list(s.iv_steps), list(s.iv_cycles)] for s in ks])
+        self.ksections_ = np.array([list(s.prof) for s in ks])
+        self._sources = None
+
+    @staticmethod
+    def solve_batch(modules):
+        """Integrate every k mode of several PerturbationsModule objects (constructed with solve=False, one
+        Context each, same device and precision settings) in ONE kernel launch (clpp_perturb_solve_batch)."""
+        ctx0 = modules[0].ctx
+        arr = (C.c_void_p * len(modules))(*[m.ctx.handle for m in modules])
+        ctx0.check(ctx0._lib.clpp_perturb_solve_batch(arr, len(modules), ctx0.err))
+        for m in modules:
+            m._fetch_kstat()
 
     @classmethod
     def from_sources(cls, inputs, background_module, k, tau, sources, info):

@@ -137,6 +137,11 @@ typedef struct clpp_kstat {
   int steps, failed, fevals, jacobians, factorizations, solves;
   int intervals, status;
   double tau_ini;
+  /* per approximation interval (at most 6): size of the ODE system, accepted steps and the SM
+   * clock cycles the mode spent in it (device profile; no reference counterpart) */
+  int iv_neq[6], iv_steps[6];
+  long long iv_cycles[6];
+  long long prof[72]; /* developer profile (builds with -DPT_PROF): cycles per (interval, code section), [6][12] */
 } clpp_kstat;
 
 /* replaces perturb_indices_of_perturbs + perturb_get_k_list + perturb_timesampling_for_sources
@@ -146,6 +151,11 @@ int clpp_perturb_grids(clpp_ctx* ctx, const clpp_perturb_desc* desc, clpp_pertur
  * k mode on the device (modes [k_begin,k_end) only; pass 0,k_size for all). Sources stay
  * resident on the device for stage 2. */
 int clpp_perturb_solve(clpp_ctx* ctx, int k_begin, int k_end, char* err);
+/* batched form for parameter sweeps (BASELINE config 5): every k mode of n_ctx cosmologies (all on
+ * the same device, same precision settings and species content) in ONE kernel launch, modes
+ * issued longest-first across the whole batch. The reference has no counterpart (it runs one
+ * Cosmology object at a time); per cosmology the result is identical to clpp_perturb_solve. */
+int clpp_perturb_solve_batch(clpp_ctx** ctxs, int n_ctx, char* err);
 int clpp_perturb_get_k(const clpp_ctx* ctx, double* k /*[k_size]*/);
 int clpp_perturb_get_tau(const clpp_ctx* ctx, double* tau /*[tau_size]*/);
 /* sources in the reference's layout sources_[index_tp][index_tau*k_size + index_k]
