@@ -93,7 +93,7 @@ struct clpp_ctx {
   clpp_transfer_desc td{};
   clpp_transfer_info tinfo{};
   std::vector<int> l, l_size_tt;
-  std::vector<double> q, kq;
+  std::vector<double> q, kq, chi_host;
 
   // --- device memory (managed in device.cu)
   struct Dev;

@@ -4,6 +4,8 @@
 
 #include <cuda_runtime.h>
 
+#include <map>
+
 #include "clpp_internal.h"
 
 struct clpp_ctx::Dev {
@@ -42,8 +44,27 @@ struct clpp_ctx::Dev {
   size_t transfer_count = 0;
   unsigned long long* tr_counters = nullptr;
 
+  // stage-2 scratch kept across calls (no cudaMalloc/cudaFree, which synchronise the device, on the hot path)
+  double* spline_u = nullptr;
+  int* bessel_scale = nullptr;
+  cudaEvent_t ev2[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::map<void*, size_t> cap;  // capacity (bytes) of the buffers managed by dev_reserve_any
+
   // stage 3
   double *pk = nullptr, *wq = nullptr, *cl = nullptr;
 };
+
+// grow-only device buffer: reallocates only when the requested size exceeds the capacity
+template <typename T>
+inline int clpp_dev_reserve(clpp_ctx::Dev* d, T** p, size_t n, char* err) {
+  const size_t bytes = (n > 0 ? n : 1) * sizeof(T);
+  auto it = d->cap.find((void*)p);
+  if (*p && it != d->cap.end() && it->second >= bytes) return CLPP_SUCCESS;
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  cudaError_t e = cudaMalloc((void**)p, bytes);
+  if (e != cudaSuccess) return clpp_fail(err, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+  d->cap[(void*)p] = bytes;
+  return CLPP_SUCCESS;
+}
 
 #endif

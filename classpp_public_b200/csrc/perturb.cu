@@ -133,11 +133,17 @@ struct Layout {
 };
 
 // background + thermodynamics at the current time; identical in all lanes
+enum { DRV_INV_R = 0, DRV_R, DRV_INV_1PR, DRV_INV_HALF_AH, DRV_INV_TAU, DRV_TAU_C, DRV_FAC_NCDM, DRV_COUNT = 8 };
 struct Env {
-  double tau, a, H, Hp, rho_g, rho_b, rho_cdm, rho_ur;
-  double dkappa, ddkappa, exp_m_kappa, g, dg, cb2;
-  // derived, hoisted out of the RHS: a^2, aH, R = 4 rho_g / 3 rho_b, reciprocals, (a_today/a)^4
-  double a2, aH, R, inv_R, inv_1pR, inv_half_aH, inv_tau, tau_c, fac_ncdm;
+  double tau, a, H, Hp;
+  // hoisted out of the RHS: R = 4 rho_g / 3 rho_b, reciprocals, (a_today/a)^4 (see env_at)
+  double drv[DRV_COUNT];
+};
+// interval cache of a table: bracketing rows (y0, y1, dd0, dd1), one column per lane
+struct TabCache {
+  double x0, x1, ih, h26;
+  int cur, pad;
+  double c[4][32];
 };
 
 struct Metric {
@@ -226,9 +232,12 @@ struct Mode {
   double* Jhh;  // global scratch [nh][nh], column-major: Jhh[i + j*nh] = J[hub i, hub j]
   double k, k2, inv_k, inv_k2;
   double nf[PT_MAX_NCDM][8];  // ncdm fluid constants at the current time (env_at)
-  // cached table intervals: entry [.][c] holds column c of the two bracketing rows (y0, y1, dd0, dd1)
-  double bx0, bx1, tx0, tx1;
-  double bc[4][32], tc[4][32];
+  TabCache bgc[2], thc[2];  // [0] time stepping, [1] source output
+  // per-cosmology scalars and table pointers (copied from PtCosmo once per mode)
+  const double *bg_tau, *bg_y, *bg_dd, *th_z, *th_y, *th_dd;
+  double z_last, th_lin, a_today;
+  double q[2 * PT_MAX_NCDM + 2];
+  int bt_size, tt_size;
   Env e;
   Metric m;
   double tca_shear_last;  // photon shear of the last Newton-iteration RHS call (used by the sources while TCA is on)
@@ -239,46 +248,61 @@ struct Mode {
   Approx ap, apprev;
   Layout L, Lprev;
   Stat st;
-  int ik, cur_bg, cur_th, need_nw, nh, nch, status, next;
+  int ik, need_nw, nh, nch, status, next;
 };
 #define MODE(P) (*(Mode*)(smem + (P).o_mode))
 
 // ---------------------------------------------------------------------------------------------
-// background_at_tau (normal_info columns) + thermodynamics_at_z, cooperative over lanes
-__device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby) {
+// background_at_tau (normal_info columns) + thermodynamics_at_z, cooperative over lanes.
+// `set` selects one of two interval caches: 0 = the time stepping, 1 = the source output (both
+// sweep the tables monotonically, at different times).  Entering a new interval also prefetches
+// the row the sweep will need next into L1.  Everything that only depends on time and that the RHS
+// would otherwise divide by is computed here ONCE per step, the divisions side by side in lanes.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+__device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby, int set) {
   Mode& M = MODE(P);
-  const PtCosmo* __restrict__ C = M.C;
   const int lane = (int)threadIdx.x;
+  double* pvb = s_pvb(P);
+  double* pvt = s_pvt(P);
   // background
-  if (!(tau >= M.bx0 && tau <= M.bx1)) {
-    const double* X = C->bg_tau;
-    const int n = C->bt_size;
-    const int inf = closeby ? locate_closeby(X, n, tau, M.cur_bg, lane) : locate_warp(X, n, tau, lane);
-    M.cur_bg = inf;
-    M.bx0 = __ldg(X + inf);
-    M.bx1 = __ldg(X + inf + 1);
-    if (lane < P.bg_size_normal) {
-      const size_t r0 = (size_t)inf * P.bg_size + lane, r1 = r0 + P.bg_size;
-      M.bc[0][lane] = __ldg(C->bg_y + r0); M.bc[1][lane] = __ldg(C->bg_y + r1);
-      M.bc[2][lane] = __ldg(C->bg_dd + r0); M.bc[3][lane] = __ldg(C->bg_dd + r1);
-    }
-  }
   {
-    const double h = M.bx1 - M.bx0, b = (tau - M.bx0) / h, a = 1 - b;
+    TabCache& T = M.bgc[set];
+    if (!(tau >= T.x0 && tau <= T.x1)) {
+      __syncwarp();
+      const double* X = M.bg_tau;
+      const int n = M.bt_size;
+      const int inf = closeby ? locate_closeby(X, n, tau, T.cur, lane) : locate_warp(X, n, tau, lane);
+      const double x0 = __ldg(X + inf), x1 = __ldg(X + inf + 1);
+      if (lane < P.bg_size_normal) {
+        const size_t r0 = (size_t)inf * P.bg_size + lane, r1 = r0 + P.bg_size;
+        T.c[0][lane] = __ldg(M.bg_y + r0); T.c[1][lane] = __ldg(M.bg_y + r1);
+        T.c[2][lane] = __ldg(M.bg_dd + r0); T.c[3][lane] = __ldg(M.bg_dd + r1);
+        if (inf + 2 < n) { prefetch_l1(M.bg_y + r1 + P.bg_size); prefetch_l1(M.bg_dd + r1 + P.bg_size); }
+      }
+      if (lane == 0) {
+        T.cur = inf; T.x0 = x0; T.x1 = x1;
+        const double h = x1 - x0;
+        T.ih = 1.0 / h; T.h26 = h * h / 6.;
+      }
+      __syncwarp();
+    }
+    const double b = (tau - T.x0) * T.ih, a = 1 - b;
     if (lane < P.bg_size_normal)
-      s_pvb(P)[lane] = a * M.bc[0][lane] + b * M.bc[1][lane] + ((a * a * a - a) * M.bc[2][lane] + (b * b * b - b) * M.bc[3][lane]) * h * h / 6.;
+      pvb[lane] = a * T.c[0][lane] + b * T.c[1][lane] + ((a * a * a - a) * T.c[2][lane] + (b * b * b - b) * T.c[3][lane]) * T.h26;
   }
   __syncwarp();
-  const double av = s_pvb(P)[P.ia], Hv = s_pvb(P)[P.iH], Hp = s_pvb(P)[P.iHp];
-  const double z = 1. / av - 1.;
+  const double av = pvb[P.ia], Hv = pvb[P.iH], Hp = pvb[P.iHp];
+  const double inv_a = 1. / av;
+  const double z = inv_a - 1.;
   // thermodynamics
-  const int ntt = C->tt_size;
-  const double z_last = __ldg(C->th_z + ntt - 1);
+  const double z_last = M.z_last;
   if (z >= z_last) {
     if (lane == 0) {
-      const double* row = C->th_y + (size_t)(ntt - 1) * P.th_size;
+      const PtCosmo* C = M.C;
+      const double* row = M.th_y + (size_t)(M.tt_size - 1) * P.th_size;
       const double x0 = row[P.ixe];
-      double* pv = s_pvt(P);
+      double* pv = pvt;
       const double r = (1. + z) / (1. + z_last);
       pv[P.ixe] = x0;
       pv[P.idkappa] = (1. + z) * (1. + z) * C->n_e * x0 * CLPP_sigma * CLPP_Mpc_over_m;
@@ -301,94 +325,116 @@ __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby)
       pv[P.irate] = pv[P.idkappa];
     }
   } else {
-    const bool linear = (z < C->th_linear_below_z);
-    if (!(z >= M.tx0 && z <= M.tx1)) {
-      const double* X = C->th_z;
-      const int inf = (closeby && !linear) ? locate_closeby(X, ntt, z, M.cur_th, lane) : locate_warp(X, ntt, z, lane);
-      M.cur_th = inf;
-      M.tx0 = __ldg(X + inf);
-      M.tx1 = __ldg(X + inf + 1);
+    TabCache& T = M.thc[set];
+    const bool linear = (z < M.th_lin);
+    if (!(z >= T.x0 && z <= T.x1)) {
+      __syncwarp();
+      const double* X = M.th_z;
+      const int n = M.tt_size;
+      const int inf = (closeby && !linear) ? locate_closeby(X, n, z, T.cur, lane) : locate_warp(X, n, z, lane);
+      const double x0 = __ldg(X + inf), x1 = __ldg(X + inf + 1);
       if (lane < P.th_size) {
         const size_t r0 = (size_t)inf * P.th_size + lane, r1 = r0 + P.th_size;
-        M.tc[0][lane] = __ldg(C->th_y + r0); M.tc[1][lane] = __ldg(C->th_y + r1);
-        M.tc[2][lane] = __ldg(C->th_dd + r0); M.tc[3][lane] = __ldg(C->th_dd + r1);
+        T.c[0][lane] = __ldg(M.th_y + r0); T.c[1][lane] = __ldg(M.th_y + r1);
+        T.c[2][lane] = __ldg(M.th_dd + r0); T.c[3][lane] = __ldg(M.th_dd + r1);
+        if (inf > 0) { prefetch_l1(M.th_y + r0 - P.th_size); prefetch_l1(M.th_dd + r0 - P.th_size); }  // z decreases with time
       }
+      if (lane == 0) {
+        T.cur = inf; T.x0 = x0; T.x1 = x1;
+        const double h = x1 - x0;
+        T.ih = 1.0 / h; T.h26 = h * h / 6.;
+      }
+      __syncwarp();
     }
-    const double h = M.tx1 - M.tx0, b = (z - M.tx0) / h, a = 1 - b;
+    const double b = (z - T.x0) * T.ih, a = 1 - b;
     if (lane < P.th_size) {
-      double v = a * M.tc[0][lane] + b * M.tc[1][lane];
-      if (!linear) v += ((a * a * a - a) * M.tc[2][lane] + (b * b * b - b) * M.tc[3][lane]) * h * h / 6.;
-      s_pvt(P)[lane] = v;
+      double v = a * T.c[0][lane] + b * T.c[1][lane];
+      if (!linear) v += ((a * a * a - a) * T.c[2][lane] + (b * b * b - b) * T.c[3][lane]) * T.h26;
+      pvt[lane] = v;
     }
   }
   // momentum-dependent ncdm weights at this scale factor (used by the RHS while the ncdm hierarchy is integrated)
   if (M.need_nw) {
     const double a2 = av * av;
     const int nq = P.nq_tot;
+    double* nw = s_nw(P);
     for (int j = lane; j < nq; j += 32) {
       int s = 0;
 #pragma unroll
       for (int t = 1; t < PT_MAX_NCDM; t++)
         if (t < P.N_ncdm && j >= P.ncdm_q_off[t]) s = t;
-      const double Ms = C->ncdm_M[s];
-      const double q = __ldg(C->ncdm_q + j), w0 = __ldg(C->ncdm_w + j);
+      const double Ms = M.C->ncdm_M[s];
+      const double q = __ldg(M.C->ncdm_q + j), w0 = __ldg(M.C->ncdm_w + j);
       const double q2 = q * q, eps = sqrt(q2 + Ms * Ms * a2);
-      s_nw(P)[j] = q / eps;
-      s_nw(P)[nq + j] = q2 * eps * w0;
-      s_nw(P)[2 * nq + j] = q2 * q * w0;
-      s_nw(P)[3 * nq + j] = q2 * q2 / eps * w0;
+      const double ieps = 1.0 / eps;
+      nw[j] = q * ieps;
+      nw[nq + j] = q2 * eps * w0;
+      nw[2 * nq + j] = q2 * q * w0;
+      nw[3 * nq + j] = q2 * q2 * ieps * w0;
     }
   }
-  // ncdm fluid constants (perturb_derivs_member :8800-8850, perturb_total_stress_energy :6380-6400)
-  if (P.has_ncdm && M.ap.ncdmfa_on && lane < P.N_ncdm) {
-    const int s = lane;
-    const double* pvb = s_pvb(P);
-    const double rho_n = pvb[P.irho_ncdm1 + s], p_n = pvb[P.ip_ncdm1 + s], pseudo_p = pvb[P.ipseudo_p_ncdm1 + s];
-    const double aH = Hv * av;
-    const double pseudo_p_over_p = pseudo_p / p_n;
-    const double w_n = p_n / rho_n;
-    const double cg2 = w_n * (1.0 - 1.0 / (3.0 + 3.0 * w_n) * (3.0 * w_n - 2.0 + pseudo_p_over_p));
-    const double ca2 = w_n / 3.0 / (1.0 + w_n) * (5.0 - pseudo_p_over_p);
-    const double cvis2 = (P.ncdmfa_method == CLPP_NCDMFA_HU) ? w_n : 3. * w_n * ca2;
-    double* nf = M.nf[s];
-    nf[0] = rho_n; nf[1] = rho_n + p_n; nf[2] = w_n; nf[3] = cg2 * rho_n; nf[4] = ca2;
-    nf[5] = ca2 / (1.0 + w_n);
-    nf[6] = 8.0 / 3.0 * cvis2 / (1.0 + w_n);
-    nf[7] = (P.ncdmfa_method == CLPP_NCDMFA_HU) ? 3.0 * aH * ca2 / w_n
-                                                : 3.0 * (aH * (2. / 3. - ca2 - pseudo_p_over_p / 3.) + 1. / tau);
-  }
-  if (lane == 0) {
-    Env& e = M.e;
-    const double* pvb = s_pvb(P);
-    const double* pvt = s_pvt(P);
-    e.tau = tau;
-    e.a = av; e.H = Hv; e.Hp = Hp;
+  __syncwarp();
+  // derived quantities: one SIMD division, the quotient of lane j is DRV j (and, from lane 8 on, the
+  // ratios w = p/rho and pseudo_p/p of the ncdm species for the fluid approximation)
+  {
     const double rho_g = pvb[P.irho_g], rho_b = pvb[P.irho_b], dkappa = pvt[P.idkappa];
-    e.rho_g = rho_g; e.rho_b = rho_b; e.rho_cdm = pvb[P.irho_cdm];
-    e.rho_ur = P.has_ur ? pvb[P.irho_ur] : 0.;
-    e.dkappa = dkappa; e.ddkappa = pvt[P.iddkappa];
-    e.exp_m_kappa = pvt[P.iexp_m_kappa]; e.g = pvt[P.ig]; e.dg = pvt[P.idg];
-    e.cb2 = pvt[P.icb2];
-    const double aH = Hv * av, R = 4. / 3. * rho_g / rho_b;
-    e.a2 = av * av; e.aH = aH; e.R = R;
-    e.inv_R = 1.0 / R; e.inv_1pR = 1.0 / (1.0 + R); e.inv_half_aH = 1.0 / (0.5 * aH);
-    e.inv_tau = 1.0 / tau; e.tau_c = 1.0 / dkappa;
-    const double a_rel = C->a_today / av;
-    e.fac_ncdm = (a_rel * a_rel) * (a_rel * a_rel);
+    const double aH = Hv * av;
+    double num = 1., den = 1.;
+    if (lane == DRV_INV_R) { num = 0.75 * rho_b; den = rho_g; }
+    else if (lane == DRV_R) { num = 4. / 3. * rho_g; den = rho_b; }
+    else if (lane == DRV_INV_1PR) { num = rho_b; den = rho_b + 4. / 3. * rho_g; }
+    else if (lane == DRV_INV_HALF_AH) { num = 2.; den = aH; }
+    else if (lane == DRV_INV_TAU) { den = tau; }
+    else if (lane == DRV_TAU_C) { den = dkappa; }
+    else if (lane >= 8 && lane < 8 + 2 * P.N_ncdm) {
+      const int s = (lane - 8) >> 1;
+      const double p_n = pvb[P.ip_ncdm1 + s];
+      if (lane & 1) { num = pvb[P.ipseudo_p_ncdm1 + s]; den = p_n; }
+      else { num = p_n; den = pvb[P.irho_ncdm1 + s]; }
+    }
+    const double q = num / den;
+    if (lane < 6) M.e.drv[lane] = q;
+    else if (lane >= 8 && lane < 8 + 2 * PT_MAX_NCDM) M.q[lane - 8] = q;
+    if (lane == 6) {
+      const double a_rel = M.a_today * inv_a;
+      M.e.drv[DRV_FAC_NCDM] = (a_rel * a_rel) * (a_rel * a_rel);
+      M.e.tau = tau; M.e.a = av; M.e.H = Hv; M.e.Hp = Hp;
+    }
   }
   __syncwarp();
+  // ncdm fluid constants (perturb_derivs_member :8800-8850, perturb_total_stress_energy :6380-6400)
+  if (P.has_ncdm && M.ap.ncdmfa_on) {
+    if (lane < P.N_ncdm) {
+      const int s = lane;
+      const double rho_n = pvb[P.irho_ncdm1 + s], p_n = pvb[P.ip_ncdm1 + s];
+      const double aH = Hv * av;
+      const double w_n = M.q[2 * s], pseudo_p_over_p = M.q[2 * s + 1];
+      const double i1w = 1.0 / (1.0 + w_n);
+      const double cg2 = w_n * (1.0 - i1w * (1. / 3.) * (3.0 * w_n - 2.0 + pseudo_p_over_p));
+      const double ca2 = w_n * (1. / 3.) * i1w * (5.0 - pseudo_p_over_p);
+      const double cvis2 = (P.ncdmfa_method == CLPP_NCDMFA_HU) ? w_n : 3. * w_n * ca2;
+      double* nf = M.nf[s];
+      nf[0] = rho_n; nf[1] = rho_n + p_n; nf[2] = w_n; nf[3] = cg2 * rho_n; nf[4] = ca2;
+      nf[5] = ca2 * i1w;
+      nf[6] = 8.0 / 3.0 * cvis2 * i1w;
+      nf[7] = (P.ncdmfa_method == CLPP_NCDMFA_HU) ? 3.0 * aH * ca2 / w_n
+                                                  : 3.0 * (aH * (2. / 3. - ca2 - pseudo_p_over_p * (1. / 3.)) + M.e.drv[DRV_INV_TAU]);
+    }
+    __syncwarp();
+  }
 }
 
 // perturb_approximations: flags at time tau (uses bisection lookups, inter_normal)
 __device__ __noinline__ Approx approximations_at(const PtParams& P, double tau) {
   Mode& M = MODE(P);
-  env_at(P, tau, false);
+  env_at(P, tau, false, 0);
   const Env& e = M.e;
   Approx a;
   const double tau_k = 1. / M.k, tau_h = 1. / (e.H * e.a);
-  if (e.dkappa == 0.) a.tca_off = 1;
+  const double dkappa = s_pvt(P)[P.idkappa];
+  if (dkappa == 0.) a.tca_off = 1;
   else {
-    const double tau_c = 1. / e.dkappa;
+    const double tau_c = 1. / dkappa;
     a.tca_off = ((tau_c / tau_h < P.tca_trigger_tau_c_over_tau_h) && (tau_c / tau_k < P.tca_trigger_tau_c_over_tau_k)) ? 0 : 1;
   }
   a.rsa_on = ((tau / tau_k > P.rsa_trigger) && (tau > M.C->tau_free_streaming) && (P.rsa_method != CLPP_RSA_NONE)) ? 1 : 0;
@@ -502,12 +548,16 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
   const Env& e = M.e;
   const int lane = threadIdx.x;
   const double k = M.k, k2 = M.k2, ik2 = M.inv_k2;
-  const double a2 = e.a2, aH = e.aH, R = e.R;
+  const double* pvb = s_pvb(P);
+  const double* pvt = s_pvt(P);
+  const double a2 = e.a * e.a, aH = e.H * e.a, R = e.drv[DRV_R];
+  const double rho_g = pvb[P.irho_g], rho_b = pvb[P.irho_b], rho_cdm = pvb[P.irho_cdm];
+  const double rho_ur = P.has_ur ? pvb[P.irho_ur] : 0.;
+  const double dkappa = pvt[P.idkappa], cb2 = pvt[P.icb2];
   Metric& m = M.m;
   const bool has_g = !ap.rsa_on;
   const bool has_ur = P.has_ur && !ap.rsa_on;
   const bool full_g = has_g && ap.tca_off;
-  const double* pvb = s_pvb(P);
 
   // ---- loads of every hub value (independent, issued up front)
   double delta_g = 0., theta_g = 0., shear_g = 0.;
@@ -523,21 +573,21 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
     if (!ap.ufa_on) { u3 = y[L.l3_ur]; u4 = y[L.l3_ur + 1]; }
   }
   const double delta_b = y[L.delta_b], theta_b = y[L.theta_b], delta_cdm = y[L.delta_cdm], eta = y[L.eta];
-  const double delta_p_b_over_rho_b = e.cb2 * delta_b;
+  const double delta_p_b_over_rho_b = cb2 * delta_b;
 
   // ---- perturb_total_stress_energy
-  double delta_rho = e.rho_g * delta_g + e.rho_b * delta_b;
-  double rpt = 4. / 3. * e.rho_g * theta_g + e.rho_b * theta_b;
-  double rps = 4. / 3. * e.rho_g * shear_g;
-  double delta_p = 1. / 3. * e.rho_g * delta_g + e.rho_b * delta_p_b_over_rho_b;
-  double delta_rho_m = e.rho_b * delta_b, rho_m = e.rho_b, rpt_m = e.rho_b * theta_b, rpm = e.rho_b;
-  delta_rho += e.rho_cdm * delta_cdm;
-  delta_rho_m += e.rho_cdm * delta_cdm; rho_m += e.rho_cdm; rpm += e.rho_cdm;
+  double delta_rho = rho_g * delta_g + rho_b * delta_b;
+  double rpt = 4. / 3. * rho_g * theta_g + rho_b * theta_b;
+  double rps = 4. / 3. * rho_g * shear_g;
+  double delta_p = 1. / 3. * rho_g * delta_g + rho_b * delta_p_b_over_rho_b;
+  double delta_rho_m = rho_b * delta_b, rho_m = rho_b, rpt_m = rho_b * theta_b, rpm = rho_b;
+  delta_rho += rho_cdm * delta_cdm;
+  delta_rho_m += rho_cdm * delta_cdm; rho_m += rho_cdm; rpm += rho_cdm;
   if (P.has_ur) {
-    delta_rho = delta_rho + e.rho_ur * delta_ur;
-    rpt = rpt + 4. / 3. * e.rho_ur * theta_ur;
-    rps = rps + 4. / 3. * e.rho_ur * shear_ur;
-    delta_p += 1. / 3. * e.rho_ur * delta_ur;
+    delta_rho = delta_rho + rho_ur * delta_ur;
+    rpt = rpt + 4. / 3. * rho_ur * theta_ur;
+    rps = rps + 4. / 3. * rho_ur * shear_ur;
+    delta_p += 1. / 3. * rho_ur * delta_ur;
   }
   if (want_matter) m.delta_cb = delta_rho_m / rho_m + 3. * aH * (rpt_m / rpm) * ik2;
   if (P.has_ncdm) {
@@ -558,7 +608,7 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
       const double* w = s_nw(P);
       for (int s = 0; s < P.N_ncdm; s++) {
         const double rho_n = pvb[P.irho_ncdm1 + s], p_n = pvb[P.ip_ncdm1 + s];
-        const double factor = M.C->ncdm_factor[s] * e.fac_ncdm;
+        const double factor = M.C->ncdm_factor[s] * e.drv[DRV_FAC_NCDM];
         double s_rho = 0., s_theta = 0., s_shear = 0., s_p = 0.;
         const int nq = P.ncdm_q_size[s], q0 = P.ncdm_q_off[s];
         const int base = L.psi0_ncdm1 + q0 * stride;
@@ -596,7 +646,7 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
   if (want_matter) m.delta_m = delta_rho_m / rho_m + 3. * aH * (rpt_m / rpm) * ik2;
 
   // ---- perturb_einstein (synchronous gauge, K = 0)
-  const double h_prime = (k2 * eta + 1.5 * a2 * delta_rho) * e.inv_half_aH;
+  const double h_prime = (k2 * eta + 1.5 * a2 * delta_rho) * e.drv[DRV_INV_HALF_AH];
   double rsa_delta_g = 0., rsa_theta_g = 0.;
   if (ap.rsa_on) {
     double rsa_delta_ur = 0., rsa_theta_ur = 0.;
@@ -605,26 +655,26 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
       rsa_theta_g = -0.5 * h_prime;
     }
     if (P.rsa_method == CLPP_RSA_MD_WITH_REIO) {
-      rsa_delta_g += -4. * ik2 * e.dkappa * (theta_b + 0.5 * h_prime);
-      rsa_theta_g += 3. * ik2 * (e.ddkappa * (theta_b + 0.5 * h_prime) +
-                                 e.dkappa * (-aH * theta_b + e.cb2 * k2 * delta_b - aH * h_prime + k2 * eta));
+      rsa_delta_g += -4. * ik2 * dkappa * (theta_b + 0.5 * h_prime);
+      rsa_theta_g += 3. * ik2 * (pvt[P.iddkappa] * (theta_b + 0.5 * h_prime) +
+                                 dkappa * (-aH * theta_b + cb2 * k2 * delta_b - aH * h_prime + k2 * eta));
     }
     if (P.has_ur && P.rsa_method != CLPP_RSA_NULL) {
       rsa_delta_ur = 4. * ik2 * (aH * h_prime - k2 * eta);
       rsa_theta_ur = -0.5 * h_prime;
     }
-    delta_rho += e.rho_g * rsa_delta_g;
-    rpt += 4. / 3. * e.rho_g * rsa_theta_g;
+    delta_rho += rho_g * rsa_delta_g;
+    rpt += 4. / 3. * rho_g * rsa_theta_g;
     if (P.has_ur) {
-      delta_rho += e.rho_ur * rsa_delta_ur;
-      rpt += 4. / 3. * e.rho_ur * rsa_theta_ur;
+      delta_rho += rho_ur * rsa_delta_ur;
+      rpt += 4. / 3. * rho_ur * rsa_theta_ur;
     }
   }
   const double eta_prime = (1.5 * a2 * rpt) * ik2;
   const double alpha = (h_prime + 6. * eta_prime) * 0.5 * ik2;
   if (!ap.tca_off) {
-    const double sg = 16. / 45. * e.tau_c * (theta_g + k2 * alpha);
-    rps += 4. / 3. * e.rho_g * sg;
+    const double sg = 16. / 45. * e.drv[DRV_TAU_C] * (theta_g + k2 * alpha);
+    rps += 4. / 3. * rho_g * sg;
   }
   const double alpha_prime = -2. * aH * alpha + eta - 4.5 * (a2 * ik2) * rps;
   m.h_prime = h_prime; m.eta_prime = eta_prime; m.alpha = alpha; m.alpha_prime = alpha_prime;
@@ -632,7 +682,7 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
   if (dy == nullptr) return;
 
   // ---- perturb_derivs: hub equations (uniform)
-  const double cotKgen = e.inv_tau * M.inv_k;
+  const double cotKgen = e.drv[DRV_INV_TAU] * M.inv_k;
   const double metric_continuity = h_prime * 0.5;
   const double metric_shear = k2 * alpha;
   const double metric_ufa_class = h_prime * 0.5;
@@ -640,43 +690,43 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
 
   double dtheta_b, dtheta_g = 0., dshear_g = 0., dl3_g = 0., dp0 = 0., dp1 = 0., dp2 = 0.;
   if (ap.tca_off) {
-    dtheta_b = -aH * theta_b + k2 * delta_p_b_over_rho_b + R * e.dkappa * (theta_g - theta_b);
+    dtheta_b = -aH * theta_b + k2 * delta_p_b_over_rho_b + R * dkappa * (theta_g - theta_b);
     if (full_g) {
       const double P0 = (p0 + p2 + 2. * shear_g) * 0.125;
-      dtheta_g = k2 * (delta_g * 0.25 - shear_g) + e.dkappa * (theta_b - theta_g);
-      dshear_g = 0.5 * (8. / 15. * (theta_g + metric_shear) - 3. / 5. * k * g3 - e.dkappa * (2. * shear_g - 4. / 5. * P0));
-      dl3_g = k * (1. / 7.0) * (3. * 2. * shear_g - 4. * g4) - e.dkappa * g3;
-      dp0 = -k * p1 - e.dkappa * (p0 - 4. * P0);
-      dp1 = k * (1. / 3.) * (p0 - 2. * p2) - e.dkappa * p1;
-      dp2 = k * (1. / 5.) * (2. * p1 - 3. * p3) - e.dkappa * (p2 - 4. / 5. * P0);
+      dtheta_g = k2 * (delta_g * 0.25 - shear_g) + dkappa * (theta_b - theta_g);
+      dshear_g = 0.5 * (8. / 15. * (theta_g + metric_shear) - 3. / 5. * k * g3 - dkappa * (2. * shear_g - 4. / 5. * P0));
+      dl3_g = k * (1. / 7.0) * (3. * 2. * shear_g - 4. * g4) - dkappa * g3;
+      dp0 = -k * p1 - dkappa * (p0 - 4. * P0);
+      dp1 = k * (1. / 3.) * (p0 - 2. * p2) - dkappa * p1;
+      dp2 = k * (1. / 5.) * (2. * p1 - 3. * p3) - dkappa * (p2 - 4. / 5. * P0);
     }
   } else {
     // ---- perturb_tca_slip_and_shear
     const double a_primeprime_over_a = e.Hp * e.a + 2. * aH * aH;
-    const double tau_c = e.tau_c;
-    const double dtau_c = -e.ddkappa * tau_c * tau_c;
-    const double i1pR = e.inv_1pR;
+    const double tau_c = e.drv[DRV_TAU_C];
+    const double dtau_c = -pvt[P.iddkappa] * tau_c * tau_c;
+    const double i1pR = e.drv[DRV_INV_1PR];
     const double F = tau_c * i1pR;
     double F_prime = 0.;
     if (P.tca_method >= CLPP_TCA_SECOND_ORDER_CLASS) F_prime = dtau_c * i1pR + tau_c * aH * R * i1pR * i1pR;
     const double metric_shear_prime = k2 * alpha_prime;
     const double common = F * (-a_primeprime_over_a * theta_b +
-                               k2 * (-aH * delta_g * 0.5 + e.cb2 * (-theta_b - metric_continuity) -
+                               k2 * (-aH * delta_g * 0.5 + cb2 * (-theta_b - metric_continuity) -
                                      4. / 3. * (-theta_g - metric_continuity) * 0.25));
     double slip;
     if (P.tca_method == CLPP_TCA_FIRST_ORDER_MB) slip = 2. * R * i1pR * aH * (theta_b - theta_g) + common;
-    else slip = (dtau_c * e.dkappa - 2. * aH * i1pR) * (theta_b - theta_g) + common;
+    else slip = (dtau_c * dkappa - 2. * aH * i1pR) * (theta_b - theta_g) + common;
     double sg = 16. / 45. * tau_c * (theta_g + metric_shear);
-    const double theta_prime = (-aH * theta_b + k2 * (e.cb2 * delta_b + R * 0.25 * delta_g)) * i1pR;
+    const double theta_prime = (-aH * theta_b + k2 * (cb2 * delta_b + R * 0.25 * delta_g)) * i1pR;
     const double shear_g_prime = 16. / 45. * (tau_c * (theta_prime + metric_shear_prime) + dtau_c * (theta_g + metric_shear));
     if (P.tca_method == CLPP_TCA_COMPROMISE_CLASS) {
       slip = (1. - 2. * aH * F) * slip +
-             F * k2 * (2. * aH * sg + shear_g_prime - (1. / 3. - e.cb2) * (F * theta_prime + 2. * F_prime * theta_b));
+             F * k2 * (2. * aH * sg + shear_g_prime - (1. / 3. - cb2) * (F * theta_prime + 2. * F_prime * theta_b));
       sg = (1. - 11. / 6. * dtau_c) * sg - 11. / 6. * tau_c * 16. / 45. * tau_c * (theta_prime + metric_shear_prime);
     }
     m.tca_shear_g = sg;
     dtheta_b = (-aH * theta_b + k2 * (delta_p_b_over_rho_b + R * (delta_g * 0.25 - sg)) + R * slip) * i1pR;
-    dtheta_g = -(dtheta_b + aH * theta_b - k2 * delta_p_b_over_rho_b) * e.inv_R + k2 * (0.25 * delta_g - sg);
+    dtheta_g = -(dtheta_b + aH * theta_b - k2 * delta_p_b_over_rho_b) * e.drv[DRV_INV_R] + k2 * (0.25 * delta_g - sg);
   }
   double ddelta_ur = 0., dtheta_ur = 0., dshear_ur = 0., dl3_ur = 0.;
   if (has_ur) {
@@ -688,9 +738,9 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
                          (1. - P.three_cvis2_ur) * (8. / 15. * (theta_ur + metric_shear)));
       dl3_ur = k * (1. / 7.) * (3. * 2. * shear_ur - 4. * u4);
     } else {
-      if (P.ufa_method == CLPP_UFA_MB) dshear_ur = -3. * e.inv_tau * shear_ur + 2. / 3. * (theta_ur + metric_shear);
+      if (P.ufa_method == CLPP_UFA_MB) dshear_ur = -3. * e.drv[DRV_INV_TAU] * shear_ur + 2. / 3. * (theta_ur + metric_shear);
       else if (P.ufa_method == CLPP_UFA_HU) dshear_ur = -3. * aH * shear_ur + 2. / 3. * (theta_ur + metric_shear);
-      else dshear_ur = -3. * e.inv_tau * shear_ur + 2. / 3. * (theta_ur + metric_ufa_class);
+      else dshear_ur = -3. * e.drv[DRV_INV_TAU] * shear_ur + 2. / 3. * (theta_ur + metric_ufa_class);
     }
   }
   // ---- stores of the hub equations (lane 0) ...
@@ -724,12 +774,12 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
     const double* yg = y + L.delta_g;  // yg[l] = F_l (l>=3), yg[2] = shear
     const double* yp = y + L.pol0_g;
     for (int l = 4 + lane; l <= lg; l += 32) {
-      if (l < lg) dy[L.delta_g + l] = k * i2l1[l] * (l * yg[l - 1] - (l + 1) * yg[l + 1]) - e.dkappa * yg[l];
-      else dy[L.delta_g + l] = k * (yg[l - 1] - (1. + l) * cotKgen * yg[l]) - e.dkappa * yg[l];
+      if (l < lg) dy[L.delta_g + l] = k * i2l1[l] * (l * yg[l - 1] - (l + 1) * yg[l + 1]) - dkappa * yg[l];
+      else dy[L.delta_g + l] = k * (yg[l - 1] - (1. + l) * cotKgen * yg[l]) - dkappa * yg[l];
     }
     for (int l = 3 + lane; l <= lp; l += 32) {
-      if (l < lp) dy[L.pol0_g + l] = k * i2l1[l] * (l * yp[l - 1] - (l + 1.) * yp[l + 1]) - e.dkappa * yp[l];
-      else dy[L.pol0_g + l] = k * (yp[l - 1] - (l + 1) * cotKgen * yp[l]) - e.dkappa * yp[l];
+      if (l < lp) dy[L.pol0_g + l] = k * i2l1[l] * (l * yp[l - 1] - (l + 1.) * yp[l + 1]) - dkappa * yp[l];
+      else dy[L.pol0_g + l] = k * (yp[l - 1] - (l + 1) * cotKgen * yp[l]) - dkappa * yp[l];
     }
   }
   if (has_ur && !ap.ufa_on) {
@@ -780,15 +830,17 @@ __device__ __noinline__ void write_sources(const PtParams& P, double tau, int sl
   Mode& M = MODE(P);
   const double* y = s_vec(P, slot_y);
   const double* dy = s_vec(P, slot_dy);
-  env_at(P, tau, true);
+  env_at(P, tau, true, 1);
   rhs_apply(P, slot_y, -1, 1);
   if ((int)threadIdx.x != 0) return;
   const Layout& L = M.L;
   const Approx& ap = M.ap;
   const Env& e = M.e;
+  const double* pvt = s_pvt(P);
+  const double e_g = pvt[P.ig], e_dg = pvt[P.idg], e_exp_m_kappa = pvt[P.iexp_m_kappa];
   const Metric& m = M.m;
   const double k = M.k;
-  const double z = M.C->a_today / e.a - 1.;
+  const double z = M.a_today / e.a - 1.;
   const double aH = e.a * e.H;
   const double aH_prime = e.Hp * e.a + (e.H * e.a) * (e.H * e.a);
   double delta_g, Pi;
@@ -806,14 +858,14 @@ __device__ __noinline__ void write_sources(const PtParams& P, double tau, int sl
     if ((P.switch_lisw == 0) && (z < P.eisw_lisw_split_z)) switch_isw = 0;
     const double eta = y[L.eta], theta_b = y[L.theta_b], dtheta_b = dy[L.theta_b];
     out[P.tp_t0 * stride_tp] =
-        P.switch_sw * e.g * (delta_g / 4. + m.alpha_prime) +
-        switch_isw * (e.g * (eta - m.alpha_prime - 2 * aH * m.alpha) +
-                      e.exp_m_kappa * 2. * (m.eta_prime - aH_prime * m.alpha - aH * m.alpha_prime)) +
-        P.switch_dop * (e.g * (dtheta_b / k / k + m.alpha_prime) + e.dg * (theta_b / k / k + m.alpha));
-    out[P.tp_t1 * stride_tp] = switch_isw * e.exp_m_kappa * k * (m.alpha_prime + 2. * aH * m.alpha - eta);
-    out[P.tp_t2 * stride_tp] = P.switch_pol * e.g * Pi;
+        P.switch_sw * e_g * (delta_g / 4. + m.alpha_prime) +
+        switch_isw * (e_g * (eta - m.alpha_prime - 2 * aH * m.alpha) +
+                      e_exp_m_kappa * 2. * (m.eta_prime - aH_prime * m.alpha - aH * m.alpha_prime)) +
+        P.switch_dop * (e_g * (dtheta_b / k / k + m.alpha_prime) + e_dg * (theta_b / k / k + m.alpha));
+    out[P.tp_t1 * stride_tp] = switch_isw * e_exp_m_kappa * k * (m.alpha_prime + 2. * aH * m.alpha - eta);
+    out[P.tp_t2 * stride_tp] = P.switch_pol * e_g * Pi;
   }
-  if (P.tp_p >= 0) out[P.tp_p * stride_tp] = sqrt(6.) * e.g * Pi;
+  if (P.tp_p >= 0) out[P.tp_p * stride_tp] = sqrt(6.) * e_g * Pi;
   if (P.tp_phi_plus_psi >= 0) out[P.tp_phi_plus_psi * stride_tp] = y[L.eta] + m.alpha_prime;
   if (P.tp_delta_m >= 0) out[P.tp_delta_m * stride_tp] = m.delta_m;
   if (P.tp_delta_cb >= 0) out[P.tp_delta_cb * stride_tp] = m.delta_cb;
@@ -1080,7 +1132,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
     for (int i = lane; i < n; i += 32) dif[j * np + i] = 0.;
   const double htspan = fabs(tfinal - t0);
   double t = t0, tnew = t0;
-  env_at(P, t0, true);
+  env_at(P, t0, true, 0);
   rhs_apply(P, V_Y, V_F0, 0);
   if (threadIdx.x == 0) M.st.fevals++;
   const double hmax = (tfinal - t0) / 10.0;
@@ -1103,7 +1155,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
     rhs_apply(P, V_F0, V_PSI, 0);
     if (threadIdx.x == 0) M.st.fevals++;
     const double tdel = (t + fmin(sqrt(eps) * fmax(fabs(t), fabs(t + h)), absh)) - t;
-    env_at(P, t + tdel, true);
+    env_at(P, t + tdel, true, 0);
     rhs_apply(P, V_Y, V_DEL, 0);  // f(t+tdel, y)
     if (threadIdx.x == 0) M.st.fevals++;
     rh = 0.0;
@@ -1186,7 +1238,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
         __syncwarp();
         PROF_END(PF_PREDICT);
         PROF_BEGIN();
-        env_at(P, tnew, true);
+        env_at(P, tnew, true, 0);
         PROF_END(PF_ENV);
         bool tooslow = false;
         for (int iter = 1; iter <= maxit; iter++) {
@@ -1236,7 +1288,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
         if (tooslow) {
           if (threadIdx.x == 0) M.st.failed++;
           if (!Jcurrent) {
-            env_at(P, t, true);
+            env_at(P, t, true, 0);
             rhs_apply(P, V_Y, V_F0, 0);
             if (threadIdx.x == 0) M.st.fevals++;
             jacobian(P);
@@ -1384,10 +1436,369 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
   // by-products are current at the end of the interval (evolver_ndf15.cpp:653-662)
   for (int i = lane; i < n; i += 32) y[i] = ynew[i];
   __syncwarp();
-  env_at(P, tnew, true);
+  env_at(P, tnew, true, 0);
   rhs_apply(P, V_Y, V_F0, 0);
   if (!M.ap.tca_off) M.tca_shear_last = M.m.tca_shear_g;
   if (threadIdx.x == 0) M.st.fevals++;
+  M.next = next;
+  return true;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// NDF1-5 for a HUB-ONLY phase (no multipole chains, neq <= 32): radiation streaming approximation
+// with the ncdm fluid approximation, i.e. the last and by far the longest interval of every
+// high-k mode (10^4..10^5 steps).  Lane i owns equation i: the state, the backward differences and
+// all step-control vectors live in REGISTERS; shared memory is only the exchange buffer of the RHS
+// and of the linear solve.  Same algorithm and constants as ndf15() above.
+__device__ __forceinline__ double pick7(const double (&d)[7], int j) {
+  double v = d[0];
+#pragma unroll
+  for (int q = 1; q < 7; q++) v = (j == q) ? d[q] : v;
+  return v;
+}
+
+__device__ __noinline__ bool ndf15_hub(const PtParams& P, double t0, double tfinal) {
+  Mode& M = MODE(P);
+  PROF_DECL;
+  const double abstol = 1e-15, eps = 1e-16, threshold = abstol;
+  const int maxit = 4, maxk = 5;
+  const double rtol = P.rtol;
+  const int n = M.L.neq, lane = threadIdx.x, ldh = P.ldh;
+  const bool act = lane < n;
+  const int li = act ? lane : 0;  // safe shared-memory index for idle lanes
+  double *YX = s_vec(P, V_YNEW), *F = s_vec(P, V_F0), *B = s_vec(P, V_DEL), *Ys = s_vec(P, V_Y);
+  const double* t_vec = M.C->tau;
+  const int tres = M.C->tau_size;
+  int next = M.next;
+  while (next < tres && __ldg(t_vec + next) < t0) next++;
+  double tnext = (next < tres) ? __ldg(t_vec + next) : 1e300;
+
+  double y = act ? Ys[li] : 0.;
+  double dif[7];
+#pragma unroll
+  for (int j = 0; j < 7; j++) dif[j] = 0.;
+  const double htspan = fabs(tfinal - t0);
+  double t = t0, tnew = t0;
+  env_at(P, t0, true, 0);
+  rhs_apply(P, V_Y, V_F0, 0);
+  if (lane == 0) M.st.fevals++;
+  const double f0i = act ? F[li] : 0.;
+  const double hmax = (tfinal - t0) / 10.0;
+  jacobian(P);
+  bool Jcurrent = true;
+  double hmin = 16.0 * eps * fabs(t);
+  const double wt0 = fmax(fabs(y), threshold);
+  double rh = wmax(act ? 1.25 / sqrt(rtol) * fabs(f0i / wt0) : 0.);
+  double absh = fmin(hmax, htspan);
+  if (absh * rh > 1.0) absh = 1.0 / rh;
+  absh = fmax(absh, hmin);
+  double h = absh;
+  {
+    rhs_apply(P, V_F0, V_PSI, 0);  // J*f0 = f(t0, f0): the system is linear and homogeneous
+    if (lane == 0) M.st.fevals++;
+    const double jf = act ? s_vec(P, V_PSI)[li] : 0.;
+    const double tdel = (t + fmin(sqrt(eps) * fmax(fabs(t), fabs(t + h)), absh)) - t;
+    env_at(P, t + tdel, true, 0);
+    rhs_apply(P, V_Y, V_DEL, 0);  // f(t+tdel, y)
+    if (lane == 0) M.st.fevals++;
+    const double s = act ? jf + (B[li] - f0i) / tdel : 0.;
+    rh = wmax(1.25 * sqrt(0.5 * fabs(s / wt0) / rtol));
+    absh = fmin(hmax, htspan);
+    if (absh * rh > 1.0) absh = 1.0 / rh;
+    absh = fmax(absh, hmin);
+    h = absh;
+  }
+  int k = 1, klast = k;
+  double abshlast = absh;
+  dif[0] = h * f0i;
+  double hinvGak = h * c_invGa[k - 1];
+  int nconhk = 0;
+  factor(P, hinvGak);
+  bool havrate = false;
+  bool done = false, at_hmin = false;
+  double rate = 0., oldnrm = 0., err = 0.;
+  double pred = 0., psi = 0., dk1 = 0., iw = 0.;
+
+  // difference-array rescaling in registers (adjust_stepsize)
+  auto rescale = [&](double r) {
+    double* RU = s_hubtmp(P);
+    if (lane < 25) {
+      const int ii = lane / 5, jj = lane % 5;
+      double s = 0.;
+#pragma unroll
+      for (int kk = 0; kk < 5; kk++) {
+        double Rv = 1.;
+        for (int mm = 1; mm <= ii + 1; mm++) Rv *= ((mm - 1) - (kk + 1) * r) / mm;
+        s += Rv * c_U[kk][jj];
+      }
+      RU[lane] = s;
+    }
+    __syncwarp();
+    double nd[5];
+#pragma unroll
+    for (int jj = 0; jj < 5; jj++) {
+      double s = 0.;
+#pragma unroll
+      for (int kk = 0; kk < 5; kk++) s += ((kk < k) ? dif[kk] : 0.) * RU[kk * 5 + jj];
+      nd[jj] = s;
+    }
+#pragma unroll
+    for (int jj = 0; jj < 5; jj++)
+      if (jj < k) dif[jj] = nd[jj];
+    __syncwarp();
+  };
+
+  while (!done) {
+    hmin = P.hmin_allowed;
+    absh = fmin(hmax, fmax(hmin, absh));
+    if (fabs(absh - hmin) < 100 * eps) {
+      if (at_hmin) absh = abshlast;
+      at_hmin = true;
+    } else {
+      at_hmin = false;
+    }
+    h = absh;
+    if (1.1 * absh >= fabs(tfinal - t)) {
+      h = tfinal - t;
+      absh = fabs(h);
+      done = true;
+    }
+    if (((fabs(absh - abshlast) / absh) > 1e-6) || (k != klast)) {
+      PROF_BEGIN();
+      rescale(absh / abshlast);
+      PROF_END(PF_ADJUST);
+      hinvGak = h * c_invGa[k - 1];
+      nconhk = 0;
+      PROF_BEGIN();
+      factor(P, hinvGak);
+      PROF_END(PF_FACTOR);
+      havrate = false;
+    }
+    bool nofailed = true;
+    for (;;) {  // loop for advancing one step
+      bool gotynew = false;
+      while (!gotynew) {
+        tnew = t + h;
+        if (done) tnew = tfinal;
+        h = tnew - t;
+        PROF_BEGIN();
+        const double invGak = c_invGa[k - 1];
+        psi = 0.;
+        pred = y;
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+          if (j < k) {
+            psi += dif[j] * c_G[j] * invGak;
+            pred += dif[j];
+          }
+        }
+        dk1 = 0.;
+        iw = 1.0 / fmax(fmax(fabs(pred), fabs(y)), threshold);
+        const double minnrm = wmax(act ? 100 * eps * fabs(pred * iw) : 0.);
+        if (act) YX[li] = pred;
+        __syncwarp();
+        PROF_END(PF_PREDICT);
+        PROF_BEGIN();
+        env_at(P, tnew, true, 0);
+        PROF_END(PF_ENV);
+        bool tooslow = false;
+        for (int iter = 1; iter <= maxit; iter++) {
+          PROF_BEGIN();
+          rhs_apply(P, V_YNEW, V_F0, 0);
+          PROF_END(PF_RHS);
+          if (lane == 0) M.st.fevals++;
+          PROF_BEGIN();
+          // residual into the exchange buffer, then x_i = sum_j Ainv[i][j] r_j (explicit hub inverse)
+          if (act) B[li] = hinvGak * F[li] - (psi + dk1);
+          __syncwarp();
+          double x0 = 0., x1 = 0.;
+          {
+            const double* w = s_sinv(P) + li * ldh;
+            int j = 0;
+            for (; j + 1 < n; j += 2) {
+              x0 += w[j] * B[j];
+              x1 += w[j + 1] * B[j + 1];
+            }
+            if (j < n) x0 += w[j] * B[j];
+          }
+          const double d = act ? x0 + x1 : 0.;
+          if (lane == 0) M.st.solves++;
+          PROF_END(PF_SOLVE);
+          PROF_BEGIN();
+          const double newnrm = wmax(fabs(d * iw));
+          dk1 += d;
+          if (act) YX[li] = pred + dk1;
+          __syncwarp();
+          PROF_END(PF_UPDATE);
+          if (newnrm <= minnrm) { gotynew = true; break; }
+          else if (iter == 1) {
+            if (havrate) {
+              const double errit = newnrm * rate / (1.0 - rate);
+              if (errit <= 0.05 * rtol) { gotynew = true; break; }
+            } else {
+              rate = 0.0;
+            }
+          } else if (newnrm > 0.9 * oldnrm) {
+            tooslow = true;
+            break;
+          } else {
+            rate = fmax(0.9 * rate, newnrm / oldnrm);
+            havrate = true;
+            const double errit = newnrm * rate / (1.0 - rate);
+            if (errit <= 0.5 * rtol) { gotynew = true; break; }
+            else if (iter == maxit) { tooslow = true; break; }
+            else {
+              double rp = rate;  // rate^(maxit-iter)
+              for (int q = 1; q < maxit - iter; q++) rp *= rate;
+              if (0.5 * rtol < errit * rp) { tooslow = true; break; }
+            }
+          }
+          oldnrm = newnrm;
+        }
+        if (tooslow) {
+          if (lane == 0) M.st.failed++;
+          if (!Jcurrent) {
+            if (act) Ys[li] = y;
+            __syncwarp();
+            env_at(P, t, true, 0);
+            rhs_apply(P, V_Y, V_F0, 0);
+            if (lane == 0) M.st.fevals++;
+            jacobian(P);
+            Jcurrent = true;
+          } else if (absh <= hmin) {
+            M.status = 2;  // step size too small
+            return false;
+          } else {
+            abshlast = absh;
+            absh = fmax(0.3 * absh, hmin);
+            h = absh;
+            done = false;
+            rescale(absh / abshlast);
+            hinvGak = h * c_invGa[k - 1];
+            nconhk = 0;
+          }
+          factor(P, hinvGak);
+          havrate = false;
+        }
+      }
+      // error estimate
+      err = wmax(fabs(dk1 * iw)) * c_erconst[k - 1];
+      if (err > rtol) {
+        if (lane == 0) M.st.failed++;
+        if (absh <= hmin) {
+          M.status = 2;
+          return false;
+        }
+        abshlast = absh;
+        if (nofailed) {
+          nofailed = false;
+          double hopt = absh * fmax(0.1, 0.833 * root_n(rtol / err, k + 1.0));
+          if (k > 1) {
+            const double errkm1 = wmax(fabs((pick7(dif, k - 1) + dk1) * iw)) * c_erconst[k - 2];
+            const double hkm1 = absh * fmax(0.1, 0.769 * root_n(rtol / errkm1, (double)k));
+            if (hkm1 > hopt) {
+              hopt = fmin(absh, hkm1);
+              k = k - 1;
+            }
+          }
+          absh = fmax(hmin, hopt);
+        } else {
+          absh = fmax(hmin, 0.5 * absh);
+        }
+        h = absh;
+        if (absh < abshlast) done = false;
+        rescale(absh / abshlast);
+        hinvGak = h * c_invGa[k - 1];
+        nconhk = 0;
+        factor(P, hinvGak);
+        havrate = false;
+      } else {
+        break;
+      }
+    }
+    if (lane == 0) M.st.steps++;
+    PROF_BEGIN();
+    // update the difference array: dif[k+1] = dk1 - dif[k]; dif[k] = dk1; dif[j] += dif[j+1] (j < k)
+    {
+      const double difk_old = pick7(dif, k);
+#pragma unroll
+      for (int j = 6; j >= 0; j--) {
+        if (j == k + 1) dif[j] = dk1 - difk_old;
+        else if (j == k) dif[j] = dk1;
+        else if (j < k) dif[j] += dif[j + 1];
+      }
+    }
+    PROF_END(PF_DIFUPD);
+    PROF_BEGIN();
+    // ---- output at the sample times passed by this step (YX holds ynew, F the last Newton RHS)
+    while ((next < tres) && ((tnew - tnext) >= 0.0)) {
+      if (tnew == tnext) {
+        if (act) YX[li] = pred + dk1;
+        __syncwarp();
+        write_sources(P, tnext, V_YNEW, V_F0, next);
+      } else {
+        const double s = (tnext - tnew) / h;
+        double a1 = 0, a2 = 0;
+        double prod = 1.0, sumfrac = 0., fact = 1.0;
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+          if (j < k) {
+            prod *= (s + j);
+            fact *= (j + 1);
+            sumfrac += 1.0 / (s + j);
+            a1 += prod / fact * dif[j];
+            a2 += prod * sumfrac / (h * fact) * dif[j];
+          }
+        }
+        if (act) {
+          s_vec(P, V_TMP)[li] = (pred + dk1) + a1;
+          s_vec(P, V_YPI)[li] = a2;
+        }
+        __syncwarp();
+        write_sources(P, tnext, V_TMP, V_YPI, next);
+      }
+      next++;
+      tnext = (next < tres) ? __ldg(t_vec + next) : 1e300;
+    }
+    PROF_END(PF_OUTPUT);
+    if (done) break;
+    PROF_BEGIN();
+    klast = k;
+    abshlast = absh;
+    nconhk = min(nconhk + 1, maxk + 2);
+    if (nconhk >= k + 2) {
+      double e_km1 = 0., e_kp1 = 0.;
+      if (k > 1) e_km1 = wmax(fabs(pick7(dif, k - 1) * iw)) * c_erconst[k - 2];
+      if (k < maxk) e_kp1 = wmax(fabs(pick7(dif, k + 1) * iw)) * c_erconst[k];
+      const double my_e = lane == 0 ? err : lane == 1 ? e_km1 : e_kp1;
+      const double my_c = lane == 0 ? 1.2 : lane == 1 ? 1.3 : 1.4;
+      const double my_n = lane == 0 ? k + 1.0 : lane == 1 ? (double)k : k + 2.0;
+      double temp = 0.;
+      if (my_e > 0.) temp = my_c * root_n(my_e / rtol, my_n);
+      const double my_h = (temp > 0.1) ? absh / temp : 10 * absh;
+      double hopt = __shfl_sync(PT_FULL, my_h, 0);
+      const double hkm1 = __shfl_sync(PT_FULL, my_h, 1), hkp1 = __shfl_sync(PT_FULL, my_h, 2);
+      int kopt = k;
+      if (k > 1 && hkm1 > hopt) { hopt = hkm1; kopt = k - 1; }
+      if (k < maxk && hkp1 > hopt) { hopt = hkp1; kopt = k + 1; }
+      if (hopt > absh) {
+        absh = hopt;
+        if (k != kopt) k = kopt;
+      }
+    }
+    t = tnew;
+    y = pred + dk1;
+    Jcurrent = false;
+    PROF_END(PF_CONTROL);
+  }
+  // final state and a last RHS call so that the by-products are current (evolver_ndf15.cpp:653-662)
+  y = pred + dk1;
+  if (act) Ys[li] = y;
+  __syncwarp();
+  env_at(P, tnew, true, 0);
+  rhs_apply(P, V_Y, V_F0, 0);
+  if (lane == 0) M.st.fevals++;
   M.next = next;
   return true;
 }
@@ -1396,17 +1807,20 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
 // perturb_initial_conditions: adiabatic mode, synchronous gauge, flat space
 __device__ __noinline__ void initial_conditions(const PtParams& P, double tau) {
   Mode& M = MODE(P);
-  env_at(P, tau, false);
+  env_at(P, tau, false, 0);
   const Env& e = M.e;
   const Layout& L = M.L;
   const int lane = (int)threadIdx.x;
   const double k = M.k, a = e.a;
   double* y = s_vec(P, V_Y);
-  double rho_r = e.rho_g, rho_m = e.rho_b + e.rho_cdm, rho_nu = 0.;
-  if (P.has_ur) { rho_r += e.rho_ur; rho_nu += e.rho_ur; }
+  const double* pvb0 = s_pvb(P);
+  const double e_rho_g = pvb0[P.irho_g], e_rho_b = pvb0[P.irho_b], e_rho_cdm = pvb0[P.irho_cdm];
+  const double e_rho_ur = P.has_ur ? pvb0[P.irho_ur] : 0.;
+  double rho_r = e_rho_g, rho_m = e_rho_b + e_rho_cdm, rho_nu = 0.;
+  if (P.has_ur) { rho_r += e_rho_ur; rho_nu += e_rho_ur; }
   for (int s = 0; s < P.N_ncdm; s++) { rho_r += s_pvb(P)[P.irho_ncdm1 + s]; rho_nu += s_pvb(P)[P.irho_ncdm1 + s]; }
   const double fracnu = rho_nu / rho_r;
-  const double fracb = e.rho_b / rho_m;
+  const double fracb = e_rho_b / rho_m;
   const double om = a * rho_m / sqrt(rho_r);
   const double ktau_two = k * k * tau * tau, ktau_three = k * tau * ktau_two;
   const double ci = P.curvature_ini;
@@ -1480,7 +1894,7 @@ __device__ __noinline__ void remap_state(const PtParams& P) {
     if (Ln.shear_g >= 0 && Lo.shear_g < 0) {
       // tight coupling switched off: seed the hierarchy from the TCA expressions (:3909-3915);
       // tca_shear_g and kappa' are those of the last RHS call of the previous interval
-      const double sg = M.m.tca_shear_g, dk = M.e.dkappa;
+      const double sg = M.m.tca_shear_g, dk = s_pvt(P)[P.idkappa];
       yn[Ln.shear_g] = sg;
       yn[Ln.l3_g] = 6. / 7. * k / dk * sg;
       yn[Ln.pol0_g] = 2.5 * sg;
@@ -1535,7 +1949,10 @@ __device__ __noinline__ void remap_state(const PtParams& P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) perturb_kernel(const __grid_constant__ PtParams P) {
+#ifndef PT_MIN_BLOCKS
+#define PT_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid_constant__ PtParams P) {
   if ((int)blockIdx.x >= P.n_modes) return;
   Mode& M = MODE(P);
   const int lane = (int)threadIdx.x;
@@ -1549,8 +1966,14 @@ __global__ void __launch_bounds__(32) perturb_kernel(const __grid_constant__ PtP
     M.k2 = M.k * M.k;
     M.inv_k = 1.0 / M.k;
     M.inv_k2 = 1.0 / M.k2;
-    M.cur_bg = 0; M.cur_th = C->tt_size - 2;
-    M.bx0 = 1.; M.bx1 = 0.; M.tx0 = 1.; M.tx1 = 0.;
+    M.bg_tau = C->bg_tau; M.bg_y = C->bg_y; M.bg_dd = C->bg_dd;
+    M.th_z = C->th_z; M.th_y = C->th_y; M.th_dd = C->th_dd;
+    M.bt_size = C->bt_size; M.tt_size = C->tt_size;
+    M.z_last = C->th_z[C->tt_size - 1]; M.th_lin = C->th_linear_below_z; M.a_today = C->a_today;
+    for (int q = 0; q < 2; q++) {
+      M.bgc[q].x0 = 1.; M.bgc[q].x1 = 0.; M.bgc[q].cur = 0;
+      M.thc[q].x0 = 1.; M.thc[q].x1 = 0.; M.thc[q].cur = C->tt_size - 2;
+    }
     M.need_nw = 0;
     M.nh = 0; M.nch = 0;
     M.status = 0;
@@ -1561,8 +1984,6 @@ __global__ void __launch_bounds__(32) perturb_kernel(const __grid_constant__ PtP
     M.ap.tca_off = M.ap.rsa_on = M.ap.ufa_on = M.ap.ncdmfa_on = 0;
     for (int q = 0; q < PF_COUNT; q++) M.prof[q] = 0;
   }
-#pragma unroll
-  for (int q = 0; q < 4; q++) { M.bc[q][lane] = 0.; M.tc[q][lane] = 0.; }
   for (int l = lane; l < P.n_i2l1; l += 32) s_i2l1(P)[l] = 1.0 / (2.0 * l + 1.0);
   __syncwarp();
   const double tau_first = C->tau[0];
@@ -1572,8 +1993,8 @@ __global__ void __launch_bounds__(32) perturb_kernel(const __grid_constant__ PtP
   double tau_lower = C->bg_tau[0], tau_upper = tau_first;
   int status = 0;
   {
-    env_at(P, tau_lower, false);
-    if (M.e.a * M.e.H / M.e.dkappa > P.start_small_k_at_tau_c_over_tau_h) status = 3;
+    env_at(P, tau_lower, false, 0);
+    if (M.e.a * M.e.H / s_pvt(P)[P.idkappa] > P.start_small_k_at_tau_c_over_tau_h) status = 3;
     if (M.k / M.e.a / M.e.H > P.start_large_k_at_tau_h_over_tau_k) status = 4;
     for (int s = 0; s < P.N_ncdm; s++)
       if (fabs(s_pvb(P)[P.ip_ncdm1 + s] / s_pvb(P)[P.irho_ncdm1 + s] - 1. / 3.) > P.tol_ncdm_initial_w) status = 5;
@@ -1581,12 +2002,12 @@ __global__ void __launch_bounds__(32) perturb_kernel(const __grid_constant__ PtP
   double tau_mid = 0.5 * (tau_lower + tau_upper);
   if (status == 0) {
     while ((tau_upper - tau_lower) / tau_lower > P.tol_tau_approx) {
-      env_at(P, tau_mid, false);
+      env_at(P, tau_mid, false, 0);
       bool early = true;
       for (int s = 0; s < P.N_ncdm; s++)
         if (fabs(s_pvb(P)[P.ip_ncdm1 + s] / s_pvb(P)[P.irho_ncdm1 + s] - 1. / 3.) > P.tol_ncdm_initial_w) early = false;
       if (early) {
-        if ((M.e.a * M.e.H / M.e.dkappa > P.start_small_k_at_tau_c_over_tau_h) ||
+        if ((M.e.a * M.e.H / s_pvt(P)[P.idkappa] > P.start_small_k_at_tau_c_over_tau_h) ||
             (M.k / M.e.a / M.e.H > P.start_large_k_at_tau_h_over_tau_k))
           early = false;
       }
@@ -1658,11 +2079,11 @@ __global__ void __launch_bounds__(32) perturb_kernel(const __grid_constant__ PtP
     else remap_state(P);
     make_structure(P);
     M.need_nw = P.has_ncdm && !apn.ncdmfa_on;
-    M.bx0 = 1.; M.bx1 = 0.;  // the first lookup of the interval refreshes everything
     __syncwarp();
     const long long c0 = clock64();
     const int s0 = M.st.steps;
-    const bool ok = ndf15(P, M.limit[iv], M.limit[iv + 1]);
+    const bool ok = (M.nch == 0 && M.L.neq <= 32) ? ndf15_hub(P, M.limit[iv], M.limit[iv + 1])
+                                                   : ndf15(P, M.limit[iv], M.limit[iv + 1]);
     __syncwarp();
     if (lane == 0) {
       ks->iv_neq[iv] = M.L.neq;

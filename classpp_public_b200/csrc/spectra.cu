@@ -179,7 +179,7 @@ int clpp_dev_spectra(clpp_ctx* c, const double* primordial_pk, int q_begin, int 
   spline_integration_weights(c->kq, w);
   std::vector<double> W(T.q_size);
   for (int i = 0; i < T.q_size; i++) W[i] = w[i] * (4. * CLPP_PI / c->kq[i]) * primordial_pk[i];
-  if (!d->wq) CLPP_CUDA(cudaMalloc((void**)&d->wq, T.q_size * sizeof(double)), err);
+  if (clpp_dev_reserve(d, &d->wq, (size_t)T.q_size, err)) return CLPP_FAILURE;
   CLPP_CUDA(cudaMemcpyAsync(d->wq, W.data(), T.q_size * sizeof(double), cudaMemcpyHostToDevice, d->stream), err);
 
   SpectraParams P;
@@ -191,9 +191,7 @@ int clpp_dev_spectra(clpp_ctx* c, const double* primordial_pk, int q_begin, int 
   P.ct_tt = I.index_ct_tt; P.ct_ee = I.index_ct_ee; P.ct_te = I.index_ct_te; P.ct_bb = I.index_ct_bb;
   P.ct_pp = I.index_ct_pp; P.ct_tp = I.index_ct_tp; P.ct_ep = I.index_ct_ep;
 
-  if (d->cl) { cudaFree(d->cl); d->cl = nullptr; }
-  CLPP_CUDA(cudaMalloc((void**)&d->cl, ((size_t)T.l_size * I.ct_size + (size_t)T.l_size * P.n_chunk * 6) * sizeof(double)),
-            err);
+  if (clpp_dev_reserve(d, &d->cl, (size_t)T.l_size * I.ct_size + (size_t)T.l_size * P.n_chunk * 6, err)) return CLPP_FAILURE;
   double* partial = d->cl + (size_t)T.l_size * I.ct_size;
   dim3 grid(T.l_size, P.n_chunk);
   cudaEventRecord(d->ev[0], d->stream);

@@ -448,12 +448,7 @@ los_kernel(LosParams P, const double* __restrict__ kgrid, const double* __restri
 // =============================================================================================
 // host driver
 // =============================================================================================
-template <typename T>
-static int dev_alloc(T** p, size_t n, char* err) {
-  if (*p) { cudaFree(*p); *p = nullptr; }
-  CLPP_CUDA(cudaMalloc((void**)p, n * sizeof(T)), err);
-  return CLPP_SUCCESS;
-}
+#define dev_alloc(p, n, err) clpp_dev_reserve(d, p, n, err)
 
 int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_begin, int q_end, char* err) {
   clpp_ctx::Dev* d = c->dev;
@@ -495,17 +490,15 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
     c->launches++;
   }
   {
-    double* u = nullptr;
-    CLPP_CUDA(cudaMalloc((void**)&u, nsrc * sizeof(double)), err);
+    if (dev_alloc(&d->spline_u, nsrc, err)) return CLPP_FAILURE;
+    for (int i = 0; i < 6; i++)
+      if (!d->ev2[i]) cudaEventCreate(&d->ev2[i]);
     const int n = ntp * nt;
-    cudaEventRecord(d->ev[0], st);
-    k_spline_kernel<<<(n + 127) / 128, 128, 0, st>>>(ntp, nk, nt, d->k, d->src_tr, d->src_ddk, u);
-    cudaEventRecord(d->ev[1], st);
+    cudaEventRecord(d->ev2[0], st);
+    k_spline_kernel<<<(n + 127) / 128, 128, 0, st>>>(ntp, nk, nt, d->k, d->src_tr, d->src_ddk, d->spline_u);
+    cudaEventRecord(d->ev2[1], st);
     c->launches++;
     CLPP_CUDA(cudaGetLastError(), err);
-    CLPP_CUDA(cudaStreamSynchronize(st), err);
-    { float ms = 0; cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); d->t_kspline_ms = ms; }
-    cudaFree(u);
   }
 
   // (b) flat Bessel table (hyperspherical_HIS_create with K=0, beta=1)
@@ -529,12 +522,12 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
     if (dev_alloc(&d->bessel_x, nx, err) || dev_alloc(&d->bessel_phi, nb, err) || dev_alloc(&d->bessel_dphi, nb, err) ||
         dev_alloc(&d->chi_at_phimin, TI.l_size_max, err))
       return CLPP_FAILURE;
-    int* scale_count = nullptr;
-    CLPP_CUDA(cudaMalloc((void**)&scale_count, nb * sizeof(int)), err);
-    cudaEventRecord(d->ev[0], st);
+    if (dev_alloc(&d->bessel_scale, nb, err)) return CLPP_FAILURE;
+    int* scale_count = d->bessel_scale;
+    cudaEventRecord(d->ev2[2], st);
     bessel_table_kernel<<<(nx + 63) / 64, 64, 0, st>>>(nx, xmin, dx, std::min(nx, xfwdidx), lmax + 1, TI.l_size_max, d->l,
                                                       d->bessel_x, d->bessel_phi, d->bessel_dphi, scale_count);
-    cudaEventRecord(d->ev[1], st);
+    cudaEventRecord(d->ev2[3], st);
     c->launches++;
     CLPP_CUDA(cudaGetLastError(), err);
     // chi_at_phimin (hyperspherical_get_xmin_from_approx, hyperspherical.c:1419-1457, K=0, nu=1)
@@ -545,10 +538,8 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
       const double alpha = -2.0 * lhs / 5.0 * (1.0 + 2.0 * cosh(1.0 / 3.0 * acosh(1.0 + 375.0 / (16.0 * lhs * lhs))));
       chi[i] = lph / cosh(alpha) / 1.0;
     }
-    CLPP_CUDA(cudaMemcpyAsync(d->chi_at_phimin, chi.data(), chi.size() * sizeof(double), cudaMemcpyHostToDevice, st), err);
-    CLPP_CUDA(cudaStreamSynchronize(st), err);
-    { float ms = 0; cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); d->t_bessel_ms = ms; }
-    cudaFree(scale_count);
+    c->chi_host = chi;  // must outlive the asynchronous copy
+    CLPP_CUDA(cudaMemcpyAsync(d->chi_at_phimin, c->chi_host.data(), chi.size() * sizeof(double), cudaMemcpyHostToDevice, st), err);
   }
 
   // (c) line-of-sight integrals
@@ -599,7 +590,12 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
   unsigned long long cnt[2];
   CLPP_CUDA(cudaMemcpyAsync(cnt, d->tr_counters, sizeof(cnt), cudaMemcpyDeviceToHost, st), err);
   CLPP_CUDA(cudaStreamSynchronize(st), err);
-  { float ms = 0; cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); d->t_los_ms = ms; }
+  {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); d->t_los_ms = ms;
+    cudaEventElapsedTime(&ms, d->ev2[0], d->ev2[1]); d->t_kspline_ms = ms;
+    cudaEventElapsedTime(&ms, d->ev2[2], d->ev2[3]); d->t_bessel_ms = ms;
+  }
   c->tinfo.n_integrals = (long)cnt[0];
   c->tinfo.n_points = (long)cnt[1];
   c->has_transfer = true;
