@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclpp.so")
+LIB_PATH = os.environ.get("CLPP_LIB") or os.path.join(_HERE, "libclpp.so")  # CLPP_LIB: developer override (build variants)
 ERRLEN = 2048
 
 

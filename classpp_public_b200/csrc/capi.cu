@@ -69,7 +69,7 @@ void clpp_ctx_destroy(clpp_ctx* c) {
     void* ptrs[] = {d->bg_tau, d->bg_y, d->bg_dd, d->th_z, d->th_y, d->th_dd, d->k, d->tau, d->sources, d->kstat,
                     d->k_order, d->queue_head, d->jac_scratch, d->q, d->kq, d->l, d->bessel_x, d->bessel_phi,
                     d->bessel_dphi, d->chi_at_phimin, d->src_tr, d->src_ddk, d->nl_corr, d->transfer, d->tr_counters,
-                    d->pk, d->wq, d->cl, d->ncdm, d->pt_cosmo, d->pt_modes, d->spline_u, d->bessel_scale};
+                    d->pk, d->wq, d->cl, d->ncdm, d->pt_cosmo, d->pt_modes, d->spline_u, d->bessel_scale, d->pt_tail};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     for (int i = 0; i < 6; i++)

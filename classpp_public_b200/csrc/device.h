@@ -27,6 +27,8 @@ struct clpp_ctx::Dev {
   int* queue_head = nullptr;  // atomic cursor into k_order
   double* jac_scratch = nullptr;  // per-CTA global workspace: hub block of the Jacobian
   double* ncdm = nullptr;         // [3][nq_tot]: q, w, dlnf0/dlnq
+  double* pt_tail = nullptr;      // hand-off records perturb_kernel -> perturb_tail_kernel
+  size_t pt_tail_cap = 0;
   unsigned char *pt_cosmo = nullptr, *pt_modes = nullptr;  // batch descriptors of the last solve (PtCosmo[], int2[])
   size_t sources_count = 0;
   size_t k_cap = 0, tau_cap = 0, kstat_cap = 0, jac_cap = 0, ncdm_cap = 0, pt_cosmo_cap = 0, pt_modes_cap = 0;

@@ -67,6 +67,7 @@ struct PtParams {
   const int2* modes;  // (cosmology index, k index), decreasing expected cost
   int n_modes;
   double* hub_jac;  // per-CTA global scratch [nh_max*nh_max]: hub block of the Jacobian
+  double* tail;     // per-mode hand-off records for perturb_tail_kernel (nullptr: no tail kernel)
   int bg_size, bg_size_normal, th_size;
   // background column indices
   int ia, iH, iHp, irho_g, irho_b, irho_cdm, irho_ur, irho_ncdm1, ip_ncdm1, ipseudo_p_ncdm1;
@@ -116,6 +117,8 @@ __constant__ double c_erconst[5] = {-37.0 / 200 * 1.0 + 1.0 / 2.0, -1.0 / 9.0 * 
                                     -8.23e-2 * (11.0 / 6.0) + 1.0 / 4.0, -4.15e-2 * (25.0 / 12.0) + 1.0 / 5.0,
                                     1.0 / 6.0};
 // difference-array rescaling matrix U (evolver_ndf15.cpp:907-943)
+// 1/m for the R(r) recurrence of adjust_stepsize
+__constant__ double c_invint[7] = {0., 1.0, 0.5, 1.0 / 3.0, 0.25, 0.2, 1.0 / 6.0};
 __constant__ double c_U[5][5] = {{-1, -2, -3, -4, -5}, {0, 1, 3, 6, 10}, {0, 0, -1, -4, -10}, {0, 0, 0, 1, 5}, {0, 0, 0, 0, -1}};
 
 struct Approx {
@@ -216,7 +219,7 @@ __device__ __forceinline__ int locate_closeby(const double* __restrict__ X, int 
 #define PROF_BEGIN()
 #define PROF_END(slot)
 #endif
-enum { PF_ENV = 0, PF_RHS, PF_SOLVE, PF_PREDICT, PF_UPDATE, PF_CONTROL, PF_FACTOR, PF_ADJUST, PF_OUTPUT, PF_JAC, PF_DIFUPD, PF_COUNT };
+enum { PF_ENV = 0, PF_RHS, PF_SOLVE, PF_PREDICT, PF_UPDATE, PF_CONTROL, PF_FACTOR, PF_ADJUST, PF_OUTPUT, PF_JAC, PF_DIFUPD, PF_X, PF_COUNT };
 
 // per-mode statistics (copied to the public clpp_kstat at the end)
 struct Stat {
@@ -236,7 +239,7 @@ struct Mode {
   // per-cosmology scalars and table pointers (copied from PtCosmo once per mode)
   const double *bg_tau, *bg_y, *bg_dd, *th_z, *th_y, *th_dd;
   double z_last, th_lin, a_today;
-  double q[2 * PT_MAX_NCDM + 2];
+  double q[4 * PT_MAX_NCDM];
   int bt_size, tt_size;
   Env e;
   Metric m;
@@ -265,6 +268,8 @@ __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby,
   const int lane = (int)threadIdx.x;
   double* pvb = s_pvb(P);
   double* pvt = s_pvt(P);
+  PROF_DECL;
+  PROF_BEGIN();
   // background
   {
     TabCache& T = M.bgc[set];
@@ -292,6 +297,8 @@ __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby,
       pvb[lane] = a * T.c[0][lane] + b * T.c[1][lane] + ((a * a * a - a) * T.c[2][lane] + (b * b * b - b) * T.c[3][lane]) * T.h26;
   }
   __syncwarp();
+  PROF_END(PF_JAC);
+  PROF_BEGIN();
   const double av = pvb[P.ia], Hv = pvb[P.iH], Hp = pvb[P.iHp];
   const double inv_a = 1. / av;
   const double z = inv_a - 1.;
@@ -353,6 +360,7 @@ __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby,
       pvt[lane] = v;
     }
   }
+  PROF_END(PF_X);
   // momentum-dependent ncdm weights at this scale factor (used by the RHS while the ncdm hierarchy is integrated)
   if (M.need_nw) {
     const double a2 = av * av;
@@ -374,53 +382,60 @@ __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby,
     }
   }
   __syncwarp();
-  // derived quantities: one SIMD division, the quotient of lane j is DRV j (and, from lane 8 on, the
-  // ratios w = p/rho and pseudo_p/p of the ncdm species for the fluid approximation)
+  // derived quantities: ONE SIMD division; lane j < 6 produces DRV j, lanes 8+4s.. the ratios of ncdm
+  // species s needed by the fluid approximation (w = p/rho, pseudo_p/p, 1/(1+w), 1/w).  Selects only,
+  // no lane-divergent branches.
   {
     const double rho_g = pvb[P.irho_g], rho_b = pvb[P.irho_b], dkappa = pvt[P.idkappa];
     const double aH = Hv * av;
     double num = 1., den = 1.;
-    if (lane == DRV_INV_R) { num = 0.75 * rho_b; den = rho_g; }
-    else if (lane == DRV_R) { num = 4. / 3. * rho_g; den = rho_b; }
-    else if (lane == DRV_INV_1PR) { num = rho_b; den = rho_b + 4. / 3. * rho_g; }
-    else if (lane == DRV_INV_HALF_AH) { num = 2.; den = aH; }
-    else if (lane == DRV_INV_TAU) { den = tau; }
-    else if (lane == DRV_TAU_C) { den = dkappa; }
-    else if (lane >= 8 && lane < 8 + 2 * P.N_ncdm) {
-      const int s = (lane - 8) >> 1;
-      const double p_n = pvb[P.ip_ncdm1 + s];
-      if (lane & 1) { num = pvb[P.ipseudo_p_ncdm1 + s]; den = p_n; }
-      else { num = p_n; den = pvb[P.irho_ncdm1 + s]; }
+    num = (lane == DRV_INV_R) ? 0.75 * rho_b : num;          den = (lane == DRV_INV_R) ? rho_g : den;
+    num = (lane == DRV_R) ? 4. / 3. * rho_g : num;           den = (lane == DRV_R) ? rho_b : den;
+    num = (lane == DRV_INV_1PR) ? rho_b : num;               den = (lane == DRV_INV_1PR) ? rho_b + 4. / 3. * rho_g : den;
+    num = (lane == DRV_INV_HALF_AH) ? 2. : num;              den = (lane == DRV_INV_HALF_AH) ? aH : den;
+    den = (lane == DRV_INV_TAU) ? tau : den;
+    den = (lane == DRV_TAU_C) ? dkappa : den;
+    const bool fluid = P.has_ncdm && M.ap.ncdmfa_on;
+    if (fluid) {
+      const int s = min(max((lane - 8) >> 2, 0), P.N_ncdm - 1), r = (lane - 8) & 3;
+      const bool mine = lane >= 8 && lane < 8 + 4 * P.N_ncdm;
+      const double rho_n = pvb[P.irho_ncdm1 + s], p_n = pvb[P.ip_ncdm1 + s], pseudo = pvb[P.ipseudo_p_ncdm1 + s];
+      const double nn = r == 0 ? p_n : r == 1 ? pseudo : rho_n;
+      const double dd = r == 0 ? rho_n : r == 1 ? p_n : r == 2 ? rho_n + p_n : p_n;
+      num = mine ? nn : num;
+      den = mine ? dd : den;
     }
     const double q = num / den;
     if (lane < 6) M.e.drv[lane] = q;
-    else if (lane >= 8 && lane < 8 + 2 * PT_MAX_NCDM) M.q[lane - 8] = q;
+    else if (lane >= 8 && lane < 8 + 4 * PT_MAX_NCDM) M.q[lane - 8] = q;
     if (lane == 6) {
       const double a_rel = M.a_today * inv_a;
       M.e.drv[DRV_FAC_NCDM] = (a_rel * a_rel) * (a_rel * a_rel);
       M.e.tau = tau; M.e.a = av; M.e.H = Hv; M.e.Hp = Hp;
     }
-  }
-  __syncwarp();
-  // ncdm fluid constants (perturb_derivs_member :8800-8850, perturb_total_stress_energy :6380-6400)
-  if (P.has_ncdm && M.ap.ncdmfa_on) {
-    if (lane < P.N_ncdm) {
-      const int s = lane;
+    __syncwarp();
+    // ncdm fluid constants (perturb_derivs_member :8800-8850, perturb_total_stress_energy :6380-6400);
+    // lane j < 8 N_ncdm writes constant (j & 7) of species (j >> 3)
+    if (fluid) {
+      const int s = min(lane >> 3, P.N_ncdm - 1), c8 = lane & 7;
       const double rho_n = pvb[P.irho_ncdm1 + s], p_n = pvb[P.ip_ncdm1 + s];
-      const double aH = Hv * av;
-      const double w_n = M.q[2 * s], pseudo_p_over_p = M.q[2 * s + 1];
-      const double i1w = 1.0 / (1.0 + w_n);
+      const double w_n = M.q[4 * s], pseudo_p_over_p = M.q[4 * s + 1], i1w = M.q[4 * s + 2], inv_w = M.q[4 * s + 3];
       const double cg2 = w_n * (1.0 - i1w * (1. / 3.) * (3.0 * w_n - 2.0 + pseudo_p_over_p));
       const double ca2 = w_n * (1. / 3.) * i1w * (5.0 - pseudo_p_over_p);
       const double cvis2 = (P.ncdmfa_method == CLPP_NCDMFA_HU) ? w_n : 3. * w_n * ca2;
-      double* nf = M.nf[s];
-      nf[0] = rho_n; nf[1] = rho_n + p_n; nf[2] = w_n; nf[3] = cg2 * rho_n; nf[4] = ca2;
-      nf[5] = ca2 * i1w;
-      nf[6] = 8.0 / 3.0 * cvis2 * i1w;
-      nf[7] = (P.ncdmfa_method == CLPP_NCDMFA_HU) ? 3.0 * aH * ca2 / w_n
-                                                  : 3.0 * (aH * (2. / 3. - ca2 - pseudo_p_over_p * (1. / 3.)) + M.e.drv[DRV_INV_TAU]);
+      const double damp = (P.ncdmfa_method == CLPP_NCDMFA_HU) ? 3.0 * aH * ca2 * inv_w
+                                                              : 3.0 * (aH * (2. / 3. - ca2 - pseudo_p_over_p * (1. / 3.)) + 1.0 / tau);
+      double v = rho_n;                          // [0] rho
+      v = c8 == 1 ? rho_n + p_n : v;             // [1] rho + p
+      v = c8 == 2 ? w_n : v;                     // [2] w
+      v = c8 == 3 ? cg2 * rho_n : v;             // [3] cg2 rho
+      v = c8 == 4 ? ca2 : v;                     // [4] ca2 (= ceff2)
+      v = c8 == 5 ? ca2 * i1w : v;               // [5] ceff2 / (1+w)
+      v = c8 == 6 ? 8.0 / 3.0 * cvis2 * i1w : v; // [6] 8/3 cvis2 / (1+w)
+      v = c8 == 7 ? damp : v;                    // [7] shear damping rate
+      if (lane < 8 * P.N_ncdm) M.nf[s][c8] = v;
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -1803,6 +1818,496 @@ __device__ __noinline__ bool ndf15_hub(const PtParams& P, double t0, double tfin
   return true;
 }
 
+
+// =============================================================================================
+// TAIL: the radiation-streaming interval (RSA on, ncdm fluid on if any): hub-only, neq = 4 + 3 N_ncdm.
+// It is the last interval of every mode and, for k >~ 0.1/Mpc, by far the longest one
+// (10^4 .. 3x10^5 steps), so it runs in its own kernel (perturb_tail_kernel) whose hot loop is small
+// enough for the instruction cache and keeps EVERYTHING in registers: lane i owns equation i, the
+// state is exchanged with warp shuffles, the Newton matrix inverse is one row per lane.
+// State order (make_layout with rsa_on): delta_b, theta_b, delta_cdm, [delta, theta, shear](ncdm s), eta.
+// =============================================================================================
+template <int N>
+__device__ __forceinline__ double pickN(const double (&d)[N], int j) {
+  double v = d[0];
+#pragma unroll
+  for (int q = 1; q < N; q++) v = (j == q) ? d[q] : v;
+  return v;
+}
+
+// time-dependent scalars of the RSA right-hand side, loaded once per step (uniform registers)
+struct RsaEnv {
+  double a2, aH, rho_b, rho_cdm, rho_g, rho_ur, dkappa, ddkappa, cb2, R, inv_half_aH;
+};
+__device__ __forceinline__ void rsa_env_load(const PtParams& P, const Mode& M, RsaEnv& E) {
+  const double* pvb = s_pvb(P);
+  const double* pvt = s_pvt(P);
+  E.a2 = M.e.a * M.e.a; E.aH = M.e.a * M.e.H;
+  E.rho_b = pvb[P.irho_b]; E.rho_cdm = pvb[P.irho_cdm]; E.rho_g = pvb[P.irho_g];
+  E.rho_ur = P.has_ur ? pvb[P.irho_ur] : 0.;
+  E.dkappa = pvt[P.idkappa]; E.ddkappa = pvt[P.iddkappa]; E.cb2 = pvt[P.icb2];
+  E.R = M.e.drv[DRV_R]; E.inv_half_aH = M.e.drv[DRV_INV_HALF_AH];
+}
+
+// f(tau, y) for the RSA interval: every lane evaluates all equations from the uniform y[] and returns
+// the derivative of ITS equation (perturb_total_stress_energy / perturb_einstein /
+// perturb_rsa_delta_and_theta / perturb_derivs_member restricted to this approximation set)
+template <int N>
+__device__ __forceinline__ double rhs_rsa(const PtParams& P, const Mode& M, const RsaEnv& E, const double (&y)[N],
+                                          int lane, int n_ncdm, double k2, double ik2) {
+  const double delta_b = y[0], theta_b = y[1], delta_cdm = y[2];
+  const double eta = pickN<N>(y, 3 + 3 * n_ncdm);
+  double delta_rho = E.rho_b * delta_b + E.rho_cdm * delta_cdm;
+  double rpt = E.rho_b * theta_b;
+  double rps = 0.;
+#pragma unroll
+  for (int s = 0; s < PT_MAX_NCDM; s++) {
+    if (3 + 3 * s + 2 < N && s < n_ncdm) {
+      const double* nf = M.nf[s];
+      delta_rho += nf[0] * y[3 + 3 * s];
+      rpt += nf[1] * y[4 + 3 * s];
+      rps += nf[1] * y[5 + 3 * s];
+    }
+  }
+  const double aH = E.aH;
+  const double h_prime = (k2 * eta + 1.5 * E.a2 * delta_rho) * E.inv_half_aH;
+  double rsa_delta_g = 0., rsa_theta_g = 0.;
+  if (P.rsa_method != CLPP_RSA_NULL) {
+    rsa_delta_g = 4. * ik2 * (aH * h_prime - k2 * eta);
+    rsa_theta_g = -0.5 * h_prime;
+  }
+  const double rsa_delta_ur = rsa_delta_g, rsa_theta_ur = rsa_theta_g;  // before the reionisation correction
+  if (P.rsa_method == CLPP_RSA_MD_WITH_REIO) {
+    rsa_delta_g += -4. * ik2 * E.dkappa * (theta_b + 0.5 * h_prime);
+    rsa_theta_g += 3. * ik2 * (E.ddkappa * (theta_b + 0.5 * h_prime) +
+                               E.dkappa * (-aH * theta_b + E.cb2 * k2 * delta_b - aH * h_prime + k2 * eta));
+  }
+  rpt += 4. / 3. * E.rho_g * rsa_theta_g;
+  if (P.has_ur) rpt += 4. / 3. * E.rho_ur * rsa_theta_ur;
+  (void)rsa_delta_ur;
+  const double eta_prime = (1.5 * E.a2 * rpt) * ik2;
+  const double alpha = (h_prime + 6. * eta_prime) * 0.5 * ik2;
+  const double metric_continuity = 0.5 * h_prime;
+  const double metric_shear = k2 * alpha;
+  (void)rps;
+  double d = 0.;
+  if (lane == 0) d = -(theta_b + metric_continuity);
+  else if (lane == 1) d = -aH * theta_b + k2 * E.cb2 * delta_b + E.R * E.dkappa * (rsa_theta_g - theta_b);
+  else if (lane == 2) d = -metric_continuity;
+  else if (lane == 3 + 3 * n_ncdm) d = eta_prime;
+#pragma unroll
+  for (int s = 0; s < PT_MAX_NCDM; s++) {
+    if (3 + 3 * s + 2 < N && s < n_ncdm) {
+      const double* nf = M.nf[s];  // [2] w, [4] ca2, [5] ceff2/(1+w), [6] 8/3 cvis2/(1+w), [7] shear damping rate
+      const double y0 = y[3 + 3 * s], y1 = y[4 + 3 * s], y2 = y[5 + 3 * s];
+      const double w_n = nf[2], ca2 = nf[4];
+      const double ms = (P.ncdmfa_method == CLPP_NCDMFA_CLASS) ? metric_continuity : metric_shear;
+      if (lane == 3 + 3 * s) d = -(1.0 + w_n) * (y1 + metric_continuity) - 3.0 * aH * (ca2 - w_n) * y0;
+      else if (lane == 4 + 3 * s) d = -aH * (1.0 - 3.0 * ca2) * y1 + nf[5] * k2 * y0 - k2 * y2;
+      else if (lane == 5 + 3 * s) d = -nf[7] * y2 + nf[6] * (y1 + ms);
+    }
+  }
+  return d;
+}
+
+// Gauss-Jordan inverse of A = I - c J with partial pivoting, one row per lane in registers.
+// Returns G = (P A)^-1 (the row exchanges P are returned as `perm`: A^-1 r = G (P r), (P r)_i = r_perm[i]).
+template <int N>
+__device__ __forceinline__ void factor_rows(const double* __restrict__ Js, int n, double c, int lane, double (&G)[N], int& perm) {
+  const int li = lane < n ? lane : 0;
+#pragma unroll
+  for (int q = 0; q < N; q++) G[q] = ((q == lane) ? 1.0 : 0.0) - ((q < n && lane < n) ? c * Js[li * N + q] : 0.0);
+  perm = lane;
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    if (j < n) {
+      // pivot: largest |G[.][j]| among rows j..n-1
+      const double v = (lane >= j && lane < n) ? fabs(G[j]) : -1.0;
+      const double vmax = wmax(v);
+      int pj = __ffs(__ballot_sync(PT_FULL, v == vmax)) - 1;
+      if (pj < 0) pj = j;
+      if (pj != j) {  // exchange rows j and pj (uniform branch)
+        const int src = (lane == j) ? pj : (lane == pj) ? j : lane;
+#pragma unroll
+        for (int q = 0; q < N; q++) G[q] = __shfl_sync(PT_FULL, G[q], src);
+        perm = __shfl_sync(PT_FULL, perm, src);
+      }
+      double pr[N];
+#pragma unroll
+      for (int q = 0; q < N; q++) pr[q] = __shfl_sync(PT_FULL, G[q], j);
+      double pv = pr[j];
+      if (pv == 0.) pv = 1e-50;  // TINY, as ludcmp does for a singular pivot
+      const double pinv = 1.0 / pv;
+      const double f = (lane == j) ? 0. : G[j];
+#pragma unroll
+      for (int q = 0; q < N; q++) {
+        const double pq = pr[q] * pinv;
+        if (q == j) G[q] = (lane == j) ? pinv : -f * pinv;
+        else G[q] = (lane == j) ? pq : G[q] - f * pq;
+      }
+    }
+  }
+}
+
+template <int N>
+__device__ __noinline__ bool ndf15_rsa(const PtParams& P, double t0, double tfinal) {
+  Mode& M = MODE(P);
+  PROF_DECL;
+  const double abstol = 1e-15, eps = 1e-16, threshold = abstol;
+  const int maxit = 4, maxk = 5;
+  const double rtol = P.rtol;
+  const int n = M.L.neq, lane = threadIdx.x, n_ncdm = P.has_ncdm ? P.N_ncdm : 0;
+  const bool act = lane < n;
+  const int li = act ? lane : 0;
+  const double k2 = M.k2, ik2 = M.inv_k2;
+  double* Js = s_sinv(P);  // Jacobian, row-major [n][N]
+  double* Ys = s_vec(P, V_Y);
+  const double* t_vec = M.C->tau;
+  const int tres = M.C->tau_size;
+  int next = M.next;
+  while (next < tres && __ldg(t_vec + next) < t0) next++;
+  double tnext = (next < tres) ? __ldg(t_vec + next) : 1e300;
+  RsaEnv E;
+  double yv[N];
+
+  auto gather = [&](double mine) {
+#pragma unroll
+    for (int q = 0; q < N; q++) yv[q] = __shfl_sync(PT_FULL, mine, q);
+  };
+  auto jacobian_rsa = [&]() {  // J columns = f(e_j) (linear, homogeneous system); environment must be current
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+#pragma unroll
+      for (int q = 0; q < N; q++) yv[q] = (q == j) ? 1.0 : 0.0;
+      const double d = rhs_rsa<N>(P, M, E, yv, lane, n_ncdm, k2, ik2);
+      if (act) Js[li * N + j] = d;
+    }
+    __syncwarp();
+    if (lane == 0) { M.st.jacobians++; M.st.fevals += n; }
+  };
+
+  double y = act ? Ys[li] : 0.;
+  double dif[7];
+#pragma unroll
+  for (int j = 0; j < 7; j++) dif[j] = 0.;
+  const double htspan = fabs(tfinal - t0);
+  double t = t0, tnew = t0;
+  env_at(P, t0, true, 0);
+  rsa_env_load(P, M, E);
+  gather(y);
+  const double f0i = rhs_rsa<N>(P, M, E, yv, lane, n_ncdm, k2, ik2);
+  if (lane == 0) M.st.fevals++;
+  const double hmax = (tfinal - t0) / 10.0;
+  jacobian_rsa();
+  bool Jcurrent = true;
+  double hmin = 16.0 * eps * fabs(t);
+  const double wt0 = fmax(fabs(y), threshold);
+  double rh = wmax(act ? 1.25 / sqrt(rtol) * fabs(f0i / wt0) : 0.);
+  double absh = fmin(hmax, htspan);
+  if (absh * rh > 1.0) absh = 1.0 / rh;
+  absh = fmax(absh, hmin);
+  double h = absh;
+  {
+    gather(f0i);  // J*f0 = f(t0, f0)
+    const double jf = rhs_rsa<N>(P, M, E, yv, lane, n_ncdm, k2, ik2);
+    const double tdel = (t + fmin(sqrt(eps) * fmax(fabs(t), fabs(t + h)), absh)) - t;
+    env_at(P, t + tdel, true, 0);
+    rsa_env_load(P, M, E);
+    gather(y);
+    const double fdel = rhs_rsa<N>(P, M, E, yv, lane, n_ncdm, k2, ik2);
+    if (lane == 0) M.st.fevals += 2;
+    const double s = act ? jf + (fdel - f0i) / tdel : 0.;
+    rh = wmax(1.25 * sqrt(0.5 * fabs(s / wt0) / rtol));
+    absh = fmin(hmax, htspan);
+    if (absh * rh > 1.0) absh = 1.0 / rh;
+    absh = fmax(absh, hmin);
+    h = absh;
+  }
+  int k = 1, klast = k;
+  double abshlast = absh;
+  dif[0] = h * f0i;
+  double hinvGak = h * c_invGa[k - 1];
+  int nconhk = 0;
+  double G[N];
+  int perm;
+  factor_rows<N>(Js, n, hinvGak, lane, G, perm);
+  if (lane == 0) M.st.factorizations++;
+  bool havrate = false;
+  bool done = false, at_hmin = false;
+  double rate = 0., oldnrm = 0., err = 0.;
+  double pred = 0., psi = 0., dk1 = 0., iw = 0., f_last = f0i;
+
+  // difference-array rescaling in registers (adjust_stepsize)
+  auto rescale = [&](double r) {
+    double* RU = s_hubtmp(P);
+    if (lane < 25) {
+      const int ii = lane / 5, jj = lane % 5;
+      double s = 0.;
+#pragma unroll 1
+      for (int kk = 0; kk < 5; kk++) {
+        double Rv = 1.;
+        for (int mm = 1; mm <= ii + 1; mm++) Rv *= ((mm - 1) - (kk + 1) * r) * c_invint[mm];
+        s += Rv * c_U[kk][jj];
+      }
+      RU[lane] = s;
+    }
+    __syncwarp();
+    double nd[5];
+#pragma unroll
+    for (int jj = 0; jj < 5; jj++) {
+      double s = 0.;
+#pragma unroll
+      for (int kk = 0; kk < 5; kk++) s += ((kk < k) ? dif[kk] : 0.) * RU[kk * 5 + jj];
+      nd[jj] = s;
+    }
+#pragma unroll
+    for (int jj = 0; jj < 5; jj++)
+      if (jj < k) dif[jj] = nd[jj];
+    __syncwarp();
+  };
+
+  while (!done) {
+    hmin = P.hmin_allowed;
+    absh = fmin(hmax, fmax(hmin, absh));
+    if (fabs(absh - hmin) < 100 * eps) {
+      if (at_hmin) absh = abshlast;
+      at_hmin = true;
+    } else {
+      at_hmin = false;
+    }
+    h = absh;
+    if (1.1 * absh >= fabs(tfinal - t)) {
+      h = tfinal - t;
+      absh = fabs(h);
+      done = true;
+    }
+    if (((fabs(absh - abshlast) / absh) > 1e-6) || (k != klast)) {
+      PROF_BEGIN();
+      rescale(absh / abshlast);
+      PROF_END(PF_ADJUST);
+      hinvGak = h * c_invGa[k - 1];
+      nconhk = 0;
+      PROF_BEGIN();
+      factor_rows<N>(Js, n, hinvGak, lane, G, perm);
+      if (lane == 0) M.st.factorizations++;
+      PROF_END(PF_FACTOR);
+      havrate = false;
+    }
+    bool nofailed = true;
+    for (;;) {  // loop for advancing one step
+      bool gotynew = false;
+      while (!gotynew) {
+        tnew = t + h;
+        if (done) tnew = tfinal;
+        h = tnew - t;
+        PROF_BEGIN();
+        const double invGak = c_invGa[k - 1];
+        psi = 0.;
+        pred = y;
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+          if (j < k) {
+            psi += dif[j] * c_G[j] * invGak;
+            pred += dif[j];
+          }
+        }
+        dk1 = 0.;
+        iw = 1.0 / fmax(fmax(fabs(pred), fabs(y)), threshold);
+        const double minnrm = wmax(act ? 100 * eps * fabs(pred * iw) : 0.);
+        PROF_END(PF_PREDICT);
+        PROF_BEGIN();
+        env_at(P, tnew, true, 0);
+        rsa_env_load(P, M, E);
+        PROF_END(PF_ENV);
+        bool tooslow = false;
+#pragma unroll 1
+        for (int iter = 1; iter <= maxit; iter++) {
+          PROF_BEGIN();
+          gather(pred + dk1);
+          f_last = rhs_rsa<N>(P, M, E, yv, lane, n_ncdm, k2, ik2);
+          PROF_END(PF_RHS);
+          PROF_BEGIN();
+          // residual r, then x = A^-1 r = G (P r): lane j fetches r[perm[j]], every lane dots its row of G
+          const double r = act ? hinvGak * f_last - (psi + dk1) : 0.;
+          const double rp = __shfl_sync(PT_FULL, r, perm);
+          double x0 = 0., x1 = 0.;
+#pragma unroll
+          for (int q = 0; q < N; q += 2) {
+            x0 += G[q] * __shfl_sync(PT_FULL, rp, q);
+            x1 += G[q + 1] * __shfl_sync(PT_FULL, rp, q + 1);
+          }
+          const double d = act ? x0 + x1 : 0.;
+          PROF_END(PF_SOLVE);
+          PROF_BEGIN();
+          const double newnrm = wmax(fabs(d * iw));
+          dk1 += d;
+          if (lane == 0) { M.st.fevals++; M.st.solves++; }
+          PROF_END(PF_UPDATE);
+          if (newnrm <= minnrm) { gotynew = true; break; }
+          else if (iter == 1) {
+            if (havrate) {
+              const double errit = newnrm * rate / (1.0 - rate);
+              if (errit <= 0.05 * rtol) { gotynew = true; break; }
+            } else {
+              rate = 0.0;
+            }
+          } else if (newnrm > 0.9 * oldnrm) {
+            tooslow = true;
+            break;
+          } else {
+            rate = fmax(0.9 * rate, newnrm / oldnrm);
+            havrate = true;
+            const double errit = newnrm * rate / (1.0 - rate);
+            if (errit <= 0.5 * rtol) { gotynew = true; break; }
+            else if (iter == maxit) { tooslow = true; break; }
+            else {
+              double rpw = rate;  // rate^(maxit-iter)
+              for (int q = 1; q < maxit - iter; q++) rpw *= rate;
+              if (0.5 * rtol < errit * rpw) { tooslow = true; break; }
+            }
+          }
+          oldnrm = newnrm;
+        }
+        if (tooslow) {
+          if (lane == 0) M.st.failed++;
+          if (!Jcurrent) {
+            env_at(P, t, true, 0);
+            rsa_env_load(P, M, E);
+            jacobian_rsa();
+            if (lane == 0) M.st.fevals++;  // the reference re-evaluates f(t, y) with a new Jacobian
+            Jcurrent = true;
+          } else if (absh <= hmin) {
+            M.status = 2;  // step size too small
+            return false;
+          } else {
+            abshlast = absh;
+            absh = fmax(0.3 * absh, hmin);
+            h = absh;
+            done = false;
+            rescale(absh / abshlast);
+            hinvGak = h * c_invGa[k - 1];
+            nconhk = 0;
+          }
+          factor_rows<N>(Js, n, hinvGak, lane, G, perm);
+          if (lane == 0) M.st.factorizations++;
+          havrate = false;
+        }
+      }
+      // error estimate
+      err = wmax(fabs(dk1 * iw)) * c_erconst[k - 1];
+      if (err > rtol) {
+        if (lane == 0) M.st.failed++;
+        if (absh <= hmin) {
+          M.status = 2;
+          return false;
+        }
+        abshlast = absh;
+        if (nofailed) {
+          nofailed = false;
+          double hopt = absh * fmax(0.1, 0.833 * root_n(rtol / err, k + 1.0));
+          if (k > 1) {
+            const double errkm1 = wmax(fabs((pick7(dif, k - 1) + dk1) * iw)) * c_erconst[k - 2];
+            const double hkm1 = absh * fmax(0.1, 0.769 * root_n(rtol / errkm1, (double)k));
+            if (hkm1 > hopt) {
+              hopt = fmin(absh, hkm1);
+              k = k - 1;
+            }
+          }
+          absh = fmax(hmin, hopt);
+        } else {
+          absh = fmax(hmin, 0.5 * absh);
+        }
+        h = absh;
+        if (absh < abshlast) done = false;
+        rescale(absh / abshlast);
+        hinvGak = h * c_invGa[k - 1];
+        nconhk = 0;
+        factor_rows<N>(Js, n, hinvGak, lane, G, perm);
+        if (lane == 0) M.st.factorizations++;
+        havrate = false;
+      } else {
+        break;
+      }
+    }
+    if (lane == 0) M.st.steps++;
+    PROF_BEGIN();
+    {
+      const double difk_old = pick7(dif, k);
+#pragma unroll
+      for (int j = 6; j >= 0; j--) {
+        if (j == k + 1) dif[j] = dk1 - difk_old;
+        else if (j == k) dif[j] = dk1;
+        else if (j < k) dif[j] += dif[j + 1];
+      }
+    }
+    PROF_END(PF_DIFUPD);
+    PROF_BEGIN();
+    // ---- output at the sample times passed by this step (through the generic source routine)
+    while ((next < tres) && ((tnew - tnext) >= 0.0)) {
+      double* yo = s_vec(P, V_TMP);
+      double* dyo = s_vec(P, V_YPI);
+      if (tnew == tnext) {
+        if (act) { yo[li] = pred + dk1; dyo[li] = f_last; }
+      } else {
+        const double s = (tnext - tnew) / h;
+        double a1 = 0, a2 = 0;
+        double prod = 1.0, sumfrac = 0., fact = 1.0;
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+          if (j < k) {
+            prod *= (s + j);
+            fact *= (j + 1);
+            sumfrac += 1.0 / (s + j);
+            a1 += prod / fact * dif[j];
+            a2 += prod * sumfrac / (h * fact) * dif[j];
+          }
+        }
+        if (act) { yo[li] = (pred + dk1) + a1; dyo[li] = a2; }
+      }
+      __syncwarp();
+      write_sources(P, tnext, V_TMP, V_YPI, next);
+      next++;
+      tnext = (next < tres) ? __ldg(t_vec + next) : 1e300;
+    }
+    PROF_END(PF_OUTPUT);
+    if (done) break;
+    PROF_BEGIN();
+    klast = k;
+    abshlast = absh;
+    nconhk = min(nconhk + 1, maxk + 2);
+    if (nconhk >= k + 2) {
+      double e_km1 = 0., e_kp1 = 0.;
+      if (k > 1) e_km1 = wmax(fabs(pick7(dif, k - 1) * iw)) * c_erconst[k - 2];
+      if (k < maxk) e_kp1 = wmax(fabs(pick7(dif, k + 1) * iw)) * c_erconst[k];
+      const double my_e = lane == 0 ? err : lane == 1 ? e_km1 : e_kp1;
+      const double my_c = lane == 0 ? 1.2 : lane == 1 ? 1.3 : 1.4;
+      const double my_n = lane == 0 ? k + 1.0 : lane == 1 ? (double)k : k + 2.0;
+      double temp = 0.;
+      if (my_e > 0.) temp = my_c * root_n(my_e / rtol, my_n);
+      const double my_h = (temp > 0.1) ? absh / temp : 10 * absh;
+      double hopt = __shfl_sync(PT_FULL, my_h, 0);
+      const double hkm1 = __shfl_sync(PT_FULL, my_h, 1), hkp1 = __shfl_sync(PT_FULL, my_h, 2);
+      int kopt = k;
+      if (k > 1 && hkm1 > hopt) { hopt = hkm1; kopt = k - 1; }
+      if (k < maxk && hkp1 > hopt) { hopt = hkp1; kopt = k + 1; }
+      if (hopt > absh) {
+        absh = hopt;
+        if (k != kopt) k = kopt;
+      }
+    }
+    t = tnew;
+    y = pred + dk1;
+    Jcurrent = false;
+    PROF_END(PF_CONTROL);
+  }
+  y = pred + dk1;
+  if (act) Ys[li] = y;
+  __syncwarp();
+  if (lane == 0) M.st.fevals++;  // the reference's final RHS call (nothing follows the last interval)
+  M.next = next;
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // perturb_initial_conditions: adiabatic mode, synchronous gauge, flat space
 __device__ __noinline__ void initial_conditions(const PtParams& P, double tau) {
@@ -1949,20 +2454,15 @@ __device__ __noinline__ void remap_state(const PtParams& P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-#ifndef PT_MIN_BLOCKS
-#define PT_MIN_BLOCKS 8
-#endif
-__global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid_constant__ PtParams P) {
-  if ((int)blockIdx.x >= P.n_modes) return;
+// common set-up of the shared-memory mode state
+__device__ __forceinline__ void mode_init(const PtParams& P, const PtCosmo* C, int ik) {
   Mode& M = MODE(P);
   const int lane = (int)threadIdx.x;
-  const int2 md = P.modes[blockIdx.x];
-  const PtCosmo* C = P.cosmo + md.x;
   if (lane == 0) {
     M.Jhh = P.hub_jac + (size_t)blockIdx.x * P.nh_max * P.nh_max;
     M.C = C;
-    M.ik = md.y;
-    M.k = C->k[md.y];
+    M.ik = ik;
+    M.k = C->k[ik];
     M.k2 = M.k * M.k;
     M.inv_k = 1.0 / M.k;
     M.inv_k2 = 1.0 / M.k2;
@@ -1986,6 +2486,40 @@ __global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid
   }
   for (int l = lane; l < P.n_i2l1; l += 32) s_i2l1(P)[l] = 1.0 / (2.0 * l + 1.0);
   __syncwarp();
+}
+
+// end of a mode: zero-fill the samples that were not reached (failure only) and publish the counters
+__device__ __forceinline__ void mode_finish(const PtParams& P, const PtCosmo* C, int ik, int n_int, int status, double tau_ini) {
+  Mode& M = MODE(P);
+  if (threadIdx.x == 0) {
+    const int tau_size = C->tau_size;
+    const size_t stride_tp = (size_t)C->k_size * tau_size;
+    double* out = C->sources + (size_t)ik * tau_size;
+    const int tps[7] = {P.tp_t0, P.tp_t1, P.tp_t2, P.tp_p, P.tp_delta_m, P.tp_delta_cb, P.tp_phi_plus_psi};
+    for (int it = M.next; it < tau_size; it++)
+      for (int j = 0; j < 7; j++)
+        if (tps[j] >= 0) out[tps[j] * stride_tp + it] = 0.;
+    clpp_kstat* ks = C->kstat + ik;
+    ks->steps = M.st.steps; ks->failed = M.st.failed; ks->fevals = M.st.fevals; ks->jacobians = M.st.jacobians;
+    ks->factorizations = M.st.factorizations; ks->solves = M.st.solves;
+    ks->intervals = n_int; ks->status = status; ks->tau_ini = tau_ini;
+  }
+}
+
+// hand-off record of a mode whose last (radiation-streaming) interval runs in perturb_tail_kernel
+enum { TL_VALID = 0, TL_T0, TL_TF, TL_NEXT, TL_IV, TL_NINT, TL_TAU_INI, TL_FLAGS, TL_STAT = TL_FLAGS + 4, TL_Y = TL_STAT + 6,
+       TL_STRIDE = TL_Y + 16 };
+
+#ifndef PT_MIN_BLOCKS
+#define PT_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid_constant__ PtParams P) {
+  if ((int)blockIdx.x >= P.n_modes) return;
+  Mode& M = MODE(P);
+  const int lane = (int)threadIdx.x;
+  const int2 md = P.modes[blockIdx.x];
+  const PtCosmo* C = P.cosmo + md.x;
+  mode_init(P, C, md.y);
   const double tau_first = C->tau[0];
   const int tau_size = C->tau_size;
 
@@ -2065,6 +2599,14 @@ __global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid
   __syncwarp();
   clpp_kstat* ks = C->kstat + md.y;
 
+  // the last interval goes to the tail kernel when it is the hub-only radiation-streaming phase
+  bool tail = false;
+  if (status == 0 && P.tail != nullptr && n_int >= 2) {
+    const Approx al = M.sched[n_int - 1];
+    tail = al.rsa_on && (!P.has_ncdm || al.ncdmfa_on) && (4 + 3 * (P.has_ncdm ? P.N_ncdm : 0) <= 16);
+  }
+  const int n_here = tail ? n_int - 1 : n_int;
+
   // ---- integrate interval by interval
   for (int iv = 0; iv < n_int && status == 0; iv++) {
     const Approx apn = M.sched[iv];
@@ -2077,13 +2619,17 @@ __global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid
     __syncwarp();
     if (iv == 0) initial_conditions(P, M.limit[0]);
     else remap_state(P);
+    if (iv >= n_here) break;  // state is laid out for the tail interval: hand it off below
     make_structure(P);
     M.need_nw = P.has_ncdm && !apn.ncdmfa_on;
     __syncwarp();
     const long long c0 = clock64();
     const int s0 = M.st.steps;
-    const bool ok = (M.nch == 0 && M.L.neq <= 32) ? ndf15_hub(P, M.limit[iv], M.limit[iv + 1])
-                                                   : ndf15(P, M.limit[iv], M.limit[iv + 1]);
+    bool ok;
+    if (M.nch == 0 && apn.rsa_on && M.L.neq <= 8) ok = ndf15_rsa<8>(P, M.limit[iv], M.limit[iv + 1]);
+    else if (M.nch == 0 && apn.rsa_on && M.L.neq <= 16) ok = ndf15_rsa<16>(P, M.limit[iv], M.limit[iv + 1]);
+    else if (M.nch == 0 && M.L.neq <= 32) ok = ndf15_hub(P, M.limit[iv], M.limit[iv + 1]);
+    else ok = ndf15(P, M.limit[iv], M.limit[iv + 1]);
     __syncwarp();
     if (lane == 0) {
       ks->iv_neq[iv] = M.L.neq;
@@ -2097,18 +2643,67 @@ __global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid
     status = M.status;
     if (!ok) break;
   }
-  // zero-fill the samples that were not reached (failure only; normally next == tau_size)
-  if (lane == 0) {
-    const size_t stride_tp = (size_t)C->k_size * tau_size;
-    double* out = C->sources + (size_t)md.y * tau_size;
-    const int tps[7] = {P.tp_t0, P.tp_t1, P.tp_t2, P.tp_p, P.tp_delta_m, P.tp_delta_cb, P.tp_phi_plus_psi};
-    for (int it = M.next; it < tau_size; it++)
-      for (int j = 0; j < 7; j++)
-        if (tps[j] >= 0) out[tps[j] * stride_tp + it] = 0.;
-    ks->steps = M.st.steps; ks->failed = M.st.failed; ks->fevals = M.st.fevals; ks->jacobians = M.st.jacobians;
-    ks->factorizations = M.st.factorizations; ks->solves = M.st.solves;
-    ks->intervals = n_int; ks->status = status; ks->tau_ini = tau_ini;
+  if (tail && status == 0) {
+    double* T = P.tail + (size_t)blockIdx.x * TL_STRIDE;
+    const int n = M.L.neq;
+    if (lane < n) T[TL_Y + lane] = s_vec(P, V_Y)[lane];
+    if (lane == 0) {
+      const Approx al = M.sched[n_int - 1];
+      T[TL_VALID] = 1.; T[TL_T0] = M.limit[n_int - 1]; T[TL_TF] = M.limit[n_int]; T[TL_NEXT] = M.next;
+      T[TL_IV] = n_int - 1; T[TL_NINT] = n_int; T[TL_TAU_INI] = tau_ini;
+      T[TL_FLAGS] = al.tca_off; T[TL_FLAGS + 1] = al.rsa_on; T[TL_FLAGS + 2] = al.ufa_on; T[TL_FLAGS + 3] = al.ncdmfa_on;
+      T[TL_STAT] = M.st.steps; T[TL_STAT + 1] = M.st.failed; T[TL_STAT + 2] = M.st.fevals; T[TL_STAT + 3] = M.st.jacobians;
+      T[TL_STAT + 4] = M.st.factorizations; T[TL_STAT + 5] = M.st.solves;
+    }
+    return;
   }
+  mode_finish(P, C, md.y, n_int, status, tau_ini);
+}
+
+// Tail kernel: the radiation-streaming interval of every mode that perturb_kernel handed off.  Small
+// shared-memory footprint and register budget (16+ warps per SM), compact hot loop (ndf15_rsa).
+__global__ void __launch_bounds__(32, 16) perturb_tail_kernel(const __grid_constant__ PtParams P) {
+  if ((int)blockIdx.x >= P.n_modes) return;
+  const double* T = P.tail + (size_t)blockIdx.x * TL_STRIDE;
+  if (T[TL_VALID] != 1.) return;
+  Mode& M = MODE(P);
+  const int lane = (int)threadIdx.x;
+  const int2 md = P.modes[blockIdx.x];
+  const PtCosmo* C = P.cosmo + md.x;
+  mode_init(P, C, md.y);
+  const int iv = (int)T[TL_IV], n_int = (int)T[TL_NINT];
+  Approx ap;
+  ap.tca_off = (int)T[TL_FLAGS]; ap.rsa_on = (int)T[TL_FLAGS + 1]; ap.ufa_on = (int)T[TL_FLAGS + 2]; ap.ncdmfa_on = (int)T[TL_FLAGS + 3];
+  if (lane == 0) {
+    M.ap = ap;
+    M.next = (int)T[TL_NEXT];
+    M.st.steps = (int)T[TL_STAT]; M.st.failed = (int)T[TL_STAT + 1]; M.st.fevals = (int)T[TL_STAT + 2];
+    M.st.jacobians = (int)T[TL_STAT + 3]; M.st.factorizations = (int)T[TL_STAT + 4]; M.st.solves = (int)T[TL_STAT + 5];
+  }
+  make_layout(P, ap, M.L);
+  __syncwarp();
+  const int n = M.L.neq;
+  if (lane < n) s_vec(P, V_Y)[lane] = T[TL_Y + lane];
+  if (lane == 0) { M.nh = n; M.nch = 0; }
+  __syncwarp();
+  const long long c0 = clock64();
+  const int s0 = M.st.steps;
+  bool ok;
+  if (n <= 8) ok = ndf15_rsa<8>(P, T[TL_T0], T[TL_TF]);
+  else ok = ndf15_rsa<16>(P, T[TL_T0], T[TL_TF]);
+  __syncwarp();
+  clpp_kstat* ks = C->kstat + md.y;
+  if (lane == 0) {
+    ks->iv_neq[iv] = n;
+    ks->iv_steps[iv] = M.st.steps - s0;
+    ks->iv_cycles[iv] = clock64() - c0;
+#ifdef PT_PROF
+    for (int q = 0; q < PF_COUNT; q++) ks->prof[iv * 12 + q] = M.prof[q];
+#endif
+  }
+  __syncwarp();
+  (void)ok;
+  mode_finish(P, C, md.y, n_int, M.status, T[TL_TAU_INI]);
 }
 
 // =============================================================================================
@@ -2122,6 +2717,8 @@ static int dev_reserve(T** p, size_t* cap, size_t n, char* err) {
   *cap = n;
   return CLPP_SUCCESS;
 }
+
+static void set_geometry(PtParams& P, int neq_max, int nh_max, const clpp_perturb_desc& pd);
 
 // settings shared by every cosmology of a batch (pointers and geometry are filled by the caller)
 static int fill_common(const clpp_ctx* c, PtParams& P, char* err) {
@@ -2181,6 +2778,12 @@ static int fill_common(const clpp_ctx* c, PtParams& P, char* err) {
              "the number of ncdm momentum bins", n_chains, PT_MAX_CHAINS);
   CLPP_CHECK(nh_max <= 128, err, "%d hub variables exceed the 128 a warp handles: reduce the number of ncdm momentum bins",
              nh_max);
+  set_geometry(P, neq_max, nh_max, pd);
+  return CLPP_SUCCESS;
+}
+
+// shared-memory layout of one CTA for state vectors of up to neq_max equations / nh_max hub variables
+static void set_geometry(PtParams& P, int neq_max, int nh_max, const clpp_perturb_desc& pd) {
   P.neq_max = neq_max;
   P.np = (neq_max + 1) & ~1;
   P.nh_max = nh_max;
@@ -2193,7 +2796,6 @@ static int fill_common(const clpp_ctx* c, PtParams& P, char* err) {
   P.o_vec = P.o_i2l1 + P.n_i2l1;
   P.o_sinv = P.o_vec + V_COUNT * P.np;
   P.o_int = P.o_sinv + ((P.nh_max * P.ldh + 1) & ~1);
-  return CLPP_SUCCESS;
 }
 
 static size_t perturb_smem_bytes(const PtParams& P) {
@@ -2284,16 +2886,31 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   P.modes = (const int2*)d0->pt_modes;
   P.n_modes = n_modes;
   P.hub_jac = d0->jac_scratch;
+  // hand-off records of the tail (radiation-streaming) kernel
+  const bool use_tail = getenv("CLPP_NO_TAIL") == nullptr;
+  if (use_tail) {
+    if (dev_reserve(&d0->pt_tail, &d0->pt_tail_cap, (size_t)std::max(n_modes, 1) * TL_STRIDE, err)) return CLPP_FAILURE;
+    CLPP_CUDA(cudaMemsetAsync(d0->pt_tail, 0, (size_t)std::max(n_modes, 1) * TL_STRIDE * sizeof(double), st), err);
+    P.tail = d0->pt_tail;
+  }
 
   const size_t smem = perturb_smem_bytes(P);
   CLPP_CHECK(smem <= 227 * 1024, err,
              "state vector of %d equations needs %zu bytes of shared memory per k-mode (> 227 KB): reduce l_max_ncdm / "
              "the number of ncdm momentum bins", P.neq_max, smem);
   CLPP_CUDA(cudaFuncSetAttribute(perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
+  PtParams Pt = P;  // geometry of the tail kernel: at most 16 equations, all hub
+  set_geometry(Pt, 16, 16, c0->pd);
+  const size_t smem_tail = perturb_smem_bytes(Pt);
+  CLPP_CUDA(cudaFuncSetAttribute(perturb_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail), err);
   cudaEventRecord(d0->ev[0], st);
   if (n_modes > 0) {
     perturb_kernel<<<n_modes, 32, smem, st>>>(P);
     c0->launches++;
+    if (use_tail) {
+      perturb_tail_kernel<<<n_modes, 32, smem_tail, st>>>(Pt);
+      c0->launches++;
+    }
   }
   cudaEventRecord(d0->ev[1], st);
   CLPP_CUDA(cudaGetLastError(), err);

@@ -9,7 +9,7 @@ inp = M.Inputs.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
 ctx = M.Context(0)
 bg = M.BackgroundModule(inp, ctx); th = M.ThermodynamicsModule(inp, bg)
 pt = M.PerturbationsModule(inp, bg, th, k_range=(lo, hi))
-names = ["env", "rhs", "solve", "predict", "update", "control", "factor", "adjust", "output", "jac", "difupd"]
+names = ["env", "rhs", "solve", "predict", "update", "control", "factor", "adjust", "output", "env_bg", "difupd", "env_th"]
 for ik in range(lo, hi):
     pr = pt.kprofile_[ik]; sec = pt.ksections_[ik].reshape(6, 12); ks = pt.kstat_[ik]
     print("k[%d] fevals/step(all)=%.2f lu/step=%.2f" % (ik, ks[2] / ks[0], ks[4] / ks[0]))
