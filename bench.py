@@ -156,7 +156,7 @@ def run_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t0 = time.perf_counter()
-    kms = {"perturb": 0.0, "k_spline": 0.0, "bessel": 0.0, "los": 0.0, "spectra": 0.0}
+    kms = {"perturb": 0.0, "k_spline": 0.0, "bessel": 0.0, "los": 0.0, "spectra": 0.0, "perturb_tail": 0.0}
     for _ in range(args.steps):
         step()
         for c in ctxs:

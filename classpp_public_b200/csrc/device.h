@@ -13,7 +13,7 @@ struct clpp_ctx::Dev {
   int sm_count = 0;
   // per-kernel device timings of the last stage calls (CUDA events on `stream`), in ms
   cudaEvent_t ev[2] = {nullptr, nullptr};
-  double t_perturb_ms = 0., t_kspline_ms = 0., t_bessel_ms = 0., t_los_ms = 0., t_spectra_ms = 0.;
+  double t_perturb_ms = 0., t_perturb_tail_ms = 0., t_kspline_ms = 0., t_bessel_ms = 0., t_los_ms = 0., t_spectra_ms = 0.;
 
   // upstream tables: row-major [n_lines][n_cols] + second derivatives, L2-resident (~6 MB)
   double *bg_tau = nullptr, *bg_y = nullptr, *bg_dd = nullptr;

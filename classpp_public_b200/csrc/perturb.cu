@@ -2907,6 +2907,9 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   if (n_modes > 0) {
     perturb_kernel<<<n_modes, 32, smem, st>>>(P);
     c0->launches++;
+    for (int i = 0; i < 6; i++)
+      if (!d0->ev2[i]) cudaEventCreate(&d0->ev2[i]);
+    cudaEventRecord(d0->ev2[4], st);
     if (use_tail) {
       perturb_tail_kernel<<<n_modes, 32, smem_tail, st>>>(Pt);
       c0->launches++;
@@ -2924,8 +2927,9 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   {
     float ms = 0;
     cudaEventElapsedTime(&ms, d0->ev[0], d0->ev[1]);
-    for (int b = 0; b < n_ctx; b++) cs[b]->dev->t_perturb_ms = 0.;
+    for (int b = 0; b < n_ctx; b++) { cs[b]->dev->t_perturb_ms = 0.; cs[b]->dev->t_perturb_tail_ms = 0.; }
     d0->t_perturb_ms = ms;
+    if (n_modes > 0) { cudaEventElapsedTime(&ms, d0->ev2[4], d0->ev[1]); d0->t_perturb_tail_ms = ms; }
   }
   for (int b = 0; b < n_ctx; b++) {
     clpp_ctx* c = cs[b];

@@ -136,9 +136,9 @@ class Context:
         return p.value or 0
 
     def kernel_ms(self):
-        out = np.zeros(5)
+        out = np.zeros(6)
         self._lib.clpp_ctx_get_kernel_ms(self._h, capi.dptr(out))
-        return dict(zip(("perturb", "k_spline", "bessel", "los", "spectra"), out.tolist()))
+        return dict(zip(("perturb", "k_spline", "bessel", "los", "spectra", "perturb_tail"), out.tolist()))
 
     def fp64_peak_tflops(self):
         v = C.c_double()
