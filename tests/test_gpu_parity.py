@@ -186,6 +186,45 @@ def test_k_range_partition_equals_full_solve(golden):
     ctx.close(); ctx2.close()
 
 
+def test_batched_solve_equals_individual_solves(golden):
+    """clpp_perturb_solve_batch: several cosmologies in one launch give, per cosmology, bit-identical sources to
+    one launch per cosmology (independent objects; the batch only changes the issue order of the modes)."""
+    inp = golden("lcdm_coarse")
+    single_ctx = M.Context(0)
+    bg = M.BackgroundModule(inp, single_ctx)
+    th = M.ThermodynamicsModule(inp, bg)
+    single = M.PerturbationsModule(inp, bg, th)
+    s_single = np.stack(single.sources_[0])
+    ctxs, pts = [], []
+    for _ in range(3):
+        c = M.Context(0)
+        b = M.BackgroundModule(inp, c)
+        t = M.ThermodynamicsModule(inp, b)
+        ctxs.append(c)
+        pts.append(M.PerturbationsModule(inp, b, t, solve=False))
+    M.PerturbationsModule.solve_batch(pts)
+    for p in pts:
+        assert np.array_equal(np.stack(p.sources_[0]), s_single)
+        assert np.array_equal(p.kstat_[:, :6], single.kstat_[:, :6])
+    for c in ctxs + [single_ctx]:
+        c.close()
+
+
+def test_tail_kernel_equals_single_kernel_path(golden, monkeypatch):
+    """The radiation-streaming interval integrated by perturb_tail_kernel (registers, shuffles) and by the
+    generic shared-memory integrator inside perturb_kernel follow the same algorithm: C_l agree to 1e-6."""
+    inp = golden("lcdm_coarse")
+    ctx, pt, tr, sp = run_pipeline(inp)
+    cl_tail = sp.cl_[0].copy()
+    ctx.close()
+    monkeypatch.setenv("CLPP_NO_TAIL", "1")
+    ctx, pt, tr, sp = run_pipeline(inp)
+    cl_one = sp.cl_[0].copy()
+    ctx.close()
+    nz = cl_one != 0
+    assert np.max(np.abs(cl_tail[nz] / cl_one[nz] - 1.0)) < 1e-6
+
+
 def test_no_device_fails_loudly():
     with pytest.raises(M.CosmoComputationError):
         M.Context(device=9999)
