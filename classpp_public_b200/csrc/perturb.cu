@@ -88,6 +88,7 @@ struct PtParams {
   double eisw_lisw_split_z;
   int tp_t0, tp_t1, tp_t2, tp_p, tp_delta_m, tp_delta_cb, tp_phi_plus_psi;
   // shared-memory geometry (offsets in doubles into the CTA's dynamic shared memory)
+  int force_generic;  // developer/test switch: integrate every interval with the generic shared-memory NDF
   int neq_max, np, nh_max, ldh;
   int o_mode, o_hubtmp, o_nw, o_i2l1, n_i2l1, o_vec, o_sinv, o_int;
 };
@@ -2626,7 +2627,8 @@ __global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid
     const long long c0 = clock64();
     const int s0 = M.st.steps;
     bool ok;
-    if (M.nch == 0 && apn.rsa_on && M.L.neq <= 8) ok = ndf15_rsa<8>(P, M.limit[iv], M.limit[iv + 1]);
+    if (P.force_generic) ok = ndf15(P, M.limit[iv], M.limit[iv + 1]);
+    else if (M.nch == 0 && apn.rsa_on && M.L.neq <= 8) ok = ndf15_rsa<8>(P, M.limit[iv], M.limit[iv + 1]);
     else if (M.nch == 0 && apn.rsa_on && M.L.neq <= 16) ok = ndf15_rsa<16>(P, M.limit[iv], M.limit[iv + 1]);
     else if (M.nch == 0 && M.L.neq <= 32) ok = ndf15_hub(P, M.limit[iv], M.limit[iv + 1]);
     else ok = ndf15(P, M.limit[iv], M.limit[iv + 1]);
@@ -2887,7 +2889,8 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   P.n_modes = n_modes;
   P.hub_jac = d0->jac_scratch;
   // hand-off records of the tail (radiation-streaming) kernel
-  const bool use_tail = getenv("CLPP_NO_TAIL") == nullptr;
+  P.force_generic = getenv("CLPP_GENERIC_ONLY") != nullptr;
+  const bool use_tail = getenv("CLPP_NO_TAIL") == nullptr && !P.force_generic;
   if (use_tail) {
     if (dev_reserve(&d0->pt_tail, &d0->pt_tail_cap, (size_t)std::max(n_modes, 1) * TL_STRIDE, err)) return CLPP_FAILURE;
     CLPP_CUDA(cudaMemsetAsync(d0->pt_tail, 0, (size_t)std::max(n_modes, 1) * TL_STRIDE * sizeof(double), st), err);

@@ -211,13 +211,14 @@ def test_batched_solve_equals_individual_solves(golden):
 
 
 def test_tail_kernel_equals_single_kernel_path(golden, monkeypatch):
-    """The radiation-streaming interval integrated by perturb_tail_kernel (registers, shuffles) and by the
-    generic shared-memory integrator inside perturb_kernel follow the same algorithm: C_l agree to 1e-6."""
+    """The specialised integrators (perturb_tail_kernel: registers + shuffles; hub-only register path) and the
+    generic shared-memory NDF (CLPP_GENERIC_ONLY=1, the fallback for very large systems) follow the same
+    algorithm: C_l agree to 1e-6."""
     inp = golden("lcdm_coarse")
     ctx, pt, tr, sp = run_pipeline(inp)
     cl_tail = sp.cl_[0].copy()
     ctx.close()
-    monkeypatch.setenv("CLPP_NO_TAIL", "1")
+    monkeypatch.setenv("CLPP_GENERIC_ONLY", "1")
     ctx, pt, tr, sp = run_pipeline(inp)
     cl_one = sp.cl_[0].copy()
     ctx.close()
