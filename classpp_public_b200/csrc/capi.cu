@@ -17,10 +17,9 @@ int clpp_dev_spectra(clpp_ctx* c, const double* primordial_pk, int q_begin, int 
 int clpp_dev_get_bessel(clpp_ctx* c, double* x, double* phi, double* dphi, double* chi, char* err);
 
 template <typename T>
-static int upload(T** dptr, const T* src, size_t n, cudaStream_t s, char* err) {
-  if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+static int upload(clpp_ctx::Dev* d, T** dptr, const T* src, size_t n, cudaStream_t s, char* err) {
   if (n == 0) return CLPP_SUCCESS;
-  CLPP_CUDA(cudaMalloc((void**)dptr, n * sizeof(T)), err);
+  if (clpp_dev_reserve(d, dptr, n, err)) return CLPP_FAILURE;  // grow-only: no cudaFree/cudaMalloc when re-used
   if (src) CLPP_CUDA(cudaMemcpyAsync(*dptr, src, n * sizeof(T), cudaMemcpyHostToDevice, s), err);
   return CLPP_SUCCESS;
 }
@@ -76,6 +75,8 @@ void clpp_ctx_destroy(clpp_ctx* c) {
       if (d->ev2[i]) cudaEventDestroy(d->ev2[i]);
     cudaEventDestroy(d->ev[0]);
     cudaEventDestroy(d->ev[1]);
+    if (d->stream2) cudaStreamDestroy(d->stream2);
+    if (d->stream_hi) cudaStreamDestroy(d->stream_hi);
     cudaStreamDestroy(d->stream);
     delete d;
   }
@@ -148,9 +149,9 @@ int clpp_set_background(clpp_ctx* c, const clpp_background_desc* desc, const dou
   if (c->dev) {
     cudaSetDevice(c->device);
     clpp_ctx::Dev* d = c->dev;
-    if (upload(&d->bg_tau, t.x.data(), t.x.size(), d->stream, err)) return CLPP_FAILURE;
-    if (upload(&d->bg_y, t.y.data(), t.y.size(), d->stream, err)) return CLPP_FAILURE;
-    if (upload(&d->bg_dd, t.ddy.data(), t.ddy.size(), d->stream, err)) return CLPP_FAILURE;
+    if (upload(d, &d->bg_tau, t.x.data(), t.x.size(), d->stream, err)) return CLPP_FAILURE;
+    if (upload(d, &d->bg_y, t.y.data(), t.y.size(), d->stream, err)) return CLPP_FAILURE;
+    if (upload(d, &d->bg_dd, t.ddy.data(), t.ddy.size(), d->stream, err)) return CLPP_FAILURE;
   }
   return CLPP_SUCCESS;
 }
@@ -171,9 +172,9 @@ int clpp_set_thermo(clpp_ctx* c, const clpp_thermo_desc* desc, const double* z_t
   if (c->dev) {
     cudaSetDevice(c->device);
     clpp_ctx::Dev* d = c->dev;
-    if (upload(&d->th_z, t.x.data(), t.x.size(), d->stream, err)) return CLPP_FAILURE;
-    if (upload(&d->th_y, t.y.data(), t.y.size(), d->stream, err)) return CLPP_FAILURE;
-    if (upload(&d->th_dd, t.ddy.data(), t.ddy.size(), d->stream, err)) return CLPP_FAILURE;
+    if (upload(d, &d->th_z, t.x.data(), t.x.size(), d->stream, err)) return CLPP_FAILURE;
+    if (upload(d, &d->th_y, t.y.data(), t.y.size(), d->stream, err)) return CLPP_FAILURE;
+    if (upload(d, &d->th_dd, t.ddy.data(), t.ddy.size(), d->stream, err)) return CLPP_FAILURE;
   }
   return CLPP_SUCCESS;
 }
@@ -276,9 +277,9 @@ int clpp_perturb_set_sources(clpp_ctx* c, const clpp_perturb_info* info, const d
       for (int ik = 0; ik < nk; ik++) tmp[((size_t)tp * nk + ik) * nt + it] = src[ik];
     }
   clpp_ctx::Dev* d = c->dev;
-  if (upload(&d->k, c->k.data(), c->k.size(), d->stream, err)) return CLPP_FAILURE;
-  if (upload(&d->tau, c->tau.data(), c->tau.size(), d->stream, err)) return CLPP_FAILURE;
-  if (upload(&d->sources, tmp.data(), tmp.size(), d->stream, err)) return CLPP_FAILURE;
+  if (upload(d, &d->k, c->k.data(), c->k.size(), d->stream, err)) return CLPP_FAILURE;
+  if (upload(d, &d->tau, c->tau.data(), c->tau.size(), d->stream, err)) return CLPP_FAILURE;
+  if (upload(d, &d->sources, tmp.data(), tmp.size(), d->stream, err)) return CLPP_FAILURE;
   d->sources_count = tmp.size();
   CLPP_CUDA(cudaStreamSynchronize(d->stream), err);
   c->has_sources = true;
@@ -338,9 +339,9 @@ int clpp_transfer_set_transfer(clpp_ctx* c, const double* transfer, char* err) {
   cudaSetDevice(c->device);
   clpp_ctx::Dev* d = c->dev;
   const size_t n = (size_t)c->tinfo.tt_size * c->tinfo.l_size * c->tinfo.q_size;
-  if (upload(&d->transfer, transfer, n, d->stream, err)) return CLPP_FAILURE;
+  if (upload(d, &d->transfer, transfer, n, d->stream, err)) return CLPP_FAILURE;
   d->transfer_count = n;
-  if (upload(&d->kq, c->kq.data(), c->kq.size(), d->stream, err)) return CLPP_FAILURE;
+  if (upload(d, &d->kq, c->kq.data(), c->kq.size(), d->stream, err)) return CLPP_FAILURE;
   CLPP_CUDA(cudaStreamSynchronize(d->stream), err);
   c->has_transfer = true;
   return CLPP_SUCCESS;

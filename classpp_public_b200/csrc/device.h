@@ -9,7 +9,7 @@
 #include "clpp_internal.h"
 
 struct clpp_ctx::Dev {
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream_hi = nullptr;  // stream2: second group of the perturbation launch
   int sm_count = 0;
   // per-kernel device timings of the last stage calls (CUDA events on `stream`), in ms
   cudaEvent_t ev[2] = {nullptr, nullptr};

@@ -90,7 +90,7 @@ struct PtParams {
   // shared-memory geometry (offsets in doubles into the CTA's dynamic shared memory)
   int force_generic;  // developer/test switch: integrate every interval with the generic shared-memory NDF
   int neq_max, np, nh_max, ldh;
-  int o_mode, o_hubtmp, o_nw, o_i2l1, n_i2l1, o_vec, o_sinv, o_int;
+  int o_mode, o_hubtmp, o_nw, o_i2l1, n_i2l1, o_tabc, ncol, o_vec, o_sinv, o_int;
 };
 
 extern __shared__ double smem[];
@@ -102,6 +102,8 @@ extern __shared__ double smem[];
 #define s_nw(P) (smem + (P).o_nw)
 #define s_vec(P, slot) (smem + ((P).o_vec + (slot) * (P).np))
 #define s_sinv(P) (smem + (P).o_sinv)
+// bracketing rows of table `tab` (0 background, 1 thermodynamics), cache set `set`: [4][ncol] = y0, y1, dd0, dd1
+#define s_tabc(P, tab, set) (smem + (P).o_tabc + (((set) * 2 + (tab)) * 4) * (P).ncol)
 #define s_i2l1(P) (smem + (P).o_i2l1)
 #define s_hub_idx(P) ((int*)(smem + (P).o_int))
 #define s_piv(P) ((int*)(smem + (P).o_int) + (P).nh_max)
@@ -146,9 +148,9 @@ struct Env {
 // interval cache of a table: bracketing rows (y0, y1, dd0, dd1), one column per lane
 struct TabCache {
   double x0, x1, ih, h26;
-  int cur, pad;
-  double c[4][32];
+  int cur, pad;  // current interval
 };
+
 
 struct Metric {
   double h_prime, eta_prime, alpha, alpha_prime;
@@ -159,8 +161,9 @@ struct Metric {
 
 // vector slots in shared memory (each np doubles)
 enum {
-  V_Y = 0, V_YNEW, V_F0, V_PRED, V_PSI, V_DIFKP1, V_DEL, V_INVWT, V_TMP, V_YPI,
-  V_DIF0,  // 7 slots: dif[0..6]
+  V_Y = 0, V_YNEW, V_F0, V_PRED, V_PSI, V_DIFKP1, V_DEL, V_INVWT,
+  V_TMP = V_PSI, V_YPI = V_PRED,  // scratch of the Jacobian probes / source output: psi and pred are dead there
+  V_DIF0 = V_INVWT + 1,  // 7 slots: dif[0..6]
   V_JD = V_DIF0 + 7, V_JL, V_JU,  // chain rows of J: diagonal, sub-diagonal J[i,i-1], super-diagonal J[i,i+1]
   V_IP, V_MU, V_LO,               // chain factors: 1/pivot, T[i,i+1]/p[i+1], T[i,i-1]
   V_COUNT
@@ -256,6 +259,8 @@ struct Mode {
 };
 #define MODE(P) (*(Mode*)(smem + (P).o_mode))
 
+
+
 // ---------------------------------------------------------------------------------------------
 // background_at_tau (normal_info columns) + thermodynamics_at_z, cooperative over lanes.
 // `set` selects one of two interval caches: 0 = the time stepping, 1 = the source output (both
@@ -274,6 +279,8 @@ __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby,
   // background
   {
     TabCache& T = M.bgc[set];
+    double* tc = s_tabc(P, 0, set);
+    const int nc = P.ncol;
     if (!(tau >= T.x0 && tau <= T.x1)) {
       __syncwarp();
       const double* X = M.bg_tau;
@@ -282,9 +289,12 @@ __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby,
       const double x0 = __ldg(X + inf), x1 = __ldg(X + inf + 1);
       if (lane < P.bg_size_normal) {
         const size_t r0 = (size_t)inf * P.bg_size + lane, r1 = r0 + P.bg_size;
-        T.c[0][lane] = __ldg(M.bg_y + r0); T.c[1][lane] = __ldg(M.bg_y + r1);
-        T.c[2][lane] = __ldg(M.bg_dd + r0); T.c[3][lane] = __ldg(M.bg_dd + r1);
-        if (inf + 2 < n) { prefetch_l1(M.bg_y + r1 + P.bg_size); prefetch_l1(M.bg_dd + r1 + P.bg_size); }
+        tc[lane] = __ldg(M.bg_y + r0); tc[nc + lane] = __ldg(M.bg_y + r1);
+        tc[2 * nc + lane] = __ldg(M.bg_dd + r0); tc[3 * nc + lane] = __ldg(M.bg_dd + r1);
+        if (inf + 3 < n) {
+          prefetch_l1(M.bg_y + r1 + P.bg_size); prefetch_l1(M.bg_dd + r1 + P.bg_size);
+          prefetch_l1(M.bg_y + r1 + 2 * P.bg_size); prefetch_l1(M.bg_dd + r1 + 2 * P.bg_size);
+        }
       }
       if (lane == 0) {
         T.cur = inf; T.x0 = x0; T.x1 = x1;
@@ -295,7 +305,7 @@ __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby,
     }
     const double b = (tau - T.x0) * T.ih, a = 1 - b;
     if (lane < P.bg_size_normal)
-      pvb[lane] = a * T.c[0][lane] + b * T.c[1][lane] + ((a * a * a - a) * T.c[2][lane] + (b * b * b - b) * T.c[3][lane]) * T.h26;
+      pvb[lane] = a * tc[lane] + b * tc[nc + lane] + ((a * a * a - a) * tc[2 * nc + lane] + (b * b * b - b) * tc[3 * nc + lane]) * T.h26;
   }
   __syncwarp();
   PROF_END(PF_JAC);
@@ -334,6 +344,8 @@ __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby,
     }
   } else {
     TabCache& T = M.thc[set];
+    double* tc = s_tabc(P, 1, set);
+    const int nc = P.ncol;
     const bool linear = (z < M.th_lin);
     if (!(z >= T.x0 && z <= T.x1)) {
       __syncwarp();
@@ -343,9 +355,12 @@ __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby,
       const double x0 = __ldg(X + inf), x1 = __ldg(X + inf + 1);
       if (lane < P.th_size) {
         const size_t r0 = (size_t)inf * P.th_size + lane, r1 = r0 + P.th_size;
-        T.c[0][lane] = __ldg(M.th_y + r0); T.c[1][lane] = __ldg(M.th_y + r1);
-        T.c[2][lane] = __ldg(M.th_dd + r0); T.c[3][lane] = __ldg(M.th_dd + r1);
-        if (inf > 0) { prefetch_l1(M.th_y + r0 - P.th_size); prefetch_l1(M.th_dd + r0 - P.th_size); }  // z decreases with time
+        tc[lane] = __ldg(M.th_y + r0); tc[nc + lane] = __ldg(M.th_y + r1);
+        tc[2 * nc + lane] = __ldg(M.th_dd + r0); tc[3 * nc + lane] = __ldg(M.th_dd + r1);
+        if (inf > 1) {  // z decreases with time
+          prefetch_l1(M.th_y + r0 - P.th_size); prefetch_l1(M.th_dd + r0 - P.th_size);
+          prefetch_l1(M.th_y + r0 - 2 * P.th_size); prefetch_l1(M.th_dd + r0 - 2 * P.th_size);
+        }
       }
       if (lane == 0) {
         T.cur = inf; T.x0 = x0; T.x1 = x1;
@@ -356,8 +371,8 @@ __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby,
     }
     const double b = (z - T.x0) * T.ih, a = 1 - b;
     if (lane < P.th_size) {
-      double v = a * T.c[0][lane] + b * T.c[1][lane];
-      if (!linear) v += ((a * a * a - a) * T.c[2][lane] + (b * b * b - b) * T.c[3][lane]) * T.h26;
+      double v = a * tc[lane] + b * tc[nc + lane];
+      if (!linear) v += ((a * a * a - a) * tc[2 * nc + lane] + (b * b * b - b) * tc[3 * nc + lane]) * T.h26;
       pvt[lane] = v;
     }
   }
@@ -934,6 +949,65 @@ __device__ __noinline__ void jacobian(const PtParams& P) {
   if (threadIdx.x == 0) M.st.fevals += nh + (nch > 0 ? 3 : 0);
 }
 
+// Gauss-Jordan inversion with partial pivoting of an n x n matrix held one row per lane in registers
+// (n <= N <= 32).  On exit G = (P A)^-1 where P are the row exchanges, returned as `perm`
+// (A^-1 r = G (P r), (P r)_j = r[perm_j]; equivalently A^-1[i][perm_j] = G[i][j]).
+template <int N>
+__device__ __forceinline__ void gj_rows(double (&G)[N], int n, int lane, int& perm) {
+  perm = lane;
+#pragma unroll 1
+  for (int j = 0; j < n; j++) {
+    double gj = G[0];
+#pragma unroll
+    for (int q = 1; q < N; q++) gj = (q == j) ? G[q] : gj;
+    // pivot: largest |G[.][j]| among rows j..n-1
+    const double v = (lane >= j && lane < n) ? fabs(gj) : -1.0;
+    const double vmax = wmax(v);
+    int pj = __ffs(__ballot_sync(PT_FULL, v == vmax)) - 1;
+    if (pj < 0) pj = j;
+    if (pj != j) {  // exchange rows j and pj (uniform branch)
+      const int src = (lane == j) ? pj : (lane == pj) ? j : lane;
+#pragma unroll
+      for (int q = 0; q < N; q++) G[q] = __shfl_sync(PT_FULL, G[q], src);
+      perm = __shfl_sync(PT_FULL, perm, src);
+      gj = __shfl_sync(PT_FULL, gj, src);
+    }
+    double pv = __shfl_sync(PT_FULL, gj, j);
+    if (pv == 0.) pv = 1e-50;  // TINY, as ludcmp does for a singular pivot
+    const double pinv = 1.0 / pv;
+    const double f = (lane == j) ? 0. : gj;
+#pragma unroll
+    for (int q = 0; q < N; q++) {
+      const double pq = __shfl_sync(PT_FULL, G[q], j) * pinv;
+      const double upd = (lane == j) ? pq : G[q] - f * pq;
+      const double piv = (lane == j) ? pinv : -f * pinv;
+      G[q] = (q == j) ? piv : upd;
+    }
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void hub_inverse_rows(const PtParams& P, Mode& M, double c, int nh, int lane) {
+  double G[N];
+  const int li = lane < nh ? lane : 0;
+  const double dg = 1.0 + s_hubtmp(P)[li];
+#pragma unroll
+  for (int q = 0; q < N; q++) {
+    const double jv = (q < nh && lane < nh) ? M.Jhh[li + (size_t)q * nh] : 0.;
+    G[q] = ((q == lane) ? (lane < nh ? dg : 1.0) : 0.0) - c * jv;
+  }
+  int perm;
+  gj_rows<N>(G, nh, lane, perm);
+  double* W = s_sinv(P);
+  const int ldh = P.ldh;
+#pragma unroll
+  for (int q = 0; q < N; q++) {
+    const int pq = __shfl_sync(PT_FULL, perm, q);
+    if (q < nh && lane < nh) W[lane * ldh + pq] = G[q];
+  }
+  __syncwarp();
+}
+
 // Factorisation of A = I - c J: chains (backward elimination towards their root), Schur
 // complement on the hub block, explicit inverse of the hub block (Gauss-Jordan, partial pivoting).
 __device__ __noinline__ void factor(const PtParams& P, double c) {
@@ -962,7 +1036,10 @@ __device__ __noinline__ void factor(const PtParams& P, double c) {
     s_hubtmp(P)[s_ch_rootslot(P)[lane]] = -mur * lon;
   }
   __syncwarp();
-  // hub block W = I - c Jhh (+ Schur terms on the diagonal of the chain roots); lane i owns row i
+  // hub block W = I - c Jhh (+ Schur terms on the diagonal of the chain roots); lane i owns row i.
+  // Up to 32 hub variables: the rows stay in registers and are exchanged with shuffles.
+  if (nh <= 16) { hub_inverse_rows<16>(P, M, c, nh, lane); if (lane == 0) M.st.factorizations++; return; }
+  if (nh <= 32) { hub_inverse_rows<32>(P, M, c, nh, lane); if (lane == 0) M.st.factorizations++; return; }
   for (int i = lane; i < nh; i += 32) {
     for (int j = 0; j < nh; j++) W[i * ldh + j] = (i == j ? 1.0 + s_hubtmp(P)[i] : 0.0) - c * M.Jhh[i + (size_t)j * nh];
   }
@@ -1911,43 +1988,13 @@ __device__ __forceinline__ double rhs_rsa(const PtParams& P, const Mode& M, cons
   return d;
 }
 
-// Gauss-Jordan inverse of A = I - c J with partial pivoting, one row per lane in registers.
-// Returns G = (P A)^-1 (the row exchanges P are returned as `perm`: A^-1 r = G (P r), (P r)_i = r_perm[i]).
+// A = I - c J from the row-major Jacobian Js[n][N] in shared memory, then gj_rows
 template <int N>
 __device__ __forceinline__ void factor_rows(const double* __restrict__ Js, int n, double c, int lane, double (&G)[N], int& perm) {
   const int li = lane < n ? lane : 0;
 #pragma unroll
   for (int q = 0; q < N; q++) G[q] = ((q == lane) ? 1.0 : 0.0) - ((q < n && lane < n) ? c * Js[li * N + q] : 0.0);
-  perm = lane;
-#pragma unroll
-  for (int j = 0; j < N; j++) {
-    if (j < n) {
-      // pivot: largest |G[.][j]| among rows j..n-1
-      const double v = (lane >= j && lane < n) ? fabs(G[j]) : -1.0;
-      const double vmax = wmax(v);
-      int pj = __ffs(__ballot_sync(PT_FULL, v == vmax)) - 1;
-      if (pj < 0) pj = j;
-      if (pj != j) {  // exchange rows j and pj (uniform branch)
-        const int src = (lane == j) ? pj : (lane == pj) ? j : lane;
-#pragma unroll
-        for (int q = 0; q < N; q++) G[q] = __shfl_sync(PT_FULL, G[q], src);
-        perm = __shfl_sync(PT_FULL, perm, src);
-      }
-      double pr[N];
-#pragma unroll
-      for (int q = 0; q < N; q++) pr[q] = __shfl_sync(PT_FULL, G[q], j);
-      double pv = pr[j];
-      if (pv == 0.) pv = 1e-50;  // TINY, as ludcmp does for a singular pivot
-      const double pinv = 1.0 / pv;
-      const double f = (lane == j) ? 0. : G[j];
-#pragma unroll
-      for (int q = 0; q < N; q++) {
-        const double pq = pr[q] * pinv;
-        if (q == j) G[q] = (lane == j) ? pinv : -f * pinv;
-        else G[q] = (lane == j) ? pq : G[q] - f * pq;
-      }
-    }
-  }
+  gj_rows<N>(G, n, lane, perm);
 }
 
 template <int N>
@@ -2711,14 +2758,6 @@ __global__ void __launch_bounds__(32, 16) perturb_tail_kernel(const __grid_const
 // =============================================================================================
 // host side
 // =============================================================================================
-template <typename T>
-static int dev_reserve(T** p, size_t* cap, size_t n, char* err) {
-  if (*p && *cap >= n) return CLPP_SUCCESS;
-  if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
-  CLPP_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)), err);
-  *cap = n;
-  return CLPP_SUCCESS;
-}
 
 static void set_geometry(PtParams& P, int neq_max, int nh_max, const clpp_perturb_desc& pd);
 
@@ -2795,7 +2834,9 @@ static void set_geometry(PtParams& P, int neq_max, int nh_max, const clpp_pertur
   P.o_nw = P.o_hubtmp + std::max(nh_max, 32);
   P.o_i2l1 = P.o_nw + 4 * ((P.nq_tot + 1) & ~1);
   P.n_i2l1 = (std::max(std::max(pd.l_max_g, pd.l_max_pol_g), std::max(pd.l_max_ur, pd.l_max_ncdm)) + 2 + 1) & ~1;
-  P.o_vec = P.o_i2l1 + P.n_i2l1;
+  P.ncol = (std::max(P.bg_size_normal, P.th_size) <= 16) ? 16 : 32;
+  P.o_tabc = P.o_i2l1 + P.n_i2l1;
+  P.o_vec = P.o_tabc + 16 * P.ncol;
   P.o_sinv = P.o_vec + V_COUNT * P.np;
   P.o_int = P.o_sinv + ((P.nh_max * P.ldh + 1) & ~1);
 }
@@ -2832,21 +2873,18 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     const int nk = I.k_size, nt = I.tau_size, ntp = I.tp_size;
     const size_t nsrc = (size_t)ntp * nk * nt;
     cudaStream_t sb = d->stream;
-    if (!d->sources || d->sources_count != nsrc) {
-      if (d->sources) { cudaFree(d->sources); d->sources = nullptr; }
-      CLPP_CUDA(cudaMalloc((void**)&d->sources, nsrc * sizeof(double)), err);
-      d->sources_count = nsrc;
-      CLPP_CUDA(cudaMemsetAsync(d->sources, 0, nsrc * sizeof(double), sb), err);
-    }
-    if (dev_reserve(&d->k, &d->k_cap, nk, err) || dev_reserve(&d->tau, &d->tau_cap, nt, err) ||
-        dev_reserve(&d->kstat, &d->kstat_cap, nk, err))
+    if (clpp_dev_reserve(d, &d->sources, nsrc, err)) return CLPP_FAILURE;
+    if (d->sources_count != nsrc) CLPP_CUDA(cudaMemsetAsync(d->sources, 0, nsrc * sizeof(double), sb), err);
+    d->sources_count = nsrc;
+    if (clpp_dev_reserve(d, &d->k, nk, err) || clpp_dev_reserve(d, &d->tau, nt, err) ||
+        clpp_dev_reserve(d, &d->kstat, nk, err))
       return CLPP_FAILURE;
     CLPP_CUDA(cudaMemcpyAsync(d->k, c->k.data(), nk * sizeof(double), cudaMemcpyHostToDevice, sb), err);
     CLPP_CUDA(cudaMemcpyAsync(d->tau, c->tau.data(), nt * sizeof(double), cudaMemcpyHostToDevice, sb), err);
     CLPP_CUDA(cudaMemsetAsync(d->kstat, 0, nk * sizeof(clpp_kstat), sb), err);
     const size_t tot = c->ncdm_q.size();
     if (c->N_ncdm > 0) {
-      if (dev_reserve(&d->ncdm, &d->ncdm_cap, 3 * tot, err)) return CLPP_FAILURE;
+      if (clpp_dev_reserve(d, &d->ncdm, 3 * tot, err)) return CLPP_FAILURE;
       CLPP_CUDA(cudaMemcpyAsync(d->ncdm, c->ncdm_q.data(), tot * sizeof(double), cudaMemcpyHostToDevice, sb), err);
       CLPP_CUDA(cudaMemcpyAsync(d->ncdm + tot, c->ncdm_w.data(), tot * sizeof(double), cudaMemcpyHostToDevice, sb), err);
       CLPP_CUDA(cudaMemcpyAsync(d->ncdm + 2 * tot, c->ncdm_dlnf0.data(), tot * sizeof(double), cudaMemcpyHostToDevice, sb), err);
@@ -2878,9 +2916,9 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   std::vector<int2> sorted(n_modes);
   for (int i = 0; i < n_modes; i++) sorted[i] = modes[perm[i]];
 
-  if (dev_reserve(&d0->pt_cosmo, &d0->pt_cosmo_cap, n_ctx * sizeof(PtCosmo), err)) return CLPP_FAILURE;
-  if (dev_reserve(&d0->pt_modes, &d0->pt_modes_cap, (size_t)std::max(n_modes, 1) * sizeof(int2), err)) return CLPP_FAILURE;
-  if (dev_reserve(&d0->jac_scratch, &d0->jac_cap, (size_t)std::max(n_modes, 1) * P.nh_max * P.nh_max, err))
+  if (clpp_dev_reserve(d0, &d0->pt_cosmo, n_ctx * sizeof(PtCosmo), err)) return CLPP_FAILURE;
+  if (clpp_dev_reserve(d0, &d0->pt_modes, (size_t)std::max(n_modes, 1) * sizeof(int2), err)) return CLPP_FAILURE;
+  if (clpp_dev_reserve(d0, &d0->jac_scratch, (size_t)std::max(n_modes, 1) * P.nh_max * P.nh_max, err))
     return CLPP_FAILURE;
   CLPP_CUDA(cudaMemcpyAsync(d0->pt_cosmo, cosmo.data(), n_ctx * sizeof(PtCosmo), cudaMemcpyHostToDevice, st), err);
   CLPP_CUDA(cudaMemcpyAsync(d0->pt_modes, sorted.data(), n_modes * sizeof(int2), cudaMemcpyHostToDevice, st), err);
@@ -2892,7 +2930,7 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   P.force_generic = getenv("CLPP_GENERIC_ONLY") != nullptr;
   const bool use_tail = getenv("CLPP_NO_TAIL") == nullptr && !P.force_generic;
   if (use_tail) {
-    if (dev_reserve(&d0->pt_tail, &d0->pt_tail_cap, (size_t)std::max(n_modes, 1) * TL_STRIDE, err)) return CLPP_FAILURE;
+    if (clpp_dev_reserve(d0, &d0->pt_tail, (size_t)std::max(n_modes, 1) * TL_STRIDE, err)) return CLPP_FAILURE;
     CLPP_CUDA(cudaMemsetAsync(d0->pt_tail, 0, (size_t)std::max(n_modes, 1) * TL_STRIDE * sizeof(double), st), err);
     P.tail = d0->pt_tail;
   }
@@ -2906,16 +2944,53 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   set_geometry(Pt, 16, 16, c0->pd);
   const size_t smem_tail = perturb_smem_bytes(Pt);
   CLPP_CUDA(cudaFuncSetAttribute(perturb_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail), err);
+  if (getenv("CLPP_VERBOSE"))
+    fprintf(stderr, "[clpp] perturb: %d modes, shared memory per mode %zu B (tail %zu B), sizeof(Mode) %zu, neq_max %d, hub %d\n",
+            n_modes, smem, smem_tail, sizeof(Mode), P.neq_max, P.nh_max);
+  // Two groups on two streams: the modes with long radiation-streaming tails (top decade in k, issued
+  // first) finish their early phases quickly and run their tails -- the serial critical path -- WHILE
+  // the bulk of the modes is still in the generic kernel.
+  int n_long = 0;
+  if (use_tail && n_modes > 0) {
+    const double kcut = 0.1 * cost[perm[0]];
+    while (n_long < n_modes && cost[perm[n_long]] >= kcut) n_long++;
+    if (n_long == n_modes) n_long = 0;  // nothing to overlap with
+  }
+  for (int i = 0; i < 6; i++)
+    if (!d0->ev2[i]) cudaEventCreate(&d0->ev2[i]);
+  if (!d0->stream2) {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority
+    CLPP_CUDA(cudaStreamCreateWithPriority(&d0->stream2, cudaStreamNonBlocking, prio_lo), err);
+    CLPP_CUDA(cudaStreamCreateWithPriority(&d0->stream_hi, cudaStreamNonBlocking, prio_hi), err);
+  }
+  cudaStream_t st2 = d0->stream2, sth = d0->stream_hi;
+  auto launch_group = [&](cudaStream_t s, int first, int count) {
+    if (count <= 0) return;
+    PtParams G = P, Gt = Pt;
+    G.modes = P.modes + first; G.n_modes = count;
+    G.hub_jac = P.hub_jac + (size_t)first * P.nh_max * P.nh_max;
+    G.tail = P.tail ? P.tail + (size_t)first * TL_STRIDE : nullptr;
+    perturb_kernel<<<count, 32, smem, s>>>(G);
+    c0->launches++;
+    if (use_tail) {
+      Gt.modes = G.modes; Gt.n_modes = count; Gt.tail = G.tail; Gt.hub_jac = G.hub_jac;
+      perturb_tail_kernel<<<count, 32, smem_tail, s>>>(Gt);
+      c0->launches++;
+    }
+  };
   cudaEventRecord(d0->ev[0], st);
   if (n_modes > 0) {
-    perturb_kernel<<<n_modes, 32, smem, st>>>(P);
-    c0->launches++;
-    for (int i = 0; i < 6; i++)
-      if (!d0->ev2[i]) cudaEventCreate(&d0->ev2[i]);
-    cudaEventRecord(d0->ev2[4], st);
-    if (use_tail) {
-      perturb_tail_kernel<<<n_modes, 32, smem_tail, st>>>(Pt);
-      c0->launches++;
+    cudaEventRecord(d0->ev2[4], st);        // uploads on st are complete before the other streams start
+    cudaStreamWaitEvent(sth, d0->ev2[4], 0);
+    cudaStreamWaitEvent(st2, d0->ev2[4], 0);
+    launch_group(sth, 0, n_long > 0 ? n_long : n_modes);  // high priority: its tail CTAs take the slots as they free up
+    cudaEventRecord(d0->ev2[5], sth);
+    cudaStreamWaitEvent(st, d0->ev2[5], 0);
+    if (n_long > 0) {
+      launch_group(st2, n_long, n_modes - n_long);
+      cudaEventRecord(d0->ev2[3], st2);
+      cudaStreamWaitEvent(st, d0->ev2[3], 0);
     }
   }
   cudaEventRecord(d0->ev[1], st);
@@ -2932,7 +3007,6 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     cudaEventElapsedTime(&ms, d0->ev[0], d0->ev[1]);
     for (int b = 0; b < n_ctx; b++) { cs[b]->dev->t_perturb_ms = 0.; cs[b]->dev->t_perturb_tail_ms = 0.; }
     d0->t_perturb_ms = ms;
-    if (n_modes > 0) { cudaEventElapsedTime(&ms, d0->ev2[4], d0->ev[1]); d0->t_perturb_tail_ms = ms; }
   }
   for (int b = 0; b < n_ctx; b++) {
     clpp_ctx* c = cs[b];
