@@ -170,10 +170,18 @@ enum {
 };
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double wmax(double v) {
+__device__ __forceinline__ double wmax_any(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(PT_FULL, v, o));
   return v;
+}
+// warp maximum of NON-NEGATIVE doubles (error norms): their bit patterns order like unsigned integers, so two
+// hardware integer reductions (REDUX) replace five double shuffle+max rounds
+__device__ __forceinline__ double wmax(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mhi = __reduce_max_sync(PT_FULL, hi);
+  const unsigned mlo = __reduce_max_sync(PT_FULL, hi == mhi ? lo : 0u);
+  return __hiloint2double((int)mhi, (int)mlo);
 }
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
@@ -181,7 +189,9 @@ __device__ __forceinline__ double wsum(double v) {
   return v;
 }
 // x^(1/n), x > 0 (step-size heuristics; the reference calls pow)
-__device__ __forceinline__ double root_n(double x, double n) { return exp(log(x) / n); }
+// (the operands are ratios of error norms to the tolerance: float range and float accuracy are ample for a
+// step-size heuristic; the reference calls pow())
+__device__ __forceinline__ double root_n(double x, double n) { return (double)exp2f(__log2f((float)x) / (float)n); }
 
 // largest index inf <= n-2 with X[inf] <= x (X growing): 32-ary search, one probe per lane
 __device__ __forceinline__ int locate_warp(const double* __restrict__ X, int n, double x, int lane) {
@@ -962,7 +972,7 @@ __device__ __forceinline__ void gj_rows(double (&G)[N], int n, int lane, int& pe
     for (int q = 1; q < N; q++) gj = (q == j) ? G[q] : gj;
     // pivot: largest |G[.][j]| among rows j..n-1
     const double v = (lane >= j && lane < n) ? fabs(gj) : -1.0;
-    const double vmax = wmax(v);
+    const double vmax = wmax_any(v);
     int pj = __ffs(__ballot_sync(PT_FULL, v == vmax)) - 1;
     if (pj < 0) pj = j;
     if (pj != j) {  // exchange rows j and pj (uniform branch)
