@@ -47,10 +47,15 @@ LCDM_COARSE = dict(LCDM, **{
     "q_linstep": 1.5,
 })
 
+# config 4 (three separate species, neq up to 316, 58 hub variables) on the coarse grids: exercises the large-system
+# fallbacks of the device path (generic NDF, shared-memory Gauss-Jordan, 18 chains)
+NCDM3_COARSE = dict(LCDM_COARSE, **{"N_ur": 0.00641, "N_ncdm": 3, "m_ncdm": "0.02,0.02,0.02"})
+
 CONFIGS = {
     "lcdm": LCDM,
     "planck18": PLANCK18,
     "planck18_linear": PLANCK18_LINEAR,
     "ncdm3_deg": NCDM3_DEG,
     "lcdm_coarse": LCDM_COARSE,
+    "ncdm3_coarse": NCDM3_COARSE,
 }

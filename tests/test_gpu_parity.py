@@ -94,6 +94,25 @@ def test_planck18_ncdm_halofit_pipeline_vs_golden(golden):
     ctx.close()
 
 
+def test_massive_neutrinos_degenerate_pipeline_vs_golden(golden):
+    """BASELINE config 4 (degenerate form): 3 degenerate massive neutrinos, m = 0.02 eV."""
+    inp = golden("ncdm3_deg")
+    ctx, pt, tr, sp = run_pipeline(inp)
+    check_cl(sp, inp.arrays["ref.cl"])
+    assert np.array_equal(pt.k_[0], inp.arrays["ref.k"]) and np.array_equal(pt.tau_sampling_, inp.arrays["ref.tau"])
+    ctx.close()
+
+
+def test_three_ncdm_species_large_system_vs_golden(golden):
+    """Three separate ncdm species (316 equations, 58 hub variables, 18 chains) on the coarse grids: the
+    large-system fallbacks of the device path (generic NDF, shared-memory Gauss-Jordan)."""
+    inp = golden("ncdm3_coarse")
+    ctx, pt, tr, sp = run_pipeline(inp)
+    check_cl(sp, inp.arrays["ref.cl"], rtol=5e-4)  # coarse grids, see lcdm_coarse
+    assert int(pt.kprofile_[:, 0, :].max()) == 316
+    ctx.close()
+
+
 @pytest.mark.parametrize("name", ["lcdm_coarse", "planck18"])
 def test_spectra_stage_vs_numpy_restatement(golden, name):
     """Stage 3 in isolation on random transfer functions: CUDA quadrature == numpy restatement of
