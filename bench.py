@@ -108,6 +108,8 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line of the contract
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
