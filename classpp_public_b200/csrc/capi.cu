@@ -77,6 +77,10 @@ void clpp_ctx_destroy(clpp_ctx* c) {
     cudaEventDestroy(d->ev[1]);
     if (d->stream2) cudaStreamDestroy(d->stream2);
     if (d->stream_hi) cudaStreamDestroy(d->stream_hi);
+    for (int i = 0; i < CLPP_PT_MAX_CHUNKS; i++) {
+      if (d->chunk_stream[i]) cudaStreamDestroy(d->chunk_stream[i]);
+      if (d->chunk_done[i]) cudaEventDestroy(d->chunk_done[i]);
+    }
     cudaStreamDestroy(d->stream);
     delete d;
   }

@@ -8,8 +8,12 @@
 
 #include "clpp_internal.h"
 
+#define CLPP_PT_MAX_CHUNKS 8
+
 struct clpp_ctx::Dev {
-  cudaStream_t stream = nullptr, stream2 = nullptr, stream_hi = nullptr;  // stream2: second group of the perturbation launch
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream_hi = nullptr;
+  cudaStream_t chunk_stream[CLPP_PT_MAX_CHUNKS] = {};  // low-priority streams of the bulk chunks of a perturbation launch
+  cudaEvent_t chunk_done[CLPP_PT_MAX_CHUNKS] = {};  // stream2: second group of the perturbation launch
   int sm_count = 0;
   // per-kernel device timings of the last stage calls (CUDA events on `stream`), in ms
   cudaEvent_t ev[2] = {nullptr, nullptr};

@@ -44,6 +44,7 @@
 #define PT_MAX_NCDM 3
 #define PT_MAX_INTERVALS 6
 #define PT_MAX_CHAINS 32
+#define PT_MAX_CHUNKS CLPP_PT_MAX_CHUNKS
 #define PT_FULL 0xffffffffu
 
 // ---------------------------------------------------------------------------------------------
@@ -2923,8 +2924,32 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   std::vector<int> perm(n_modes);
   for (int i = 0; i < n_modes; i++) perm[i] = i;
   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  // Launch groups.  Group L: the modes with long radiation-streaming tails (top decade in k), high-priority
+  // stream, issued first: they finish their early phases quickly and run their tails -- the serial critical
+  // path -- while the bulk is still in the generic kernel.  The bulk is dealt round-robin into chunks, one
+  // low-priority stream each (generic kernel -> tail kernel), so that the tails of a chunk overlap the
+  // generic phases of the next ones instead of all waiting for the last generic CTA.
+  const bool force_generic = getenv("CLPP_GENERIC_ONLY") != nullptr;
+  const bool use_tail = getenv("CLPP_NO_TAIL") == nullptr && !force_generic;
+  int n_long = 0;
+  if (use_tail && n_modes > 0) {
+    const double kcut = 0.1 * cost[perm[0]];
+    while (n_long < n_modes && cost[perm[n_long]] >= kcut) n_long++;
+    if (n_long == n_modes) n_long = 0;  // nothing to overlap with
+  }
+  const int n_bulk = n_modes - n_long;
+  const int n_chunks = use_tail ? std::max(1, std::min(PT_MAX_CHUNKS, n_bulk / 4000)) : 1;
   std::vector<int2> sorted(n_modes);
-  for (int i = 0; i < n_modes; i++) sorted[i] = modes[perm[i]];
+  std::vector<int> chunk_first(n_chunks + 1, n_long);
+  for (int i = 0; i < n_long; i++) sorted[i] = modes[perm[i]];
+  {
+    int pos = n_long;
+    for (int c = 0; c < n_chunks; c++) {
+      chunk_first[c] = pos;
+      for (int i = n_long + c; i < n_modes; i += n_chunks) sorted[pos++] = modes[perm[i]];
+    }
+    chunk_first[n_chunks] = pos;
+  }
 
   if (clpp_dev_reserve(d0, &d0->pt_cosmo, n_ctx * sizeof(PtCosmo), err)) return CLPP_FAILURE;
   if (clpp_dev_reserve(d0, &d0->pt_modes, (size_t)std::max(n_modes, 1) * sizeof(int2), err)) return CLPP_FAILURE;
@@ -2937,8 +2962,7 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   P.n_modes = n_modes;
   P.hub_jac = d0->jac_scratch;
   // hand-off records of the tail (radiation-streaming) kernel
-  P.force_generic = getenv("CLPP_GENERIC_ONLY") != nullptr;
-  const bool use_tail = getenv("CLPP_NO_TAIL") == nullptr && !P.force_generic;
+  P.force_generic = force_generic;
   if (use_tail) {
     if (clpp_dev_reserve(d0, &d0->pt_tail, (size_t)std::max(n_modes, 1) * TL_STRIDE, err)) return CLPP_FAILURE;
     CLPP_CUDA(cudaMemsetAsync(d0->pt_tail, 0, (size_t)std::max(n_modes, 1) * TL_STRIDE * sizeof(double), st), err);
@@ -2957,15 +2981,6 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   if (getenv("CLPP_VERBOSE"))
     fprintf(stderr, "[clpp] perturb: %d modes, shared memory per mode %zu B (tail %zu B), sizeof(Mode) %zu, neq_max %d, hub %d\n",
             n_modes, smem, smem_tail, sizeof(Mode), P.neq_max, P.nh_max);
-  // Two groups on two streams: the modes with long radiation-streaming tails (top decade in k, issued
-  // first) finish their early phases quickly and run their tails -- the serial critical path -- WHILE
-  // the bulk of the modes is still in the generic kernel.
-  int n_long = 0;
-  if (use_tail && n_modes > 0) {
-    const double kcut = 0.1 * cost[perm[0]];
-    while (n_long < n_modes && cost[perm[n_long]] >= kcut) n_long++;
-    if (n_long == n_modes) n_long = 0;  // nothing to overlap with
-  }
   for (int i = 0; i < 6; i++)
     if (!d0->ev2[i]) cudaEventCreate(&d0->ev2[i]);
   if (!d0->stream2) {
@@ -2973,8 +2988,12 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority
     CLPP_CUDA(cudaStreamCreateWithPriority(&d0->stream2, cudaStreamNonBlocking, prio_lo), err);
     CLPP_CUDA(cudaStreamCreateWithPriority(&d0->stream_hi, cudaStreamNonBlocking, prio_hi), err);
+    for (int c = 0; c < PT_MAX_CHUNKS; c++) {
+      CLPP_CUDA(cudaStreamCreateWithPriority(&d0->chunk_stream[c], cudaStreamNonBlocking, prio_lo), err);
+      CLPP_CUDA(cudaEventCreateWithFlags(&d0->chunk_done[c], cudaEventDisableTiming), err);
+    }
   }
-  cudaStream_t st2 = d0->stream2, sth = d0->stream_hi;
+  cudaStream_t sth = d0->stream_hi;
   auto launch_group = [&](cudaStream_t s, int first, int count) {
     if (count <= 0) return;
     PtParams G = P, Gt = Pt;
@@ -2992,15 +3011,18 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   cudaEventRecord(d0->ev[0], st);
   if (n_modes > 0) {
     cudaEventRecord(d0->ev2[4], st);        // uploads on st are complete before the other streams start
-    cudaStreamWaitEvent(sth, d0->ev2[4], 0);
-    cudaStreamWaitEvent(st2, d0->ev2[4], 0);
-    launch_group(sth, 0, n_long > 0 ? n_long : n_modes);  // high priority: its tail CTAs take the slots as they free up
-    cudaEventRecord(d0->ev2[5], sth);
-    cudaStreamWaitEvent(st, d0->ev2[5], 0);
     if (n_long > 0) {
-      launch_group(st2, n_long, n_modes - n_long);
-      cudaEventRecord(d0->ev2[3], st2);
-      cudaStreamWaitEvent(st, d0->ev2[3], 0);
+      cudaStreamWaitEvent(sth, d0->ev2[4], 0);
+      launch_group(sth, 0, n_long);  // high priority: its tail CTAs take the slots as they free up
+      cudaEventRecord(d0->ev2[5], sth);
+      cudaStreamWaitEvent(st, d0->ev2[5], 0);
+    }
+    for (int c = 0; c < n_chunks; c++) {
+      cudaStream_t sc = d0->chunk_stream[c];
+      cudaStreamWaitEvent(sc, d0->ev2[4], 0);
+      launch_group(sc, chunk_first[c], chunk_first[c + 1] - chunk_first[c]);
+      cudaEventRecord(d0->chunk_done[c], sc);
+      cudaStreamWaitEvent(st, d0->chunk_done[c], 0);
     }
   }
   cudaEventRecord(d0->ev[1], st);
