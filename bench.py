@@ -260,9 +260,11 @@ def run_gpu(args):
                    "fixture": "tests/golden/%s.npz" % args.config, "batch_per_gpu": B,
                    "k_modes": int(results[0][0].info.k_size), "tau_samples": int(results[0][0].info.tau_size),
                    "q_values": int(tr_info.q_size), "l_values": int(tr_info.l_size),
-                   "parallelism": "independent cosmologies per GPU (replicas, no data-path collective)",
-                   "l2_policy": "working set per step (sources 24 MB + source spline 48 MB + Bessel 17 MB + transfer 12 MB "
-                                "+ Jacobian scratch) is reallocated and rewritten every step; > L2 with the scratch",
+                   "parallelism": "independent cosmologies per GPU (replicas, no data-path collective); per GPU all k modes "
+                                  "of the batch in one batched launch: long-tail modes on a high-priority stream, the bulk in "
+                                  "chunks on low-priority streams, generic kernel -> radiation-streaming tail kernel",
+                   "l2_policy": "working set per step = batch x (tables 6 MB + sources 24 MB + source spline 72 MB + Bessel 25 MB "
+                                "+ transfer 12 MB) >> 126 MB L2; every buffer is rewritten every step",
                    "timing": "torch.cuda.Event around K steps after device-wide synchronize, max over ranks; per-kernel "
                              "times from cudaEvents on the launching stream inside libclpp.so"},
         "k_modes_per_s": value * int(results[0][0].info.k_size),
@@ -350,7 +352,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="planck18")
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("CLPP_BENCH_BATCH", 64)),
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("CLPP_BENCH_BATCH", 128)),
                     help="cosmologies per GPU and per step (one batched perturbation launch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

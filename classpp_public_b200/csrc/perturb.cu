@@ -2722,7 +2722,10 @@ __global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid
 
 // Tail kernel: the radiation-streaming interval of every mode that perturb_kernel handed off.  Small
 // shared-memory footprint and register budget (16+ warps per SM), compact hot loop (ndf15_rsa).
-__global__ void __launch_bounds__(32, 16) perturb_tail_kernel(const __grid_constant__ PtParams P) {
+#ifndef PT_TAIL_MIN_BLOCKS
+#define PT_TAIL_MIN_BLOCKS 12  // 168 registers: no spills in ndf15_rsa (16 -> 128 registers spills and is 25 % slower)
+#endif
+__global__ void __launch_bounds__(32, PT_TAIL_MIN_BLOCKS) perturb_tail_kernel(const __grid_constant__ PtParams P) {
   if ((int)blockIdx.x >= P.n_modes) return;
   const double* T = P.tail + (size_t)blockIdx.x * TL_STRIDE;
   if (T[TL_VALID] != 1.) return;
