@@ -2835,6 +2835,11 @@ static int fill_common(const clpp_ctx* c, PtParams& P, char* err) {
   P.iTb = th.index_th_Tb; P.itau_d = th.index_th_tau_d; P.irate = th.index_th_rate; P.ir_d = th.index_th_r_d;
   P.idcb2 = th.index_th_dcb2; P.iddcb2 = th.index_th_ddcb2;
   P.compute_cb2_derivatives = th.compute_cb2_derivatives; P.compute_damping_scale = th.compute_damping_scale;
+  // the reference leaves the indices of absent columns unset: normalise them so that equal settings compare equal
+  if (!P.compute_damping_scale) P.ir_d = 0;
+  if (!P.compute_cb2_derivatives) { P.idcb2 = 0; P.iddcb2 = 0; }
+  if (!bg.has_ur) P.irho_ur = 0;
+  if (!bg.has_ncdm) { P.irho_ncdm1 = 0; P.ip_ncdm1 = 0; P.ipseudo_p_ncdm1 = 0; }
   P.has_ur = bg.has_ur; P.has_ncdm = bg.has_ncdm; P.N_ncdm = bg.has_ncdm ? bg.N_ncdm : 0;
   int off = 0;
   for (int s = 0; s < P.N_ncdm; s++) {
@@ -2912,9 +2917,13 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     CLPP_CHECK(cs[b]->dev && cs[b]->device == c0->device, err, "all contexts of a batch must live on the same CUDA device");
     PtParams Q;
     if (fill_common(cs[b], Q, err)) return CLPP_FAILURE;
-    CLPP_CHECK(memcmp(&P, &Q, sizeof(P)) == 0, err,
-               "cosmology %d of the batch differs from cosmology 0 in the precision settings / species content / "
-               "requested sources: such cosmologies must be solved in separate batches", b);
+    if (memcmp(&P, &Q, sizeof(P)) != 0) {
+      size_t off = 0;
+      while (off < sizeof(P) && ((const unsigned char*)&P)[off] == ((const unsigned char*)&Q)[off]) off++;
+      return clpp_fail(err, "cosmology %d of the batch differs from cosmology 0 in the precision settings / species content / "
+                       "requested sources (first difference at byte %zu of the common block): such cosmologies must be solved "
+                       "in separate batches", b, off);
+    }
   }
 
   std::vector<PtCosmo> cosmo(n_ctx);

@@ -183,6 +183,48 @@ def test_stage_isolation_vs_live_reference(reference):
     ctx.close()
 
 
+def test_sweep_of_different_cosmologies_in_one_batch_vs_live_reference():
+    """BASELINE config 5 in miniature: a Latin-hypercube sweep of 6 DIFFERENT cosmologies (different tables,
+    different k/tau/q grid sizes) pushed through ONE batched perturbation launch; every cosmology must match the
+    reference run with the same parameters (coarse grids: 5e-4, see lcdm_coarse)."""
+    from oracle import refprobe
+    if not refprobe.available():
+        pytest.skip("oracle/_ref not loadable on this box")
+    import os
+    from scipy.stats import qmc
+    from classpp_public_b200.configs import CONFIGS
+    from refutil import inputs_from_reference
+    lo = np.array([0.020, 0.10, 0.60, 2.9, 0.92, 0.03])   # omega_b, omega_cdm, h, ln(1e10 A_s), n_s, tau_reio
+    hi = np.array([0.024, 0.14, 0.75, 3.2, 1.00, 0.09])
+    pts_lhs = qmc.scale(qmc.LatinHypercube(d=6, seed=0).random(6), lo, hi)
+    refs, inps = [], []
+    for x in pts_lhs:
+        par = dict(CONFIGS["lcdm_coarse"], omega_b=x[0], omega_cdm=x[1], h=x[2], A_s=1e-10 * np.exp(x[3]), n_s=x[4],
+                   tau_reio=x[5])
+        ref = refprobe.RefCosmology(par, threads=os.cpu_count()).compute("spectra")
+        refs.append(ref)
+        inps.append(inputs_from_reference(ref))
+    ctxs, mods, pts = [], [], []
+    for inp in inps:
+        c = M.Context(0)
+        b = M.BackgroundModule(inp, c)
+        t = M.ThermodynamicsModule(inp, b)
+        ctxs.append(c)
+        mods.append((b, t))
+        pts.append(M.PerturbationsModule(inp, b, t, solve=False))
+    assert len({p.info.k_size for p in pts} | {p.info.tau_size for p in pts}) > 2  # the grids really differ
+    M.PerturbationsModule.solve_batch(pts)
+    for inp, ref, (b, t), p in zip(inps, refs, mods, pts):
+        assert np.array_equal(p.k_[0], ref.get("pt.k")) and np.array_equal(p.tau_sampling_, ref.get("pt.tau_sampling"))
+        tr = M.TransferModule(inp, b, t, p, None)
+        sp = M.SpectraModule(inp, p, M.TabulatedPrimordial(ref.get("pm.pk_at_transfer_k")), None, tr)
+        check_cl(sp, ref.get("sp.cl"), rtol=5e-4)
+    for c in ctxs:
+        c.close()
+    for r in refs:
+        r.close()
+
+
 def test_k_range_partition_equals_full_solve(golden):
     """Multi-GPU partition property: integrating two k ranges separately fills the same source table."""
     inp = golden("lcdm_coarse")
