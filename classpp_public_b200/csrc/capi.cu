@@ -14,6 +14,7 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
 int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_begin, int q_end, char* err);
 int clpp_dev_spectra(clpp_ctx* c, const double* primordial_pk, int q_begin, int q_end, clpp_spectra_info* info,
                      double* cl_out, char* err);
+int clpp_host_cl_at_l(const clpp_ctx* c, double l, double* cl_tot, char* err);
 int clpp_dev_get_bessel(clpp_ctx* c, double* x, double* phi, double* dphi, double* chi, char* err);
 
 template <typename T>
@@ -373,6 +374,23 @@ int clpp_spectra_compute_range(clpp_ctx* c, const double* primordial_pk, int q_b
   CLPP_CHECK(0 <= q_begin && q_begin <= q_end && q_end <= c->tinfo.q_size, err, "bad q range [%d,%d)", q_begin, q_end);
   cudaSetDevice(c->device);
   return clpp_dev_spectra(c, primordial_pk, q_begin, q_end, info, cl_out, err);
+}
+
+int clpp_spectra_cl_at_l(const clpp_ctx* c, double l, double* cl_tot, char* err) {
+  CLPP_CHECK(c && cl_tot, err, "null argument");
+  return clpp_host_cl_at_l(c, l, cl_tot, err);
+}
+
+int clpp_spectra_cl_output(const clpp_ctx* c, int lmax, double* out, char* err) {
+  CLPP_CHECK(c && out, err, "null argument");
+  CLPP_CHECK(c->has_cl, err, "Error: Cls have not been computed! lmax = %d", lmax);
+  const int l_max_tot = (int)c->clt.x[c->clt.n_lines - 1];
+  CLPP_CHECK(lmax >= 0 && lmax <= l_max_tot, err, "Error: lmax = %d is outside the allowed range [0, %d]", lmax, l_max_tot);
+  const int ct = c->clt.n_cols;
+  for (int i = 0; i < 2 * ct && i < (lmax + 1) * ct; i++) out[i] = 0.;
+  for (int l = 2; l <= lmax; l++)
+    if (clpp_host_cl_at_l(c, (double)l, out + (size_t)l * ct, err)) return CLPP_FAILURE;
+  return CLPP_SUCCESS;
 }
 
 int clpp_spectra_compute(clpp_ctx* c, const double* primordial_pk, clpp_spectra_info* info, double* cl_out,

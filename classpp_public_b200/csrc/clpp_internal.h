@@ -95,6 +95,11 @@ struct clpp_ctx {
   std::vector<int> l, l_size_tt;
   std::vector<double> q, kq, chi_host;
 
+  // --- stage 3: C_l table on the l grid + its spline along l (spectra_cl_at_l)
+  bool has_cl = false;
+  HostTable clt;
+  int cl_l_max = 0;  // l_max_ct: C_l are zero above it
+
   // --- device memory (managed in device.cu)
   struct Dev;
   Dev* dev = nullptr;

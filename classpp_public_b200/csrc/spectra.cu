@@ -204,5 +204,34 @@ int clpp_dev_spectra(clpp_ctx* c, const double* primordial_pk, int q_begin, int 
                             d->stream), err);
   CLPP_CUDA(cudaStreamSynchronize(d->stream), err);
   { float ms = 0; cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); d->t_spectra_ms = ms; }
+  // table on the l grid + second derivatives along l for spectra_cl_at_l (spectra_module.cpp:905-927); only
+  // meaningful for the full q range (partial sums of a multi-GPU partition are splined after the all-reduce)
+  if (q_begin == 0 && q_end == T.q_size) {
+    HostTable& t = c->clt;
+    t.n_lines = T.l_size;
+    t.n_cols = I.ct_size;
+    t.x.resize(T.l_size);
+    for (int i = 0; i < T.l_size; i++) t.x[i] = (double)c->l[i];
+    t.y.assign(cl_out, cl_out + (size_t)T.l_size * I.ct_size);
+    t.ddy.resize(t.y.size());
+    clpp_spline_table_lines(t.x.data(), t.n_lines, t.y.data(), t.n_cols, t.ddy.data());
+    c->cl_l_max = c->td.l_scalar_max;
+    c->has_cl = true;
+  }
+  return CLPP_SUCCESS;
+}
+
+// spectra_cl_at_l, case (a): one mode, one initial condition (spectra_module.cpp:236-264)
+int clpp_host_cl_at_l(const clpp_ctx* c, double l, double* cl_tot, char* err) {
+  CLPP_CHECK(c && c->has_cl, err, "no C_l table: run clpp_spectra_compute first");
+  const HostTable& t = c->clt;
+  if ((int)l <= (int)t.x[t.n_lines - 1]) {
+    int last = 0;
+    if (clpp_interp_spline(t, l, &last, cl_tot, t.n_cols, err)) return CLPP_FAILURE;
+    if ((int)l > c->cl_l_max)
+      for (int ct = 0; ct < t.n_cols; ct++) cl_tot[ct] = 0.;
+  } else {
+    for (int ct = 0; ct < t.n_cols; ct++) cl_tot[ct] = 0.;
+  }
   return CLPP_SUCCESS;
 }

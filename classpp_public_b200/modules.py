@@ -389,6 +389,21 @@ class SpectraModule:
         self.l_size_max_ = i.l_size
         self.l_ = transfer_module.l_[: i.l_size].astype(np.float64)
         self.cl_ = [cl[: i.l_size * i.ct_size].copy()]
+        self.l_max_tot_ = int(self.l_[-1])
+
+    def spectra_cl_at_l(self, l):
+        """C_l^{ct} at (real) multipole l: spline in l, zero above l_max (reference: spectra_module.cpp:220)."""
+        out = np.zeros(self.ct_size_)
+        self.ctx.check(self.ctx._lib.clpp_spectra_cl_at_l(self.ctx.handle, float(l), capi.dptr(out), self.ctx.err))
+        return out
+
+    def cl_output(self, lmax):
+        """dict name -> C_l[0..lmax] (dimensionless), like SpectraModule::cl_output (spectra_module.cpp:146)."""
+        out = np.zeros((int(lmax) + 1) * self.ct_size_)
+        self.ctx.check(self.ctx._lib.clpp_spectra_cl_output(self.ctx.handle, int(lmax), capi.dptr(out), self.ctx.err))
+        tab = out.reshape(int(lmax) + 1, self.ct_size_)
+        return {n: tab[:, getattr(self, "index_ct_%s_" % n)].copy() for n in ("tt", "ee", "te", "bb", "pp", "tp", "ep")
+                if getattr(self, "has_%s_" % n)}
 
 
 class AnalyticPrimordial:

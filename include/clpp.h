@@ -225,6 +225,13 @@ int clpp_spectra_compute(clpp_ctx* ctx, const double* primordial_pk, clpp_spectr
 int clpp_spectra_compute_range(clpp_ctx* ctx, const double* primordial_pk, int q_begin, int q_end,
                                clpp_spectra_info* info, double* cl_out, char* err);
 
+/* replaces SpectraModule::spectra_cl_at_l (spectra_module.cpp:220-264, one mode / one initial condition):
+ * cubic spline in l through the table of clpp_spectra_compute, zero above l_scalar_max. cl_tot[ct_size]. */
+int clpp_spectra_cl_at_l(const clpp_ctx* ctx, double l, double* cl_tot, char* err);
+/* replaces SpectraModule::cl_output (spectra_module.cpp:146-198): out[(lmax+1)*ct_size], row l = C_l^{ct}
+ * (dimensionless), rows l = 0, 1 are zero; fails like the reference when lmax is outside [0, l_max_tot]. */
+int clpp_spectra_cl_output(const clpp_ctx* ctx, int lmax, double* out, char* err);
+
 #ifdef __cplusplus
 }
 #endif

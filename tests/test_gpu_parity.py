@@ -180,6 +180,17 @@ def test_stage_isolation_vs_live_reference(reference):
         assert np.max(np.abs(mine[tt] - r[tt])) < 1e-9 * np.max(np.abs(r[tt]))
     sp = M.SpectraModule(inp, pt, M.TabulatedPrimordial(ref.get("pm.pk_at_transfer_k")), None, tr)
     check_cl(sp, ref.get("sp.cl"), rtol=1e-9)
+    # spectra_cl_at_l / cl_output: the l-spline of the table, at every integer l, against the reference's own
+    lmax = 500
+    ref_at_l = ref.get("sp.cl_at_l.%d" % lmax).reshape(lmax + 1, sp.ct_size_)
+    out = sp.cl_output(lmax)
+    for name in ("tt", "ee", "pp"):
+        col = ref_at_l[:, getattr(sp.info, "index_ct_" + name)]
+        assert out[name][0] == 0.0 and out[name][1] == 0.0
+        assert np.max(np.abs(out[name][2:] / col[2:] - 1.0)) < 1e-8, name
+    assert np.all(sp.spectra_cl_at_l(sp.l_max_tot_ + 1) == 0.0)
+    with pytest.raises(M.CosmoComputationError):
+        sp.cl_output(sp.l_max_tot_ + 1)
     ctx.close()
 
 
