@@ -129,7 +129,7 @@ SYMBOLS = [
     "clpp_ctx_create", "clpp_ctx_destroy", "clpp_ctx_launch_count", "clpp_version",
     "clpp_ctx_get_stream", "clpp_ctx_get_kernel_ms", "clpp_measure_fp64_peak",
     "clpp_set_background", "clpp_set_thermo", "clpp_set_ncdm",
-    "clpp_perturb_grids", "clpp_perturb_solve", "clpp_perturb_solve_batch", "clpp_perturb_get_k", "clpp_perturb_get_tau",
+    "clpp_perturb_grids", "clpp_perturb_solve", "clpp_perturb_solve_batch", "clpp_perturb_solve_list", "clpp_perturb_get_k", "clpp_perturb_get_tau",
     "clpp_perturb_get_sources", "clpp_perturb_get_kstat", "clpp_perturb_set_sources",
     "clpp_perturb_device_sources",
     "clpp_transfer_grids", "clpp_transfer_compute", "clpp_transfer_get_l", "clpp_transfer_get_q",
@@ -167,6 +167,7 @@ def lib():
         L.clpp_perturb_grids.argtypes = [vp, P(PerturbDesc), P(PerturbInfo), cp]
         L.clpp_perturb_solve.argtypes = [vp, C.c_int, C.c_int, cp]
         L.clpp_perturb_solve_batch.argtypes = [P(vp), C.c_int, cp]
+        L.clpp_perturb_solve_list.argtypes = [vp, ip, C.c_int, cp]
         L.clpp_perturb_get_k.argtypes = [vp, dp]
         L.clpp_perturb_get_tau.argtypes = [vp, dp]
         L.clpp_perturb_get_sources.argtypes = [vp, dp, cp]

@@ -10,7 +10,9 @@
 
 // implemented in the stage files
 int clpp_dev_perturb_solve(clpp_ctx* c, int k_begin, int k_end, char* err);
-int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, const int* k_end, char* err);
+int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, const int* k_end, const int* k_list,
+                                 int n_list, char* err);
+int clpp_dev_perturb_solve_list(clpp_ctx* c, const int* k_list, int n, char* err);
 int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_begin, int q_end, char* err);
 int clpp_dev_spectra(clpp_ctx* c, const double* primordial_pk, int q_begin, int q_end, clpp_spectra_info* info,
                      double* cl_out, char* err);
@@ -228,7 +230,15 @@ int clpp_perturb_solve_batch(clpp_ctx** ctxs, int n_ctx, char* err) {
     ke[b] = c->pinfo.k_size;
   }
   cudaSetDevice(ctxs[0]->device);
-  return clpp_dev_perturb_solve_batch(ctxs, n_ctx, kb.data(), ke.data(), err);
+  return clpp_dev_perturb_solve_batch(ctxs, n_ctx, kb.data(), ke.data(), nullptr, 0, err);
+}
+
+int clpp_perturb_solve_list(clpp_ctx* c, const int* k_indices, int n, char* err) {
+  CLPP_CHECK(c && c->has_pgrids, err, "clpp_perturb_grids must be called first");
+  CLPP_CHECK(c->dev, err, "this context has no CUDA device: the B200 path has no CPU fallback");
+  CLPP_CHECK(k_indices != nullptr && n >= 0, err, "bad mode list");
+  cudaSetDevice(c->device);
+  return clpp_dev_perturb_solve_list(c, k_indices, n, err);
 }
 
 int clpp_perturb_get_k(const clpp_ctx* c, double* k) {

@@ -2906,8 +2906,14 @@ static size_t perturb_smem_bytes(const PtParams& P) {
 
 // Integrates modes [k_begin[i], k_end[i]) of every context in ONE kernel launch on the stream of
 // the first context (all contexts must live on the same device).
-int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, const int* k_end, char* err) {
+// `k_list` (optional): explicit mode indices of context 0 instead of the range (cost-balanced multi-GPU partitions).
+int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, const int* k_end, const int* k_list,
+                                 int n_list, char* err) {
   CLPP_CHECK(n_ctx >= 1, err, "empty batch");
+  CLPP_CHECK(k_list == nullptr || n_ctx == 1, err, "an explicit mode list is only supported for a single context");
+  // the modes of context b that this call integrates
+  auto n_sel = [&](int b) { return (k_list && b == 0) ? n_list : k_end[b] - k_begin[b]; };
+  auto sel = [&](int b, int i) { return (k_list && b == 0) ? k_list[i] : k_begin[b] + i; };
   clpp_ctx* c0 = cs[0];
   clpp_ctx::Dev* d0 = c0->dev;
   cudaStream_t st = d0->stream;
@@ -2965,7 +2971,9 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     Q.n_e = c->th.n_e; Q.YHe = c->th.YHe; Q.T_cmb = c->bg.T_cmb; Q.tau_free_streaming = c->th.tau_free_streaming;
     Q.a_today = c->bg.a_today;
     for (int s = 0; s < P.N_ncdm; s++) { Q.ncdm_M[s] = c->ncdm_M[s]; Q.ncdm_factor[s] = c->ncdm_factor[s]; }
-    for (int ik = k_begin[b]; ik < k_end[b]; ik++) {
+    for (int i = 0; i < n_sel(b); i++) {
+      const int ik = sel(b, i);
+      CLPP_CHECK(ik >= 0 && ik < nk, err, "mode index %d outside [0,%d)", ik, nk);
       modes.push_back(make_int2(b, ik));
       cost.push_back(c->k[ik]);  // the number of steps of a mode grows with k tau_0
     }
@@ -3094,7 +3102,8 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   }
   for (int b = 0; b < n_ctx; b++) {
     clpp_ctx* c = cs[b];
-    for (int ik = k_begin[b]; ik < k_end[b]; ik++) {
+    for (int i = 0; i < n_sel(b); i++) {
+      const int ik = sel(b, i);
       const int s = c->kstat[ik].status;
       if (s != 0) {
         const char* what = s == 2 ? "Step size too small in the NDF15 evolver"
@@ -3114,5 +3123,10 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
 }
 
 int clpp_dev_perturb_solve(clpp_ctx* c, int k_begin, int k_end, char* err) {
-  return clpp_dev_perturb_solve_batch(&c, 1, &k_begin, &k_end, err);
+  return clpp_dev_perturb_solve_batch(&c, 1, &k_begin, &k_end, nullptr, 0, err);
+}
+
+int clpp_dev_perturb_solve_list(clpp_ctx* c, const int* k_list, int n, char* err) {
+  const int zero = 0;
+  return clpp_dev_perturb_solve_batch(&c, 1, &zero, &zero, k_list, n, err);
 }

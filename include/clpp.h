@@ -157,6 +157,9 @@ int clpp_perturb_solve(clpp_ctx* ctx, int k_begin, int k_end, char* err);
  * issued longest-first across the whole batch. The reference has no counterpart (it runs one
  * Cosmology object at a time); per cosmology the result is identical to clpp_perturb_solve. */
 int clpp_perturb_solve_batch(clpp_ctx** ctxs, int n_ctx, char* err);
+/* (multi-GPU, one cosmology over several GPUs) integrates an explicit list of modes: cost-balanced partitions
+ * of the k grid are interleaved, not contiguous. Same result per mode as clpp_perturb_solve. */
+int clpp_perturb_solve_list(clpp_ctx* ctx, const int* k_indices, int n, char* err);
 int clpp_perturb_get_k(const clpp_ctx* ctx, double* k /*[k_size]*/);
 int clpp_perturb_get_tau(const clpp_ctx* ctx, double* tau /*[tau_size]*/);
 /* sources in the reference's layout sources_[index_tp][index_tau*k_size + index_k]

@@ -300,6 +300,55 @@ def test_tail_kernel_equals_single_kernel_path(golden, monkeypatch):
     assert np.max(np.abs(cl_tail[nz] / cl_one[nz] - 1.0)) < 2e-5
 
 
+def test_one_cosmology_over_two_ranks_equals_single_gpu(golden):
+    """Multi-GPU path of ONE cosmology (cost-balanced k partition -> exchange of S -> q partition -> sum of the
+    partial C_l), with the two ranks emulated as two contexts of this process and the collectives replaced by direct
+    device copies: the merged result equals the single-context run (sources bit-identical, C_l to rounding)."""
+    import torch
+    from classpp_public_b200 import multigpu
+    inp = golden("lcdm_coarse")
+    a = inp.arrays
+    prim = M.TabulatedPrimordial(a["pm.pk_at_transfer_k"])
+    ctx, pt_full, tr_full, sp_full = run_pipeline(inp)
+    s_full = np.stack(pt_full.sources_[0])
+    world = 2
+    ranks = []
+    for r in range(world):
+        c = M.Context(0)
+        bg, th, pt, parts = multigpu.stage1_partition(inp, c, world)
+        multigpu.solve_modes(pt, parts[r])
+        ranks.append((c, bg, th, pt, parts))
+    assert sorted(np.concatenate(ranks[0][4]).tolist()) == list(range(pt_full.info.k_size))
+    # "all-gather": copy every rank's columns into every other rank's table
+    views = [multigpu.device_sources(rk[3]) for rk in ranks]
+    for r in range(world):
+        idx = torch.as_tensor(ranks[r][4][r], device="cuda:0", dtype=torch.long)
+        for o in range(world):
+            if o != r:
+                views[o].index_copy_(1, idx, views[r].index_select(1, idx))
+    torch.cuda.synchronize()
+
+    class LocalSum:  # "all-reduce": collect the partial tables, sum at the end
+        parts = []
+
+        def allreduce_sum(self, cl, device):
+            self.parts.append(np.array(cl))
+            return cl
+
+    ex = LocalSum()
+    for r, (c, bg, th, pt, parts) in enumerate(ranks):
+        pt._sources = None
+        assert np.array_equal(np.stack(pt.sources_[0]), s_full)  # every rank now holds the full, identical table
+        multigpu.finish(inp, bg, th, pt, prim, None, r, world, ex)
+    cl = np.sum(ex.parts, axis=0)
+    full = sp_full.cl_[0]
+    nz = full != 0
+    assert np.max(np.abs(cl[nz] / full[nz] - 1.0)) < 1e-11
+    for rk in ranks:
+        rk[0].close()
+    ctx.close()
+
+
 def test_no_device_fails_loudly():
     with pytest.raises(M.CosmoComputationError):
         M.Context(device=9999)
