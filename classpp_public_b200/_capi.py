@@ -75,6 +75,7 @@ class PerturbDesc(C.Structure):
     double: ncdm_fluid_trigger_tau_over_tau_k
     int: evolver
     double: curvature_ini
+    double: perturb_integration_stepsize
     """)
 
 

@@ -162,7 +162,7 @@ int clpp_host_perturb_grids(clpp_ctx* c, char* err) {
   CLPP_CHECK(bg.sgnK == 0 && !bg.has_curvature, err, "the B200 path supports flat space only (K=0)");
   CLPP_CHECK(!bg.has_fld && !bg.has_scf && !bg.has_dcdm && !bg.has_dr && !bg.has_idr && !bg.has_idm_dr, err,
              "species fld/scf/dcdm/dr/idr/idm_dr are not supported by the B200 path");
-  CLPP_CHECK(p.evolver == 1, err, "the B200 path implements the ndf15 evolver only (evolver = 1)");
+  CLPP_CHECK(p.evolver == 0 || p.evolver == 1, err, "evolver = %d: must be 0 (rk) or 1 (ndf15)", p.evolver);
   CLPP_CHECK(p.tight_coupling_approximation >= CLPP_TCA_FIRST_ORDER_MB &&
                  p.tight_coupling_approximation <= CLPP_TCA_COMPROMISE_CLASS,
              err, "your tight_coupling_approximation is set to %d, out of range defined in perturbations.h",

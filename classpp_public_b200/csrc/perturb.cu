@@ -89,6 +89,8 @@ struct PtParams {
   double eisw_lisw_split_z;
   int tp_t0, tp_t1, tp_t2, tp_p, tp_delta_m, tp_delta_cb, tp_phi_plus_psi;
   // shared-memory geometry (offsets in doubles into the CTA's dynamic shared memory)
+  int evolver;        // 0 = rk (Cash-Karp), 1 = ndf15
+  double rk_stepsize; // perturb_integration_stepsize (rk only)
   int force_generic;  // developer/test switch: integrate every interval with the generic shared-memory NDF
   int neq_max, np, nh_max, ldh;
   int o_mode, o_hubtmp, o_nw, o_i2l1, n_i2l1, o_tabc, ncol, o_vec, o_sinv, o_int;
@@ -2397,6 +2399,142 @@ __device__ __noinline__ bool ndf15_rsa(const PtParams& P, double t0, double tfin
   return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// evolver = rk: Cash-Karp Runge-Kutta 4(5) with time-scale limited stepping (the reference's non-default
+// evolver: tools/evolver_rkck.c:3-178, tools/dei_rkck.c:79-238, perturb_timescale_member
+// perturbations_module.cpp:5691-5826).  Explicit and therefore slow in the stiff phases; provided because it is
+// on the path, with the same driver logic: every sample time of the source grid is hit exactly.
+__device__ __noinline__ bool rk_interval(const PtParams& P, double t0, double tfinal) {
+  Mode& M = MODE(P);
+  const int n = M.L.neq, lane = threadIdx.x;
+  const double eps_tol = P.rtol;
+  const double SAFETY = 0.9, PGROW = -0.2, PSHRNK = -0.25, ERRCON = 1.89e-4, TINY = 1.0e-30;
+  const int MAXSTP = 100000;
+  double *ys = s_vec(P, V_Y), *y = s_vec(P, V_YNEW), *dydx = s_vec(P, V_F0), *ytemp = s_vec(P, V_PRED),
+         *ak2 = s_vec(P, V_PSI), *ak3 = s_vec(P, V_DIFKP1), *ak4 = s_vec(P, V_DEL), *ak5 = s_vec(P, V_INVWT);
+  double *ak6 = s_vec(P, V_DIF0), *yerr = s_vec(P, V_DIF0 + 1), *yscal = s_vec(P, V_DIF0 + 2);
+  const double* t_vec = M.C->tau;
+  const int tres = M.C->tau_size;
+  int next = M.next;
+  while (next < tres && __ldg(t_vec + next) < t0) next++;
+  double x1 = t0;
+  while ((x1 < tfinal) && (next < tres)) {
+    // perturb_timescale: min(tau_h, tau_k [unless rsa without ncdm], tau_c [when tight coupling is off])
+    env_at(P, x1, true, 0);
+    double timescale = 1. / (M.e.a * M.e.H);
+    if (!M.ap.rsa_on || P.has_ncdm) timescale = fmin(1. / M.k, timescale);
+    if (M.ap.tca_off) {
+      const double dkappa = s_pvt(P)[P.idkappa];
+      if (dkappa != 0.) timescale = fmin(1. / dkappa, timescale);
+    }
+    const double timestep = P.rk_stepsize * timescale;
+    if (fabs(timestep / x1) < P.hmin_allowed) { M.status = 2; return false; }
+    const double tnext = __ldg(t_vec + next);
+    double x2;
+    bool call_output = false;
+    if (x1 + 2. * timestep < tnext) x2 = x1 + timestep;
+    else { x2 = tnext; call_output = true; }
+    if (x2 > tfinal) { x2 = tfinal; call_output = false; }
+    // ---- generic_integrator(x1 -> x2) with adaptive Cash-Karp steps
+    {
+      double x = x1, h = x2 - x1;
+      const double hmin = x1 * P.hmin_allowed;
+#pragma unroll 1
+      for (int i = lane; i < n; i += 32) y[i] = ys[i];
+      __syncwarp();
+      bool reached = false;
+#pragma unroll 1
+      for (int nstp = 1; nstp <= MAXSTP; nstp++) {
+        env_at(P, x, true, 0);
+        rhs_apply(P, V_YNEW, V_F0, 0);
+        if (lane == 0) M.st.fevals++;
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) yscal[i] = fabs(y[i]) + fabs(dydx[i] * h) + TINY;
+        if ((x + h - x2) * (x + h - x1) > 0.0) h = x2 - x;
+        // rkqs: shrink the step until the embedded error estimate passes
+        double errmax, hnext;
+        for (;;) {
+          // rkck
+#pragma unroll 1
+          for (int i = lane; i < n; i += 32) ytemp[i] = y[i] + 0.2 * h * dydx[i];
+          __syncwarp();
+          env_at(P, x + 0.2 * h, true, 0); rhs_apply(P, V_PRED, V_PSI, 0);
+#pragma unroll 1
+          for (int i = lane; i < n; i += 32) ytemp[i] = y[i] + h * (3.0 / 40.0 * dydx[i] + 9.0 / 40.0 * ak2[i]);
+          __syncwarp();
+          env_at(P, x + 0.3 * h, true, 0); rhs_apply(P, V_PRED, V_DIFKP1, 0);
+#pragma unroll 1
+          for (int i = lane; i < n; i += 32) ytemp[i] = y[i] + h * (0.3 * dydx[i] - 0.9 * ak2[i] + 1.2 * ak3[i]);
+          __syncwarp();
+          env_at(P, x + 0.6 * h, true, 0); rhs_apply(P, V_PRED, V_DEL, 0);
+#pragma unroll 1
+          for (int i = lane; i < n; i += 32)
+            ytemp[i] = y[i] + h * (-11.0 / 54.0 * dydx[i] + 2.5 * ak2[i] - 70.0 / 27.0 * ak3[i] + 35.0 / 27.0 * ak4[i]);
+          __syncwarp();
+          env_at(P, x + 1.0 * h, true, 0); rhs_apply(P, V_PRED, V_INVWT, 0);
+#pragma unroll 1
+          for (int i = lane; i < n; i += 32)
+            ytemp[i] = y[i] + h * (1631.0 / 55296.0 * dydx[i] + 175.0 / 512.0 * ak2[i] + 575.0 / 13824.0 * ak3[i] +
+                                   44275.0 / 110592.0 * ak4[i] + 253.0 / 4096.0 * ak5[i]);
+          __syncwarp();
+          env_at(P, x + 0.875 * h, true, 0); rhs_apply(P, V_PRED, V_DIF0, 0);
+          if (lane == 0) M.st.fevals += 5;
+          double em = 0.0;
+#pragma unroll 1
+          for (int i = lane; i < n; i += 32) {
+            ytemp[i] = y[i] + h * (37.0 / 378.0 * dydx[i] + 250.0 / 621.0 * ak3[i] + 125.0 / 594.0 * ak4[i] + 512.0 / 1771.0 * ak6[i]);
+            const double ye = h * ((37.0 / 378.0 - 2825.0 / 27648.) * dydx[i] + (250.0 / 621.0 - 18575.0 / 48384.0) * ak3[i] +
+                                   (125.0 / 594.0 - 13525.0 / 55296.0) * ak4[i] - 277.00 / 14336.0 * ak5[i] +
+                                   (512.0 / 1771.0 - 0.25) * ak6[i]);
+            yerr[i] = ye;
+            em = fmax(em, fabs(ye / yscal[i]));
+          }
+          errmax = wmax(em) / eps_tol;
+          __syncwarp();
+          if (errmax <= 1.0) break;
+          if (lane == 0) M.st.failed++;
+          const double htemp = SAFETY * h * pow(errmax, PSHRNK);
+          h = (h >= 0.0 ? fmax(htemp, 0.1 * h) : fmin(htemp, 0.1 * h));
+          if (x + h == x) { M.status = 2; return false; }  // stepsize underflow
+        }
+        if (errmax > ERRCON) hnext = SAFETY * h * pow(errmax, PGROW);
+        else hnext = 5.0 * h;
+        x += h;
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) y[i] = ytemp[i];
+        __syncwarp();
+        if (lane == 0) M.st.steps++;
+        if ((x - x2) * (x2 - x1) >= 0.0) { reached = true; break; }
+        if (fabs(hnext / x1) <= hmin) { M.status = 2; return false; }
+        h = hnext;
+      }
+      if (!reached) { M.status = 9; return false; }  // too many steps within one sub-interval
+#pragma unroll 1
+      for (int i = lane; i < n; i += 32) ys[i] = y[i];
+      __syncwarp();
+    }
+    if (call_output) {
+      env_at(P, x2, true, 0);
+      rhs_apply(P, V_Y, V_F0, 0);
+      if (!M.ap.tca_off) M.tca_shear_last = M.m.tca_shear_g;
+      if (lane == 0) M.st.fevals++;
+      __syncwarp();
+      write_sources(P, x2, V_Y, V_F0, next);
+      next++;
+    }
+    x1 = x2;
+  }
+  // last call so that the environment and the TCA/RSA by-products are current at the end of the interval
+  env_at(P, x1, true, 0);
+  rhs_apply(P, V_Y, V_F0, 0);
+  if (!M.ap.tca_off) M.tca_shear_last = M.m.tca_shear_g;
+  if (lane == 0) M.st.fevals++;
+  __syncwarp();
+  M.next = next;
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // perturb_initial_conditions: adiabatic mode, synchronous gauge, flat space
 __device__ __noinline__ void initial_conditions(const PtParams& P, double tau) {
@@ -2725,7 +2863,8 @@ __global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid
     const long long c0 = clock64();
     const int s0 = M.st.steps;
     bool ok;
-    if (P.force_generic) ok = ndf15(P, M.limit[iv], M.limit[iv + 1]);
+    if (P.evolver == 0) ok = rk_interval(P, M.limit[iv], M.limit[iv + 1]);
+    else if (P.force_generic) ok = ndf15(P, M.limit[iv], M.limit[iv + 1]);
     else if (M.nch == 0 && apn.rsa_on && M.L.neq <= 8) ok = ndf15_rsa<8>(P, M.limit[iv], M.limit[iv + 1]);
     else if (M.nch == 0 && apn.rsa_on && M.L.neq <= 16) ok = ndf15_rsa<16>(P, M.limit[iv], M.limit[iv + 1]);
     else if (M.nch == 0 && M.L.neq <= 32) ok = ndf15_hub(P, M.limit[iv], M.limit[iv + 1]);
@@ -2859,6 +2998,7 @@ static int fill_common(const clpp_ctx* c, PtParams& P, char* err) {
   P.l_max_g = pd.l_max_g; P.l_max_pol_g = pd.l_max_pol_g; P.l_max_ur = pd.l_max_ur; P.l_max_ncdm = pd.l_max_ncdm;
   P.tol_ncdm_initial_w = pd.tol_ncdm_initial_w; P.tol_tau_approx = pd.tol_tau_approx;
   P.rtol = pd.tol_perturb_integration; P.hmin_allowed = pd.smallest_allowed_variation;
+  P.evolver = pd.evolver; P.rk_stepsize = pd.perturb_integration_stepsize;
   P.curvature_ini = pd.curvature_ini; P.three_ceff2_ur = pd.three_ceff2_ur; P.three_cvis2_ur = pd.three_cvis2_ur;
   P.switch_sw = pd.switch_sw; P.switch_eisw = pd.switch_eisw; P.switch_lisw = pd.switch_lisw;
   P.switch_dop = pd.switch_dop; P.switch_pol = pd.switch_pol; P.eisw_lisw_split_z = pd.eisw_lisw_split_z;
@@ -2990,7 +3130,7 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   // low-priority stream each (generic kernel -> tail kernel), so that the tails of a chunk overlap the
   // generic phases of the next ones instead of all waiting for the last generic CTA.
   const bool force_generic = getenv("CLPP_GENERIC_ONLY") != nullptr;
-  const bool use_tail = getenv("CLPP_NO_TAIL") == nullptr && !force_generic;
+  const bool use_tail = getenv("CLPP_NO_TAIL") == nullptr && !force_generic && c0->pd.evolver == 1;
   int n_long = 0;
   if (use_tail && n_modes > 0) {
     const double kcut = 0.1 * cost[perm[0]];
@@ -3112,6 +3252,7 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
                          : s == 5 ? "your choice of initial time for integrating wavenumbers is inappropriate: ncdm species not ultra-relativistic"
                          : s == 6 ? "an approximation flag goes backward in time, this cannot be handled"
                          : s == 7 ? "you switch several approximations at the same time, this cannot be handled"
+                         : s == 9 ? "Too many integration steps needed within one interval (rk evolver), the system of equations is probably buggy or featuring a discontinuity"
                          : s == 8 ? "scalar initial conditions assume tight coupling on and all other approximations off"
                                   : "unknown device error";
         return clpp_fail(err, "perturb_solve failed for k=%e (index %d, cosmology %d of the batch): %s", c->k[ik], ik, b, what);

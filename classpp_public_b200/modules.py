@@ -91,6 +91,7 @@ class Inputs:
                     "has_pk_matter", "has_nl_corrections_based_on_delta_m", "gauge", "l_scalar_max",
                     "k_max_for_pk", "z_max_pk", "switch_sw", "switch_eisw", "switch_lisw", "switch_dop",
                     "switch_pol", "eisw_lisw_split_z", "three_ceff2_ur", "three_cvis2_ur"}
+        self.meta.setdefault("pr.perturb_integration_stepsize", 0.5)  # precisions.h:226 (fixtures older than the rk evolver)
         return _fill(d, self.meta, lambda n: ("pt." if n in pt_names else "pr.") + n)
 
     def transfer_desc(self):

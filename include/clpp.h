@@ -119,8 +119,9 @@ typedef struct clpp_perturb_desc {
   double ur_fluid_trigger_tau_over_tau_k;
   int ncdm_fluid_approximation; /* enum ncdmfa_method; 2 = ncdmfa_CLASS */
   double ncdm_fluid_trigger_tau_over_tau_k;
-  int evolver; /* 1 = ndf15 (only one supported on device) */
+  int evolver; /* enum evolver_type: 0 = rk (Cash-Karp RK45, tools/evolver_rkck.c), 1 = ndf15 (default) */
   double curvature_ini;
+  double perturb_integration_stepsize; /* rk only: step = this * min(tau_h, tau_k, tau_c) (precisions.h:226) */
 } clpp_perturb_desc;
 
 /* sizes and indices that the reference publishes as PerturbationsModule members */

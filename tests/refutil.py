@@ -18,6 +18,7 @@ start_sources_at_tau_c_over_tau_h tight_coupling_approximation l_max_g l_max_pol
 tol_ncdm_initial_w tol_tau_approx tol_perturb_integration perturb_sampling_stepsize smallest_allowed_variation
 radiation_streaming_approximation radiation_streaming_trigger_tau_over_tau_k ur_fluid_approximation
 ur_fluid_trigger_tau_over_tau_k ncdm_fluid_approximation ncdm_fluid_trigger_tau_over_tau_k evolver curvature_ini
+perturb_integration_stepsize
 l_logstep l_linstep hyper_x_min hyper_sampling_flat hyper_phi_min_abs q_linstep q_logstep_spline q_logstep_open
 transfer_neglect_delta_k_S_t0 transfer_neglect_delta_k_S_t1 transfer_neglect_delta_k_S_t2
 transfer_neglect_delta_k_S_e transfer_neglect_late_source l_switch_limber""".split()

@@ -236,6 +236,21 @@ def test_sweep_of_different_cosmologies_in_one_batch_vs_live_reference():
         r.close()
 
 
+def test_rk_evolver_vs_ndf15_golden(golden):
+    """evolver = rk: the device Cash-Karp integrator.  The unmodified reference SEGFAULTS with
+    `evolver = 0` in this container (oracle run), so this row has no reference output to pin against:
+    the explicit integrator is checked against the reference's ndf15 result for the same inputs instead (both
+    integrate the same equations to tol_perturb_integration)."""
+    from classpp_public_b200.modules import Inputs
+    base = golden("lcdm_coarse")
+    inp = Inputs(dict(base.meta, **{"pr.evolver": 0}), base.arrays)
+    ctx, pt, tr, sp = run_pipeline(inp)
+    check_cl(sp, base.arrays["ref.cl"], rtol=5e-4)  # coarse grids, see lcdm_coarse
+    ks = pt.kstat_
+    assert np.all(ks[:, 7] == 0) and ks[:, 3].sum() == 0 and ks[:, 4].sum() == 0  # explicit: no Jacobian, no LU
+    ctx.close()
+
+
 def test_k_range_partition_equals_full_solve(golden):
     """Multi-GPU partition property: integrating two k ranges separately fills the same source table."""
     inp = golden("lcdm_coarse")
