@@ -8,7 +8,7 @@
 
 #include "clpp_internal.h"
 
-#define CLPP_PT_MAX_CHUNKS 8
+#define CLPP_PT_MAX_CHUNKS 16
 
 struct clpp_ctx::Dev {
   cudaStream_t stream = nullptr, stream2 = nullptr, stream_hi = nullptr;

@@ -3124,7 +3124,7 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   std::vector<int> perm(n_modes);
   for (int i = 0; i < n_modes; i++) perm[i] = i;
   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-  // Launch groups.  Group L: the modes with long radiation-streaming tails (top decade in k), high-priority
+  // Launch groups.  Group L: the modes with long radiation-streaming tails (k >= 3 % of k_max: measured optimum), high-priority
   // stream, issued first: they finish their early phases quickly and run their tails -- the serial critical
   // path -- while the bulk is still in the generic kernel.  The bulk is dealt round-robin into chunks, one
   // low-priority stream each (generic kernel -> tail kernel), so that the tails of a chunk overlap the
@@ -3133,12 +3133,14 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   const bool use_tail = getenv("CLPP_NO_TAIL") == nullptr && !force_generic && c0->pd.evolver == 1;
   int n_long = 0;
   if (use_tail && n_modes > 0) {
-    const double kcut = 0.1 * cost[perm[0]];
+    const double kcut_frac = getenv("CLPP_KCUT") ? atof(getenv("CLPP_KCUT")) : 0.03;  // developer knob
+    const double kcut = kcut_frac * cost[perm[0]];
     while (n_long < n_modes && cost[perm[n_long]] >= kcut) n_long++;
     if (n_long == n_modes) n_long = 0;  // nothing to overlap with
   }
   const int n_bulk = n_modes - n_long;
-  const int n_chunks = use_tail ? std::max(1, std::min(PT_MAX_CHUNKS, n_bulk / 4000)) : 1;
+  const int chunk_modes = getenv("CLPP_CHUNK_MODES") ? atoi(getenv("CLPP_CHUNK_MODES")) : 4000;  // developer knob
+  const int n_chunks = use_tail ? std::max(1, std::min(PT_MAX_CHUNKS, n_bulk / std::max(chunk_modes, 1))) : 1;
   std::vector<int2> sorted(n_modes);
   std::vector<int> chunk_first(n_chunks + 1, n_long);
   for (int i = 0; i < n_long; i++) sorted[i] = modes[perm[i]];
