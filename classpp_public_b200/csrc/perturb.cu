@@ -2865,9 +2865,7 @@ __global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid
     bool ok;
     if (P.evolver == 0) ok = rk_interval(P, M.limit[iv], M.limit[iv + 1]);
     else if (P.force_generic) ok = ndf15(P, M.limit[iv], M.limit[iv + 1]);
-    else if (M.nch == 0 && apn.rsa_on && M.L.neq <= 8) ok = ndf15_rsa<8>(P, M.limit[iv], M.limit[iv + 1]);
-    else if (M.nch == 0 && apn.rsa_on && M.L.neq <= 16) ok = ndf15_rsa<16>(P, M.limit[iv], M.limit[iv + 1]);
-    else if (M.nch == 0 && M.L.neq <= 32) ok = ndf15_hub(P, M.limit[iv], M.limit[iv + 1]);
+    else if (M.nch == 0 && M.L.neq <= 32) ok = ndf15_hub(P, M.limit[iv], M.limit[iv + 1]);  // (the register-only RSA integrator lives in the tail kernel)
     else ok = ndf15(P, M.limit[iv], M.limit[iv + 1]);
     __syncwarp();
     if (lane == 0) {
