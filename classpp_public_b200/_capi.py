@@ -136,7 +136,7 @@ SYMBOLS = [
     "clpp_transfer_grids", "clpp_transfer_compute", "clpp_transfer_get_l", "clpp_transfer_get_q",
     "clpp_transfer_get_transfer", "clpp_transfer_set_transfer", "clpp_transfer_device_transfer",
     "clpp_transfer_get_bessel",
-    "clpp_spectra_compute", "clpp_spectra_compute_range", "clpp_spectra_cl_at_l", "clpp_spectra_cl_output",
+    "clpp_spectra_compute", "clpp_spectra_compute_range", "clpp_spectra_cl_at_l", "clpp_spectra_cl_output", "clpp_pk_linear",
 ]
 
 _lib = None
@@ -185,6 +185,7 @@ def lib():
         L.clpp_transfer_get_bessel.argtypes = [vp, dp, dp, dp, dp, cp]
         L.clpp_spectra_compute.argtypes = [vp, dp, P(SpectraInfo), dp, cp]
         L.clpp_spectra_compute_range.argtypes = [vp, dp, C.c_int, C.c_int, P(SpectraInfo), dp, cp]
+        L.clpp_pk_linear.argtypes = [vp, dp, C.c_int, C.c_int, dp, cp]
         L.clpp_spectra_cl_at_l.argtypes = [vp, C.c_double, dp, cp]
         L.clpp_spectra_cl_output.argtypes = [vp, C.c_int, dp, cp]
         _lib = L

@@ -17,6 +17,7 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
 int clpp_dev_spectra(clpp_ctx* c, const double* primordial_pk, int q_begin, int q_end, clpp_spectra_info* info,
                      double* cl_out, char* err);
 int clpp_host_cl_at_l(const clpp_ctx* c, double l, double* cl_tot, char* err);
+int clpp_dev_pk_linear(clpp_ctx* c, const double* primordial_pk, int index_tau, int cb, double* pk_out, char* err);
 int clpp_dev_get_bessel(clpp_ctx* c, double* x, double* phi, double* dphi, double* chi, char* err);
 
 template <typename T>
@@ -384,6 +385,14 @@ int clpp_spectra_compute_range(clpp_ctx* c, const double* primordial_pk, int q_b
   CLPP_CHECK(0 <= q_begin && q_begin <= q_end && q_end <= c->tinfo.q_size, err, "bad q range [%d,%d)", q_begin, q_end);
   cudaSetDevice(c->device);
   return clpp_dev_spectra(c, primordial_pk, q_begin, q_end, info, cl_out, err);
+}
+
+int clpp_pk_linear(clpp_ctx* c, const double* primordial_pk, int index_tau, int cb, double* pk_out, char* err) {
+  CLPP_CHECK(c && primordial_pk && pk_out, err, "null argument");
+  CLPP_CHECK(c->dev, err, "this context has no CUDA device: the B200 path has no CPU fallback");
+  CLPP_CHECK(c->has_sources, err, "no sources: run clpp_perturb_solve first");
+  cudaSetDevice(c->device);
+  return clpp_dev_pk_linear(c, primordial_pk, index_tau, cb, pk_out, err);
 }
 
 int clpp_spectra_cl_at_l(const clpp_ctx* c, double l, double* cl_tot, char* err) {

@@ -235,3 +235,37 @@ int clpp_host_cl_at_l(const clpp_ctx* c, double l, double* cl_tot, char* err) {
   }
   return CLPP_SUCCESS;
 }
+
+
+// =============================================================================================
+// Linear matter power spectrum P(k) = 2 pi^2 / k^3 P_R(k) delta_m(k, tau)^2 on the perturbation k grid
+// (NonlinearModule::nonlinear_pk_linear, nonlinear_module.cpp:1886-2024, adiabatic mode): SURVEY 8f row 1.
+// Reads delta_m (or delta_cb) straight from the device-resident source table [tp][k][tau].
+// =============================================================================================
+__global__ void pk_linear_kernel(int nk, int nt, int index_tau, const double* __restrict__ k, const double* __restrict__ src_tp,
+                                 const double* __restrict__ primordial, double* __restrict__ pk) {
+  const int ik = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ik >= nk) return;
+  const double s = src_tp[(size_t)ik * nt + index_tau];
+  const double kk = k[ik];
+  pk[ik] = 2. * CLPP_PI * CLPP_PI / (kk * kk * kk) * s * s * primordial[ik];
+}
+
+int clpp_dev_pk_linear(clpp_ctx* c, const double* primordial_pk, int index_tau, int cb, double* pk_out, char* err) {
+  clpp_ctx::Dev* d = c->dev;
+  const clpp_perturb_info& I = c->pinfo;
+  const int nk = I.k_size, nt = I.tau_size;
+  const int tp = cb ? I.index_tp_delta_cb : I.index_tp_delta_m;
+  CLPP_CHECK(tp >= 0, err, "P(k) is set neither to total matter nor to cold dark matter + baryons: no %s source", cb ? "delta_cb" : "delta_m");
+  if (index_tau < 0) index_tau = nt - 1;
+  CLPP_CHECK(index_tau < nt, err, "index_tau=%d out of range [0,%d)", index_tau, nt);
+  if (clpp_dev_reserve(d, &d->pk, (size_t)2 * nk, err)) return CLPP_FAILURE;
+  CLPP_CUDA(cudaMemcpyAsync(d->pk, primordial_pk, nk * sizeof(double), cudaMemcpyHostToDevice, d->stream), err);
+  pk_linear_kernel<<<(nk + 127) / 128, 128, 0, d->stream>>>(nk, nt, index_tau, d->k, d->sources + (size_t)tp * nk * nt, d->pk,
+                                                           d->pk + nk);
+  c->launches++;
+  CLPP_CUDA(cudaGetLastError(), err);
+  CLPP_CUDA(cudaMemcpyAsync(pk_out, d->pk + nk, nk * sizeof(double), cudaMemcpyDeviceToHost, d->stream), err);
+  CLPP_CUDA(cudaStreamSynchronize(d->stream), err);
+  return CLPP_SUCCESS;
+}

@@ -274,6 +274,16 @@ class PerturbationsModule:
         self._sources = None
         return self
 
+    def pk_linear(self, primordial_pk, index_tau=-1, cb=False):
+        """Linear P(k) [Mpc^3] on the k grid of this module at sample index_tau (default: today), from delta_m
+        (cb: delta_cb) and the primordial spectrum P_R(k_i) (reference: nonlinear_pk_linear, nonlinear_module.cpp:1886)."""
+        pr = np.ascontiguousarray(primordial_pk, dtype=np.float64)
+        assert len(pr) == self.info.k_size
+        out = np.empty(self.info.k_size)
+        self.ctx.check(self.ctx._lib.clpp_pk_linear(self.ctx.handle, capi.dptr(pr), int(index_tau), int(bool(cb)),
+                                                    capi.dptr(out), self.ctx.err))
+        return out
+
     @property
     def sources_(self):
         """sources_[index_md][index_ic*tp_size+index_tp][index_tau*k_size+index_k] (perturbations.h:20)."""

@@ -229,6 +229,13 @@ int clpp_spectra_compute(clpp_ctx* ctx, const double* primordial_pk, clpp_spectr
 int clpp_spectra_compute_range(clpp_ctx* ctx, const double* primordial_pk, int q_begin, int q_end,
                                clpp_spectra_info* info, double* cl_out, char* err);
 
+/* ---- P(k): first "next" row of SURVEY 8f ---------------------------------------------------- */
+/* replaces NonlinearModule::nonlinear_pk_linear (nonlinear_module.cpp:1886-2024, adiabatic mode):
+ * pk_out[i] = 2 pi^2 / k_i^3 * primordial_pk[i] * delta(k_i, tau)^2 on the perturbation k grid, read from the
+ * device-resident sources. primordial_pk[k_size] = P_R(k_i) (primordial_spectrum_at_k, linear);
+ * index_tau < 0: today (last sample); cb = 0: total matter (delta_m), 1: cdm+baryons (delta_cb). */
+int clpp_pk_linear(clpp_ctx* ctx, const double* primordial_pk, int index_tau, int cb, double* pk_out, char* err);
+
 /* replaces SpectraModule::spectra_cl_at_l (spectra_module.cpp:220-264, one mode / one initial condition):
  * cubic spline in l through the table of clpp_spectra_compute, zero above l_scalar_max. cl_tot[ct_size]. */
 int clpp_spectra_cl_at_l(const clpp_ctx* ctx, double l, double* cl_tot, char* err);

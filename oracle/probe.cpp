@@ -274,6 +274,35 @@ long rp_get(void* h, const char* cname, double* out, long cap) {
     }
     return put(pk.data(), t.q_size_, out, cap);
   }
+  // ---- primordial spectrum on the perturbation k grid, and the reference's linear P(k, z=0) on that grid ----
+  if (name == "pm.pk_at_pt_k") {
+    const PrimordialModule& pm = *c.GetPrimordialModule();
+    const PerturbationsModule& m = *c.GetPerturbationsModule();
+    const int md = m.index_md_scalars_;
+    std::vector<double> pk(m.k_size_[md]);
+    for (int i = 0; i < m.k_size_[md]; i++) {
+      double v[8];
+      pm.primordial_spectrum_at_k(md, linear, m.k_[md][i], v);
+      pk[i] = v[0];
+    }
+    return put(pk.data(), m.k_size_[md], out, cap);
+  }
+  if (name == "nl.pk_lin_m_at_pt_k" || name == "nl.pk_lin_cb_at_pt_k") {
+    const NonlinearModule& n = *c.GetNonlinearModule();
+    const PerturbationsModule& m = *c.GetPerturbationsModule();
+    const int md = m.index_md_scalars_;
+    const int nk = m.k_size_[md];
+    // (nonlinear_pks_at_kvec_and_zvec dereferences the cb table even without cb: use the per-spectrum accessor;
+    //  the module's k grid starts with the perturbation grid, nonlinear_get_k_list)
+    const bool cb = (name == "nl.pk_lin_cb_at_pt_k");
+    if (cb && !n.has_pk_cb_) return 0;
+    if (!cb && !n.has_pk_m_) return 0;
+    std::vector<double> pk(n.k_size_);
+    if (n.nonlinear_pk_at_z(linear, pk_linear, 0., cb ? n.index_pk_cb_ : n.index_pk_m_, pk.data(), nullptr) != 0) return -1;
+    for (int i = 0; i < nk; i++)
+      if (fabs(exp(n.ln_k_[i]) / m.k_[md][i] - 1.) > 1e-12) return -1;
+    return put(pk.data(), nk, out, cap);
+  }
   // ---- nonlinear corrections seen by the transfer stage (transfer_module.cpp:559-590) ----
   if (name.rfind("nl.", 0) == 0) {
     const NonlinearModule& n = *c.GetNonlinearModule();

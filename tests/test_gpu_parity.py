@@ -251,6 +251,29 @@ def test_rk_evolver_vs_ndf15_golden(golden):
     ctx.close()
 
 
+def test_linear_matter_power_spectrum_vs_live_reference(reference):
+    """P(k) (north star: within 1e-4 of the reference): 2 pi^2/k^3 P_R(k) delta_m^2 from the device-resident sources
+    against NonlinearModule's linear P(k, z=0) at the nodes of the perturbation k grid."""
+    if reference is None:
+        pytest.skip("oracle/_ref not loadable on this box")
+    from refutil import inputs_from_reference
+    for name in ("lcdm_coarse", "ncdm3_deg"):
+        ref = reference(name, "lensing")
+        inp = inputs_from_reference(ref)
+        ctx = M.Context(0)
+        bg = M.BackgroundModule(inp, ctx)
+        th = M.ThermodynamicsModule(inp, bg)
+        pt = M.PerturbationsModule(inp, bg, th)
+        pr = ref.get("pm.pk_at_pt_k")
+        pk = pt.pk_linear(pr)
+        rpk = ref.get("nl.pk_lin_m_at_pt_k")
+        assert np.max(np.abs(pk / rpk - 1.0)) < 1e-4, name
+        if pt.info.index_tp_delta_cb >= 0:
+            rcb = ref.get("nl.pk_lin_cb_at_pt_k")
+            assert np.max(np.abs(pt.pk_linear(pr, cb=True) / rcb - 1.0)) < 1e-4, name
+        ctx.close()
+
+
 def test_k_range_partition_equals_full_solve(golden):
     """Multi-GPU partition property: integrating two k ranges separately fills the same source table."""
     inp = golden("lcdm_coarse")
