@@ -118,6 +118,12 @@ class TransferInfo(C.Structure):
     """)
 
 
+class HalofitDesc(C.Structure):
+    _fields_ = _fields("""
+    double: halofit_min_k_nonlinear, halofit_k_per_decade, halofit_sigma_precision, halofit_tol_sigma
+    """)
+
+
 class SpectraInfo(C.Structure):
     _fields_ = _fields("""
     int: ct_size, l_size
@@ -136,7 +142,7 @@ SYMBOLS = [
     "clpp_transfer_grids", "clpp_transfer_compute", "clpp_transfer_get_l", "clpp_transfer_get_q",
     "clpp_transfer_get_transfer", "clpp_transfer_set_transfer", "clpp_transfer_device_transfer",
     "clpp_transfer_get_bessel",
-    "clpp_spectra_compute", "clpp_spectra_compute_range", "clpp_spectra_cl_at_l", "clpp_spectra_cl_output", "clpp_pk_linear",
+    "clpp_spectra_compute", "clpp_spectra_compute_range", "clpp_spectra_cl_at_l", "clpp_spectra_cl_output", "clpp_pk_linear", "clpp_nonlinear_halofit",
 ]
 
 _lib = None
@@ -186,6 +192,7 @@ def lib():
         L.clpp_spectra_compute.argtypes = [vp, dp, P(SpectraInfo), dp, cp]
         L.clpp_spectra_compute_range.argtypes = [vp, dp, C.c_int, C.c_int, P(SpectraInfo), dp, cp]
         L.clpp_pk_linear.argtypes = [vp, dp, C.c_int, C.c_int, dp, cp]
+        L.clpp_nonlinear_halofit.argtypes = [vp, P(HalofitDesc), dp, dp, ip, cp]
         L.clpp_spectra_cl_at_l.argtypes = [vp, C.c_double, dp, cp]
         L.clpp_spectra_cl_output.argtypes = [vp, C.c_int, dp, cp]
         _lib = L

@@ -17,6 +17,8 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
 int clpp_dev_spectra(clpp_ctx* c, const double* primordial_pk, int q_begin, int q_end, clpp_spectra_info* info,
                      double* cl_out, char* err);
 int clpp_host_cl_at_l(const clpp_ctx* c, double l, double* cl_tot, char* err);
+int clpp_dev_halofit(clpp_ctx* c, const clpp_halofit_desc* hd, const double* primordial_pk, double* nl_corr_out,
+                     int* index_tau_min_nl, char* err);
 int clpp_dev_pk_linear(clpp_ctx* c, const double* primordial_pk, int index_tau, int cb, double* pk_out, char* err);
 int clpp_dev_get_bessel(clpp_ctx* c, double* x, double* phi, double* dphi, double* chi, char* err);
 
@@ -72,7 +74,7 @@ void clpp_ctx_destroy(clpp_ctx* c) {
     void* ptrs[] = {d->bg_tau, d->bg_y, d->bg_dd, d->th_z, d->th_y, d->th_dd, d->k, d->tau, d->sources, d->kstat,
                     d->k_order, d->queue_head, d->jac_scratch, d->q, d->kq, d->l, d->bessel_x, d->bessel_phi,
                     d->bessel_dphi, d->chi_at_phimin, d->src_tr, d->src_ddk, d->nl_corr, d->transfer, d->tr_counters,
-                    d->pk, d->wq, d->cl, d->ncdm, d->pt_cosmo, d->pt_modes, d->spline_u, d->bessel_scale, d->pt_tail};
+                    d->pk, d->wq, d->cl, d->ncdm, d->pt_cosmo, d->pt_modes, d->spline_u, d->bessel_scale, d->pt_tail, d->nl_corr2, d->hf_flags};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     for (int i = 0; i < 6; i++)
@@ -393,6 +395,15 @@ int clpp_pk_linear(clpp_ctx* c, const double* primordial_pk, int index_tau, int 
   CLPP_CHECK(c->has_sources, err, "no sources: run clpp_perturb_solve first");
   cudaSetDevice(c->device);
   return clpp_dev_pk_linear(c, primordial_pk, index_tau, cb, pk_out, err);
+}
+
+int clpp_nonlinear_halofit(clpp_ctx* c, const clpp_halofit_desc* desc, const double* primordial_pk, double* nl_corr_out,
+                           int* index_tau_min_nl, char* err) {
+  CLPP_CHECK(c && desc && primordial_pk, err, "null argument");
+  CLPP_CHECK(c->dev, err, "this context has no CUDA device: the B200 path has no CPU fallback");
+  CLPP_CHECK(c->has_sources, err, "no sources: run clpp_perturb_solve first");
+  cudaSetDevice(c->device);
+  return clpp_dev_halofit(c, desc, primordial_pk, nl_corr_out, index_tau_min_nl, err);
 }
 
 int clpp_spectra_cl_at_l(const clpp_ctx* c, double l, double* cl_tot, char* err) {

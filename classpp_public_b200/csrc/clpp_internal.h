@@ -90,6 +90,7 @@ struct clpp_ctx {
 
   // --- stage 2
   bool has_tgrids = false, has_transfer = false;
+  bool nl_dev_valid = false;  // a device-resident halofit correction matches the current sources
   clpp_transfer_desc td{};
   clpp_transfer_info tinfo{};
   std::vector<int> l, l_size_tt;

@@ -46,6 +46,9 @@ struct clpp_ctx::Dev {
   double* src_tr = nullptr;   // sources seen by the transfer stage (after nl correction) [tp][k][tau]
   double* src_ddk = nullptr;  // d2S/dk2 for the cubic spline in k, same layout
   double* nl_corr = nullptr;
+  double* nl_corr2 = nullptr;  // halofit on the device: R_NL [spec][k][tau] (spec 0 = total matter)
+  int* hf_flags = nullptr;
+  double t_halofit_ms = 0.;
   double* transfer = nullptr;  // [tt][l][q], q fastest (= reference layout)
   size_t transfer_count = 0;
   unsigned long long* tr_counters = nullptr;

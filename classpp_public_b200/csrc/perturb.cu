@@ -3259,6 +3259,7 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
       }
     }
     c->has_sources = true;
+    c->nl_dev_valid = false;
   }
   return CLPP_SUCCESS;
 }

@@ -477,7 +477,13 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
   if (dev_alloc(&d->src_tr, nsrc, err) || dev_alloc(&d->src_ddk, nsrc, err)) return CLPP_FAILURE;
   CLPP_CUDA(cudaMemcpyAsync(d->src_tr, d->sources, nsrc * sizeof(double), cudaMemcpyDeviceToDevice, st), err);
   std::vector<double> corr_t;
-  if (nl_corr_density && PI.index_tp_phi_plus_psi >= 0) {
+  if (!nl_corr_density && c->nl_dev_valid && d->nl_corr2 && PI.index_tp_phi_plus_psi >= 0) {
+    // halofit ran on the device (clpp_nonlinear_halofit): total-matter correction, already in the [k][tau] layout
+    const size_t n = (size_t)nk * nt;
+    nl_correction_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d->src_tr + (size_t)PI.index_tp_phi_plus_psi * n,
+                                                                     d->nl_corr2);
+    c->launches++;
+  } else if (nl_corr_density && PI.index_tp_phi_plus_psi >= 0) {
     // reference layout [tau][k] -> device layout [k][tau]
     corr_t.resize((size_t)nk * nt);
     for (int it = 0; it < nt; it++)

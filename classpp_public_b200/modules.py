@@ -417,6 +417,34 @@ class SpectraModule:
                 if getattr(self, "has_%s_" % n)}
 
 
+class NonlinearModule:
+    """NonlinearModule(input, background, perturbations, primordial) (reference: source/nonlinear_module.h) for
+    `non linear = halofit`: R_NL(k,tau) = sqrt(P_NL/P_L) computed ON THE DEVICE from the resident delta_m sources
+    (clpp_nonlinear_halofit).  The table stays on the device for the next TransferModule; `nl_corr_density_`
+    fetches it in the reference layout [index_pk_m][tau*k_size+k]."""
+
+    on_device = True
+
+    def __init__(self, inputs, background_module, perturbations_module, primordial_module, fetch=False):
+        ctx = perturbations_module.ctx
+        self.ctx, self.info = ctx, perturbations_module.info
+        m = inputs.meta
+        d = capi.HalofitDesc()
+        d.halofit_min_k_nonlinear = float(m.get("pr.halofit_min_k_nonlinear", 1.0e-4))   # precisions.h:432
+        d.halofit_k_per_decade = float(m.get("pr.halofit_k_per_decade", 80.0))            # :436
+        d.halofit_sigma_precision = float(m.get("pr.halofit_sigma_precision", 0.05))      # :441
+        d.halofit_tol_sigma = float(m.get("pr.halofit_tol_sigma", 1.0e-6))                # :449
+        pk = np.ascontiguousarray(primordial_module.pk_at_k(perturbations_module.k_[0]), dtype=np.float64)
+        i = self.info
+        out = np.empty(i.tau_size * i.k_size) if fetch else None
+        imin = C.c_int()
+        ctx.check(ctx._lib.clpp_nonlinear_halofit(ctx.handle, C.byref(d), capi.dptr(pk), capi.dptr(out), C.byref(imin),
+                                                  ctx.err))
+        self.index_tau_min_nl_ = imin.value
+        self.nl_corr_density_ = [out] if fetch else None
+        self.nl_corr_density_m = None  # TransferModule: None -> the device-resident table is used
+
+
 class AnalyticPrimordial:
     """P_R(k) = A_s (k/k_pivot)^(n_s-1+...) -- stand-in for PrimordialModule (out of scope); tests use the
     tabulated values of the reference instead (Inputs.arrays['pm.pk_at_transfer_k'])."""

@@ -236,6 +236,17 @@ int clpp_spectra_compute_range(clpp_ctx* ctx, const double* primordial_pk, int q
  * index_tau < 0: today (last sample); cb = 0: total matter (delta_m), 1: cdm+baryons (delta_cb). */
 int clpp_pk_linear(clpp_ctx* ctx, const double* primordial_pk, int index_tau, int cb, double* pk_out, char* err);
 
+/* replaces the halofit branch of NonlinearModule::nonlinear_init (nonlinear_module.cpp:1228-1420) with
+ * nonlinear_halofit (:2291-2726): R_NL(k,tau) = sqrt(P_NL/P_L) from the device-resident delta_m / delta_cb sources.
+ * The result stays on the device and is applied by the next clpp_transfer_compute called with nl_corr_density = NULL
+ * (it is invalidated by a new clpp_perturb_solve).  nl_corr_out: NULL, or [tau_size*k_size] in the reference layout
+ * nl_corr_density_[index_pk_m][tau*k_size+k]; index_tau_min_nl: NULL or the reference's index_tau_min_nl_. */
+typedef struct clpp_halofit_desc {
+  double halofit_min_k_nonlinear, halofit_k_per_decade, halofit_sigma_precision, halofit_tol_sigma; /* precisions.h:432-449 */
+} clpp_halofit_desc;
+int clpp_nonlinear_halofit(clpp_ctx* ctx, const clpp_halofit_desc* desc, const double* primordial_pk /*[k_size]*/,
+                           double* nl_corr_out, int* index_tau_min_nl, char* err);
+
 /* replaces SpectraModule::spectra_cl_at_l (spectra_module.cpp:220-264, one mode / one initial condition):
  * cubic spline in l through the table of clpp_spectra_compute, zero above l_scalar_max. cl_tot[ct_size]. */
 int clpp_spectra_cl_at_l(const clpp_ctx* ctx, double l, double* cl_tot, char* err);

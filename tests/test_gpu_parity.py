@@ -274,6 +274,30 @@ def test_linear_matter_power_spectrum_vs_live_reference(reference):
         ctx.close()
 
 
+def test_halofit_on_device_vs_golden(golden):
+    """`non linear = halofit` (BASELINE config 2) with the NonlinearModule step on the device: the
+    correction table R_NL(k,tau) against the reference's nl_corr_density_, and the C_l of the fully device-resident
+    pipeline perturbations -> halofit -> transfer -> spectra against the reference's."""
+    from classpp_public_b200.configs import CONFIGS
+    inp = golden("planck18")
+    a = inp.arrays
+    par = CONFIGS["planck18"]
+    prim_k = M.AnalyticPrimordial(par["A_s"], par["n_s"])  # the reference's analytic P_R(k), k_pivot = 0.05/Mpc
+    ctx = M.Context(0)
+    bg = M.BackgroundModule(inp, ctx)
+    th = M.ThermodynamicsModule(inp, bg)
+    pt = M.PerturbationsModule(inp, bg, th)
+    nl = M.NonlinearModule(inp, bg, pt, prim_k, fetch=True)
+    mine = nl.nl_corr_density_[0].reshape(pt.info.tau_size, pt.info.k_size)
+    ref = a["nl.nl_corr_density_m"].reshape(pt.info.tau_size, pt.info.k_size)
+    assert np.array_equal(mine == 1.0, ref == 1.0)  # same "not computable at this redshift" region, same linear k range
+    assert np.max(np.abs(mine / ref - 1.0)) < 1e-4
+    tr = M.TransferModule(inp, bg, th, pt, nl)  # correction applied from the device-resident table
+    sp = M.SpectraModule(inp, pt, M.TabulatedPrimordial(a["pm.pk_at_transfer_k"]), nl, tr)
+    check_cl(sp, a["ref.cl"])
+    ctx.close()
+
+
 def test_k_range_partition_equals_full_solve(golden):
     """Multi-GPU partition property: integrating two k ranges separately fills the same source table."""
     inp = golden("lcdm_coarse")
