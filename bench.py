@@ -117,6 +117,11 @@ def run_gpu(args):
     a = inp.arrays
     pk = a["pm.pk_at_transfer_k"]
     nl = _NL(a["nl.nl_corr_density_m"]) if "nl.nl_corr_density_m" in a else None
+    # `non linear = halofit` (config 2): by default the halofit step runs on the device between stages 1 and 2
+    #  instead of taking the reference's correction table as an input
+    from classpp_public_b200.configs import CONFIGS
+    halofit_on_device = nl is not None and args.halofit == "device"
+    prim_k = M.AnalyticPrimordial(CONFIGS[args.config].get("A_s", 2.215e-9), CONFIGS[args.config].get("n_s", 0.9619))
     B = args.batch
 
     # ---- device-resident inputs: one context (own stream) per cosmology of the batch
@@ -149,8 +154,11 @@ def run_gpu(args):
         M.PerturbationsModule.solve_batch(pts)
 
         def back(b):
-            tr = M.TransferModule(x, mods[b][0], mods[b][1], pts[b], n_)
-            sp = M.SpectraModule(x, pts[b], M.TabulatedPrimordial(p_), n_, tr)
+            nlb = n_
+            if halofit_on_device:  # NonlinearModule (halofit) on the device, from the resident delta_m sources
+                nlb = M.NonlinearModule(x, mods[b][0], pts[b], prim_k)
+            tr = M.TransferModule(x, mods[b][0], mods[b][1], pts[b], nlb)
+            sp = M.SpectraModule(x, pts[b], M.TabulatedPrimordial(p_), nlb, tr)
             out_bytes = sp.cl_[0].nbytes
             if fetch:  # device -> host: the public members downstream modules read (Nonlinear/Lensing/Output)
                 out_bytes += sum(s_.nbytes for s_ in pts[b].sources_[0])
@@ -173,7 +181,7 @@ def run_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t0 = time.perf_counter()
-    kms = {"perturb": 0.0, "k_spline": 0.0, "bessel": 0.0, "los": 0.0, "spectra": 0.0, "perturb_tail": 0.0}
+    kms = {"perturb": 0.0, "k_spline": 0.0, "bessel": 0.0, "los": 0.0, "spectra": 0.0, "perturb_tail": 0.0, "halofit": 0.0}
     for _ in range(args.steps):
         step()
         for c in ctxs:
@@ -258,6 +266,8 @@ def run_gpu(args):
                                 "1 ncdm species, halofit, l_max_scalars=2500, P_k_max_h/Mpc=1)") if args.config == "planck18"
                                else args.config,
                    "fixture": "tests/golden/%s.npz" % args.config, "batch_per_gpu": B,
+                   "halofit": ("on the device, inside the step (clpp_nonlinear_halofit)" if halofit_on_device else
+                               "correction table is an input" if nl is not None else "none"),
                    "k_modes": int(results[0][0].info.k_size), "tau_samples": int(results[0][0].info.tau_size),
                    "q_values": int(tr_info.q_size), "l_values": int(tr_info.l_size),
                    "parallelism": "independent cosmologies per GPU (replicas, no data-path collective); per GPU all k modes "
@@ -355,6 +365,8 @@ def main():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("CLPP_BENCH_BATCH", 128)),
                     help="cosmologies per GPU and per step (one batched perturbation launch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halofit", default="device", choices=["device", "input"],
+                    help="config with halofit: run it on the device (default) or take the reference's table as input")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -101,10 +101,10 @@ int clpp_ctx_get_stream(clpp_ctx* c, void** stream) {
   return CLPP_SUCCESS;
 }
 
-int clpp_ctx_get_kernel_ms(const clpp_ctx* c, double out[6]) {
+int clpp_ctx_get_kernel_ms(const clpp_ctx* c, double out[7]) {
   if (!c || !c->dev) return CLPP_FAILURE;
   out[0] = c->dev->t_perturb_ms; out[1] = c->dev->t_kspline_ms; out[2] = c->dev->t_bessel_ms;
-  out[3] = c->dev->t_los_ms; out[4] = c->dev->t_spectra_ms; out[5] = c->dev->t_perturb_tail_ms;
+  out[3] = c->dev->t_los_ms; out[4] = c->dev->t_spectra_ms; out[5] = c->dev->t_perturb_tail_ms; out[6] = c->dev->t_halofit_ms;
   return CLPP_SUCCESS;
 }
 

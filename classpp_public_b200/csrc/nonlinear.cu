@@ -65,7 +65,10 @@ __global__ void __launch_bounds__(32) halofit_kernel(const HfParams P) {
   double* pki = ki + ni;        // [ni]
   double* f = pki + ni;         // [ni]
   double* dd = f + ni;          // [ni]
-  double* u = dd + ni;          // [max(ni,nk)]
+  double* sgi = dd + ni;        // [ni] x-only spline coefficients of the integrand grid: sig,
+  double* pin = sgi + ni;       // [ni]   1/p,
+  double* cdd = pin + ni;       // [ni]   (sig-1)/p
+  double* u = cdd + ni;         // [max(ni,nk)]
   const int tp = spec == 0 ? P.tp_m : P.tp_cb;
   const double fnu = spec == 0 ? P.fnu_m : 0.;
   const double* src = P.sources + (size_t)tp * nk * nt;
@@ -125,6 +128,18 @@ __global__ void __launch_bounds__(32) halofit_kernel(const HfParams P) {
     pki[i] = exp(lp);
   }
   __syncwarp();
+  // the abscissae of the sigma(R) integrals never change: factor the tridiagonal matrix of their natural spline once
+  if (lane == 0) {
+    cdd[0] = 0.;
+    for (int i = 1; i < ni - 1; i++) {
+      const double sig = (ki[i] - ki[i - 1]) / (ki[i + 1] - ki[i - 1]);
+      const double p = sig * cdd[i - 1] + 2.0;
+      sgi[i] = sig;
+      pin[i] = 1.0 / p;
+      cdd[i] = (sig - 1.0) / p;
+    }
+  }
+  __syncwarp();
   const double anorm = 1. / (2 * PI * PI);
   // sigma^2-type integral at radius R (nonlinear_halofit_integrate): type 1, 2, 3
   auto integrate = [&](double R, int type) {
@@ -136,7 +151,26 @@ __global__ void __launch_bounds__(32) halofit_kernel(const HfParams P) {
       f[i] = v;
     }
     __syncwarp();
-    if (lane == 0) hf_spline_natural(ni, ki, f, dd, u);
+    // natural spline of f on the integrand grid: right-hand sides in parallel, the two sweeps on lane 0
+    for (int i = 1 + lane; i < ni - 1; i += 32) {
+      const double t = (f[i + 1] - f[i]) / (ki[i + 1] - ki[i]) - (f[i] - f[i - 1]) / (ki[i] - ki[i - 1]);
+      u[i] = 6.0 * t / (ki[i + 1] - ki[i - 1]);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double up = 0.;
+      for (int i = 1; i < ni - 1; i++) {
+        up = (u[i] - sgi[i] * up) * pin[i];
+        u[i] = up;
+      }
+      double dn = 0.;
+      dd[ni - 1] = 0.;
+      for (int k = ni - 2; k >= 1; k--) {
+        dn = cdd[k] * dn + u[k];
+        dd[k] = dn;
+      }
+      dd[0] = 0.;
+    }
     __syncwarp();
     double s = 0.;
     for (int i = lane; i < ni - 1; i += 32) {
@@ -275,7 +309,7 @@ int clpp_dev_halofit(clpp_ctx* c, const clpp_halofit_desc* hd, const double* pri
   CLPP_CUDA(cudaMemsetAsync(d->hf_flags, 0, ((size_t)2 * nt + 1) * sizeof(int), st), err);
   P.k = d->k; P.tau = d->tau; P.sources = d->sources; P.primordial = d->pk;
   P.corr = d->nl_corr2; P.fail = d->hf_flags; P.status = d->hf_flags + 2 * nt;
-  const size_t smem = (size_t)(3 * nk + 4 * P.ni + std::max(P.ni, nk)) * sizeof(double);
+  const size_t smem = (size_t)(3 * nk + 7 * P.ni + std::max(P.ni, nk)) * sizeof(double);
   CLPP_CHECK(smem <= 200 * 1024, err, "k grid too large for the shared-memory staging of halofit");
   CLPP_CUDA(cudaFuncSetAttribute(halofit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
   cudaEventRecord(d->ev[0], st);

@@ -137,9 +137,9 @@ class Context:
         return p.value or 0
 
     def kernel_ms(self):
-        out = np.zeros(6)
+        out = np.zeros(7)
         self._lib.clpp_ctx_get_kernel_ms(self._h, capi.dptr(out))
-        return dict(zip(("perturb", "k_spline", "bessel", "los", "spectra", "perturb_tail"), out.tolist()))
+        return dict(zip(("perturb", "k_spline", "bessel", "los", "spectra", "perturb_tail", "halofit"), out.tolist()))
 
     def fp64_peak_tflops(self):
         v = C.c_double()

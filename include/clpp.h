@@ -43,8 +43,8 @@ const char* clpp_version(void);
 int clpp_ctx_get_stream(clpp_ctx* ctx, void** stream);
 /* device time (ms, CUDA events on the ctx stream) of the kernels of the last stage calls:
  * out[0] perturb_kernel + perturb_tail_kernel, [1] k_spline_kernel, [2] bessel_table_kernel, [3] los_kernel,
- * [4] spectra kernels, [5] perturb_tail_kernel alone (included in [0]) */
-int clpp_ctx_get_kernel_ms(const clpp_ctx* ctx, double out[6]);
+ * [4] spectra kernels, [5] perturb_tail_kernel alone (included in [0]; 0 when the groups overlap), [6] halofit_kernel */
+int clpp_ctx_get_kernel_ms(const clpp_ctx* ctx, double out[7]);
 /* FP64 vector-pipe peak of this device measured with a dependent-free DFMA loop (TFLOP/s);
  * the denominator of the stage-1/2 roofline (MEASURED_PEAKS.json has no FP64 entry) */
 int clpp_measure_fp64_peak(clpp_ctx* ctx, double* tflops, char* err);
