@@ -124,6 +124,20 @@ class HalofitDesc(C.Structure):
     """)
 
 
+class LensingDesc(C.Structure):
+    _fields_ = _fields("""
+    int: accurate_lensing, delta_l_max, num_mu_minus_lmax
+    double: tol_gauss_legendre
+    """)
+
+
+class LensingInfo(C.Structure):
+    _fields_ = _fields("""
+    int: lt_size, l_size, l_unlensed_max, l_lensed_max
+    int: index_lt_tt, index_lt_ee, index_lt_te, index_lt_bb, index_lt_pp, index_lt_tp, index_lt_ep
+    """)
+
+
 class SpectraInfo(C.Structure):
     _fields_ = _fields("""
     int: ct_size, l_size
@@ -143,6 +157,7 @@ SYMBOLS = [
     "clpp_transfer_get_transfer", "clpp_transfer_set_transfer", "clpp_transfer_device_transfer",
     "clpp_transfer_get_bessel",
     "clpp_spectra_compute", "clpp_spectra_compute_range", "clpp_spectra_cl_at_l", "clpp_spectra_cl_output", "clpp_pk_linear", "clpp_nonlinear_halofit",
+    "clpp_lensing_compute", "clpp_lensing_cl_at_l",
 ]
 
 _lib = None
@@ -193,6 +208,8 @@ def lib():
         L.clpp_spectra_compute_range.argtypes = [vp, dp, C.c_int, C.c_int, P(SpectraInfo), dp, cp]
         L.clpp_pk_linear.argtypes = [vp, dp, C.c_int, C.c_int, dp, cp]
         L.clpp_nonlinear_halofit.argtypes = [vp, P(HalofitDesc), dp, dp, ip, cp]
+        L.clpp_lensing_compute.argtypes = [vp, P(LensingDesc), P(LensingInfo), dp, dp, cp]
+        L.clpp_lensing_cl_at_l.argtypes = [vp, C.c_int, dp, cp]
         L.clpp_spectra_cl_at_l.argtypes = [vp, C.c_double, dp, cp]
         L.clpp_spectra_cl_output.argtypes = [vp, C.c_int, dp, cp]
         _lib = L

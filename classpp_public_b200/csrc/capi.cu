@@ -20,6 +20,9 @@ int clpp_host_cl_at_l(const clpp_ctx* c, double l, double* cl_tot, char* err);
 int clpp_dev_halofit(clpp_ctx* c, const clpp_halofit_desc* hd, const double* primordial_pk, double* nl_corr_out,
                      int* index_tau_min_nl, char* err);
 int clpp_dev_pk_linear(clpp_ctx* c, const double* primordial_pk, int index_tau, int cb, double* pk_out, char* err);
+int clpp_dev_lensing(clpp_ctx* c, const clpp_lensing_desc* ld, clpp_lensing_info* info, double* l_out, double* cl_lens_out,
+                     char* err);
+int clpp_host_lensing_cl_at_l(const clpp_ctx* c, int l, double* cl_lensed, char* err);
 int clpp_dev_get_bessel(clpp_ctx* c, double* x, double* phi, double* dphi, double* chi, char* err);
 
 template <typename T>
@@ -74,7 +77,8 @@ void clpp_ctx_destroy(clpp_ctx* c) {
     void* ptrs[] = {d->bg_tau, d->bg_y, d->bg_dd, d->th_z, d->th_y, d->th_dd, d->k, d->tau, d->sources, d->kstat,
                     d->k_order, d->queue_head, d->jac_scratch, d->q, d->kq, d->l, d->bessel_x, d->bessel_phi,
                     d->bessel_dphi, d->chi_at_phimin, d->src_tr, d->src_ddk, d->nl_corr, d->transfer, d->tr_counters,
-                    d->pk, d->wq, d->cl, d->ncdm, d->pt_cosmo, d->pt_modes, d->spline_u, d->bessel_scale, d->pt_tail, d->nl_corr2, d->hf_flags};
+                    d->pk, d->wq, d->cl, d->ncdm, d->pt_cosmo, d->pt_modes, d->spline_u, d->bessel_scale, d->pt_tail, d->nl_corr2, d->hf_flags,
+                    d->lens_stage, d->lens_work, d->lens_coef, d->lens_lgrid};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     for (int i = 0; i < 6; i++)
@@ -101,10 +105,11 @@ int clpp_ctx_get_stream(clpp_ctx* c, void** stream) {
   return CLPP_SUCCESS;
 }
 
-int clpp_ctx_get_kernel_ms(const clpp_ctx* c, double out[7]) {
+int clpp_ctx_get_kernel_ms(const clpp_ctx* c, double out[8]) {
   if (!c || !c->dev) return CLPP_FAILURE;
   out[0] = c->dev->t_perturb_ms; out[1] = c->dev->t_kspline_ms; out[2] = c->dev->t_bessel_ms;
   out[3] = c->dev->t_los_ms; out[4] = c->dev->t_spectra_ms; out[5] = c->dev->t_perturb_tail_ms; out[6] = c->dev->t_halofit_ms;
+  out[7] = c->dev->t_lensing_ms;
   return CLPP_SUCCESS;
 }
 
@@ -404,6 +409,19 @@ int clpp_nonlinear_halofit(clpp_ctx* c, const clpp_halofit_desc* desc, const dou
   CLPP_CHECK(c->has_sources, err, "no sources: run clpp_perturb_solve first");
   cudaSetDevice(c->device);
   return clpp_dev_halofit(c, desc, primordial_pk, nl_corr_out, index_tau_min_nl, err);
+}
+
+int clpp_lensing_compute(clpp_ctx* c, const clpp_lensing_desc* desc, clpp_lensing_info* info, double* l_out,
+                         double* cl_lens_out, char* err) {
+  CLPP_CHECK(c && desc, err, "null argument");
+  CLPP_CHECK(c->dev, err, "this context has no CUDA device: the B200 path has no CPU fallback");
+  cudaSetDevice(c->device);
+  return clpp_dev_lensing(c, desc, info, l_out, cl_lens_out, err);
+}
+
+int clpp_lensing_cl_at_l(const clpp_ctx* c, int l, double* cl_lensed, char* err) {
+  CLPP_CHECK(c && cl_lensed, err, "null argument");
+  return clpp_host_lensing_cl_at_l(c, l, cl_lensed, err);
 }
 
 int clpp_spectra_cl_at_l(const clpp_ctx* c, double l, double* cl_tot, char* err) {

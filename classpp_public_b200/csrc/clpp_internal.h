@@ -100,6 +100,15 @@ struct clpp_ctx {
   bool has_cl = false;
   HostTable clt;
   int cl_l_max = 0;  // l_max_ct: C_l are zero above it
+  clpp_spectra_info sinfo{};
+
+  // --- lensing: lensed C_l table on its l grid + spline along l (lensing_cl_at_l)
+  bool has_cl_lens = false;
+  HostTable cl_lens;
+  int l_lensed_max = 0;
+  std::vector<double> lens_stage, gl_nodes;  // host staging; cached Gauss-Legendre nodes | weights
+  int gl_n = 0;
+  double gl_tol = 0.;
 
   // --- device memory (managed in device.cu)
   struct Dev;

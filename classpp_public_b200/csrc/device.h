@@ -61,6 +61,12 @@ struct clpp_ctx::Dev {
 
   // stage 3
   double *pk = nullptr, *wq = nullptr, *cl = nullptr;
+
+  // lensing
+  double *lens_stage = nullptr, *lens_work = nullptr, *lens_coef = nullptr;
+  int* lens_lgrid = nullptr;
+  int lens_lmax = -1;  // l_max the recurrence-coefficient table was built for
+  double t_lensing_ms = 0.;
 };
 
 // grow-only device buffer: reallocates only when the requested size exceeds the capacity

@@ -216,6 +216,8 @@ int clpp_dev_spectra(clpp_ctx* c, const double* primordial_pk, int q_begin, int 
     t.ddy.resize(t.y.size());
     clpp_spline_table_lines(t.x.data(), t.n_lines, t.y.data(), t.n_cols, t.ddy.data());
     c->cl_l_max = c->td.l_scalar_max;
+    c->sinfo = I;
+    c->has_cl_lens = false;
     c->has_cl = true;
   }
   return CLPP_SUCCESS;

@@ -137,9 +137,10 @@ class Context:
         return p.value or 0
 
     def kernel_ms(self):
-        out = np.zeros(7)
+        out = np.zeros(8)
         self._lib.clpp_ctx_get_kernel_ms(self._h, capi.dptr(out))
-        return dict(zip(("perturb", "k_spline", "bessel", "los", "spectra", "perturb_tail", "halofit"), out.tolist()))
+        return dict(zip(("perturb", "k_spline", "bessel", "los", "spectra", "perturb_tail", "halofit", "lensing"),
+                        out.tolist()))
 
     def fp64_peak_tflops(self):
         v = C.c_double()
@@ -414,6 +415,50 @@ class SpectraModule:
         self.ctx.check(self.ctx._lib.clpp_spectra_cl_output(self.ctx.handle, int(lmax), capi.dptr(out), self.ctx.err))
         tab = out.reshape(int(lmax) + 1, self.ct_size_)
         return {n: tab[:, getattr(self, "index_ct_%s_" % n)].copy() for n in ("tt", "ee", "te", "bb", "pp", "tp", "ep")
+                if getattr(self, "has_%s_" % n)}
+
+
+class LensingModule:
+    """LensingModule(input, spectra) (reference: source/lensing_module.h): lensed TT, TE, EE, BB on the device
+    (clpp_lensing_compute) from the C_l table of the SpectraModule. Members as in the reference: `l_`, `l_size_`,
+    `lt_size_`, `cl_lens_` ([index_l*lt_size_+index_lt]), `l_unlensed_max_`, `l_lensed_max_`, `index_lt_*_`, `has_*_`."""
+
+    def __init__(self, inputs, spectra_module):
+        ctx = spectra_module.ctx
+        self.ctx = ctx
+        m = inputs.meta
+        d = capi.LensingDesc()
+        d.accurate_lensing = int(m.get("pr.accurate_lensing", 0))              # precisions.h:492
+        d.delta_l_max = int(m.get("pr.delta_l_max", 500))                      # :494
+        d.num_mu_minus_lmax = int(m.get("pr.num_mu_minus_lmax", 70))           # :493
+        d.tol_gauss_legendre = float(m.get("pr.tol_gauss_legendre", np.finfo(np.float64).eps))  # :495
+        self.info = capi.LensingInfo()
+        l = np.zeros(spectra_module.l_size_max_)
+        cl = np.zeros(spectra_module.l_size_max_ * spectra_module.ct_size_)
+        ctx.check(ctx._lib.clpp_lensing_compute(ctx.handle, C.byref(d), C.byref(self.info), capi.dptr(l), capi.dptr(cl),
+                                                ctx.err))
+        i = self.info
+        self.lt_size_, self.l_size_ = i.lt_size, i.l_size
+        self.l_unlensed_max_, self.l_lensed_max_ = i.l_unlensed_max, i.l_lensed_max
+        self.l_ = l[: i.l_size].copy()
+        self.cl_lens_ = cl[: i.l_size * i.lt_size].copy()
+        for n in ("tt", "ee", "te", "bb", "pp", "tp", "ep"):
+            idx = getattr(i, "index_lt_" + n)
+            setattr(self, "index_lt_%s_" % n, idx)
+            setattr(self, "has_%s_" % n, int(idx >= 0))
+
+    def lensing_cl_at_l(self, l):
+        """lensed C_l^{lt} at integer l <= l_lensed_max_ (reference: lensing_module.cpp:111)."""
+        out = np.zeros(self.lt_size_)
+        self.ctx.check(self.ctx._lib.clpp_lensing_cl_at_l(self.ctx.handle, int(l), capi.dptr(out), self.ctx.err))
+        return out
+
+    def cl_output(self, lmax):
+        """dict name -> lensed C_l[0..lmax] like LensingModule::cl_output (lensing_module.cpp:62-108)."""
+        tab = np.zeros((int(lmax) + 1, self.lt_size_))
+        for l in range(2, int(lmax) + 1):
+            tab[l] = self.lensing_cl_at_l(l)
+        return {n: tab[:, getattr(self, "index_lt_%s_" % n)].copy() for n in ("tt", "ee", "te", "bb", "pp", "tp", "ep")
                 if getattr(self, "has_%s_" % n)}
 
 

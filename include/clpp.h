@@ -43,8 +43,9 @@ const char* clpp_version(void);
 int clpp_ctx_get_stream(clpp_ctx* ctx, void** stream);
 /* device time (ms, CUDA events on the ctx stream) of the kernels of the last stage calls:
  * out[0] perturb_kernel + perturb_tail_kernel, [1] k_spline_kernel, [2] bessel_table_kernel, [3] los_kernel,
- * [4] spectra kernels, [5] perturb_tail_kernel alone (included in [0]; 0 when the groups overlap), [6] halofit_kernel */
-int clpp_ctx_get_kernel_ms(const clpp_ctx* ctx, double out[7]);
+ * [4] spectra kernels, [5] perturb_tail_kernel alone (included in [0]; 0 when the groups overlap), [6] halofit_kernel,
+ * [7] lensing kernels */
+int clpp_ctx_get_kernel_ms(const clpp_ctx* ctx, double out[8]);
 /* FP64 vector-pipe peak of this device measured with a dependent-free DFMA loop (TFLOP/s);
  * the denominator of the stage-1/2 roofline (MEASURED_PEAKS.json has no FP64 entry) */
 int clpp_measure_fp64_peak(clpp_ctx* ctx, double* tflops, char* err);
@@ -246,6 +247,26 @@ typedef struct clpp_halofit_desc {
 } clpp_halofit_desc;
 int clpp_nonlinear_halofit(clpp_ctx* ctx, const clpp_halofit_desc* desc, const double* primordial_pk /*[k_size]*/,
                            double* nl_corr_out, int* index_tau_min_nl, char* err);
+
+/* ---- lensed C_l: second "next" row of SURVEY 8f ---------------------------------------------- */
+/* replaces LensingModule::lensing_init (lensing_module.cpp:149-860) with lensing_indices (:886-1092): lensed
+ * TT, TE, EE, BB by the full-sky correlation-function method from the table of clpp_spectra_compute (which must hold
+ * tt and pp). Fast mode (accurate_lensing = 0, the default of precisions.h:492) or Gauss-Legendre mode.
+ * l_out[info.l_size] (NULL allowed): multipoles l_; cl_lens_out[info.l_size*info.lt_size] (NULL allowed): cl_lens_
+ * in the reference layout [index_l*lt_size + index_lt]; types other than tt/te/ee/bb are copied unlensed. */
+typedef struct clpp_lensing_desc {
+  int accurate_lensing, delta_l_max, num_mu_minus_lmax; /* precisions.h:492-494 */
+  double tol_gauss_legendre;                              /* precisions.h:495 */
+} clpp_lensing_desc;
+typedef struct clpp_lensing_info {
+  int lt_size, l_size, l_unlensed_max, l_lensed_max;
+  int index_lt_tt, index_lt_ee, index_lt_te, index_lt_bb, index_lt_pp, index_lt_tp, index_lt_ep; /* -1 absent */
+} clpp_lensing_info;
+int clpp_lensing_compute(clpp_ctx* ctx, const clpp_lensing_desc* desc, clpp_lensing_info* info, double* l_out,
+                         double* cl_lens_out, char* err);
+/* replaces LensingModule::lensing_cl_at_l (lensing_module.cpp:111-140): spline in l through cl_lens_, fails above
+ * l_lensed_max with the reference's message; cl_lensed[lt_size]. */
+int clpp_lensing_cl_at_l(const clpp_ctx* ctx, int l, double* cl_lensed, char* err);
 
 /* replaces SpectraModule::spectra_cl_at_l (spectra_module.cpp:220-264, one mode / one initial condition):
  * cubic spline in l through the table of clpp_spectra_compute, zero above l_scalar_max. cl_tot[ct_size]. */

@@ -162,6 +162,8 @@ long rp_get(void* h, const char* cname, double* out, long cap) {
   PR(q_linstep); PR(q_logstep_spline); PR(q_logstep_open); PR(q_logstep_trapzd); PR(q_numstep_transition);
   PR(transfer_neglect_delta_k_S_t0); PR(transfer_neglect_delta_k_S_t1); PR(transfer_neglect_delta_k_S_t2);
   PR(transfer_neglect_delta_k_S_e); PR(transfer_neglect_late_source); PR(l_switch_limber);
+  PR(accurate_lensing); PR(delta_l_max); PR(num_mu_minus_lmax); PR(tol_gauss_legendre);
+  PR(halofit_min_k_nonlinear); PR(halofit_k_per_decade); PR(halofit_sigma_precision); PR(halofit_tol_sigma);
 #undef PR
   // ---- background / thermo / perturbs input structs ----
   S("ba.h", ba.h); S("ba.H0", ba.H0); S("ba.K", ba.K); S("ba.sgnK", ba.sgnK); S("ba.a_today", ba.a_today);

@@ -21,7 +21,9 @@ ur_fluid_trigger_tau_over_tau_k ncdm_fluid_approximation ncdm_fluid_trigger_tau_
 perturb_integration_stepsize
 l_logstep l_linstep hyper_x_min hyper_sampling_flat hyper_phi_min_abs q_linstep q_logstep_spline q_logstep_open
 transfer_neglect_delta_k_S_t0 transfer_neglect_delta_k_S_t1 transfer_neglect_delta_k_S_t2
-transfer_neglect_delta_k_S_e transfer_neglect_late_source l_switch_limber""".split()
+transfer_neglect_delta_k_S_e transfer_neglect_late_source l_switch_limber
+accurate_lensing delta_l_max num_mu_minus_lmax tol_gauss_legendre
+halofit_min_k_nonlinear halofit_k_per_decade halofit_sigma_precision halofit_tol_sigma""".split()
 BA_KEYS = """h H0 K sgnK a_today T_cmb Omega0_b has_cdm has_ur has_ncdm has_fld has_curvature has_dcdm has_dr has_scf
 has_idr has_idm_dr N_ncdm""".split()
 TH_IN_KEYS = "reio_parametrization compute_cb2_derivatives compute_damping_scale".split()

@@ -298,6 +298,81 @@ def test_halofit_on_device_vs_golden(golden):
     ctx.close()
 
 
+@pytest.mark.parametrize("name,rtol", [("lcdm_coarse", 5e-4), ("planck18", CL_RTOL)])
+def test_lensed_cl_on_device_vs_golden(golden, name, rtol):
+    """LensingModule on the device (clpp_lensing_compute + clpp_lensing_cl_at_l) against the
+    reference's lensing_cl_at_l at every l = 2..l_lensed_max (fast mode, the default). The lensing operator itself
+    (lensed/unlensed ratio, which cancels the 1e-4-level differences of the unlensed input) is held to 2e-5."""
+    inp = golden(name)
+    a = inp.arrays
+    ctx, pt, tr, sp = run_pipeline(inp)
+    le = M.LensingModule(inp, sp)
+    lt = le.lt_size_
+    ref = a["ref.cl_lensed"].reshape(-1, lt)
+    assert le.l_lensed_max_ == ref.shape[0] - 1 and le.l_unlensed_max_ == sp.l_max_tot_
+    mine = np.zeros_like(ref)
+    for l in range(2, le.l_lensed_max_ + 1):
+        mine[l] = le.lensing_cl_at_l(l)
+    m, r = mine[2:], ref[2:]
+    tt, ee, te, bb = le.index_lt_tt_, le.index_lt_ee_, le.index_lt_te_, le.index_lt_bb_
+    assert np.max(np.abs(m[:, tt] / r[:, tt] - 1.0)) < rtol
+    assert np.max(np.abs(m[:, ee] / r[:, ee] - 1.0)) < rtol
+    assert np.max(np.abs(m[:, te] - r[:, te]) / np.sqrt(r[:, tt] * r[:, ee])) < rtol
+    assert np.all(r[:, bb] > 0) and np.max(np.abs(m[:, bb] / r[:, bb] - 1.0)) < 2 * rtol
+    # types lensing leaves alone: unlensed values on the (truncated) lensing l grid, splined there like the reference
+    pp, tp, ep = le.index_lt_pp_, le.index_lt_tp_, le.index_lt_ep_
+    assert np.max(np.abs(m[:, pp] / r[:, pp] - 1.0)) < rtol
+    assert np.max(np.abs(m[:, tp] - r[:, tp]) / np.sqrt(r[:, tt] * r[:, pp])) < rtol
+    assert np.max(np.abs(m[:, ep] - r[:, ep]) / np.sqrt(r[:, ee] * r[:, pp])) < rtol
+    assert np.array_equal(le.cl_lens_.reshape(-1, lt)[:, pp], sp.cl_[0].reshape(-1, lt)[: le.l_size_, pp])
+    # the operator: lensed/unlensed at the grid multipoles, ours vs the reference's
+    lgrid = sp.l_.astype(int)
+    ref_unl = a["ref.cl"].reshape(-1, lt)
+    rows = np.nonzero((lgrid >= 2) & (lgrid <= le.l_lensed_max_))[0]
+    sel = lgrid[rows]
+    for c in (tt, ee):
+        ratio_mine = mine[sel, c] / sp.cl_[0].reshape(-1, lt)[rows, c]
+        ratio_ref = ref[sel, c] / ref_unl[rows, c]
+        assert np.max(np.abs(ratio_mine / ratio_ref - 1.0)) < 2e-5
+    with pytest.raises(M.CosmoComputationError, match="you asked for lensed Cls at l="):
+        le.lensing_cl_at_l(le.l_lensed_max_ + 1)
+    assert ctx.kernel_ms()["lensing"] > 0
+    ctx.close()
+
+
+def test_accurate_lensing_mode_vs_live_reference():
+    """accurate_lensing = 1 (Gauss-Legendre nodes on [-1,1], no unlensed subtraction; lensing_module.cpp:237-248)
+    against the unmodified reference run with the same switch, and with a non-default delta_l_max."""
+    from oracle import refprobe
+    if not refprobe.available():
+        pytest.skip("oracle/_ref not loadable on this box")
+    import os
+    from classpp_public_b200.configs import CONFIGS
+    from refutil import inputs_from_reference
+    par = dict(CONFIGS["lcdm_coarse"], accurate_lensing=1, delta_l_max=300)
+    ref = refprobe.RefCosmology(par, threads=os.cpu_count()).compute("lensing")
+    inp = inputs_from_reference(ref)
+    assert int(inp.meta["pr.accurate_lensing"]) == 1 and int(inp.meta["pr.delta_l_max"]) == 300
+    ctx = M.Context(0)
+    bg = M.BackgroundModule(inp, ctx)
+    th = M.ThermodynamicsModule(inp, bg)
+    pt = M.PerturbationsModule(inp, bg, th)
+    tr = M.TransferModule(inp, bg, th, pt, None)
+    sp = M.SpectraModule(inp, pt, M.TabulatedPrimordial(ref.get("pm.pk_at_transfer_k")), None, tr)
+    le = M.LensingModule(inp, sp)
+    lt = le.lt_size_
+    r = ref.get("le.cl_lensed").reshape(-1, lt)[2:]
+    assert le.l_lensed_max_ == ref.iscalar("le.l_lensed_max") == le.l_unlensed_max_ - 300
+    m = np.array([le.lensing_cl_at_l(l) for l in range(2, le.l_lensed_max_ + 1)])
+    tt, ee, te, bb = le.index_lt_tt_, le.index_lt_ee_, le.index_lt_te_, le.index_lt_bb_
+    assert np.max(np.abs(m[:, tt] / r[:, tt] - 1.0)) < 5e-4
+    assert np.max(np.abs(m[:, ee] / r[:, ee] - 1.0)) < 5e-4
+    assert np.max(np.abs(m[:, te] - r[:, te]) / np.sqrt(r[:, tt] * r[:, ee])) < 5e-4
+    assert np.max(np.abs(m[:, bb] / r[:, bb] - 1.0)) < 1e-3
+    ctx.close()
+    ref.close()
+
+
 def test_k_range_partition_equals_full_solve(golden):
     """Multi-GPU partition property: integrating two k ranges separately fills the same source table."""
     inp = golden("lcdm_coarse")
