@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "lensed C_l spectra/sec (Planck-18 LCDM hot path: perturbations+transfer+spectra)"
+METRIC = "lensed C_l spectra/sec (Planck-18 LCDM hot path: perturbations+halofit+transfer+spectra+lensing)"
 UNIT = "spectra/s"
 
 # Algorithmic FP64 work of stage 1 per cosmology (SURVEY.md 8d / BASELINE.md 2): oracle stepstat
@@ -123,6 +123,7 @@ def run_gpu(args):
     halofit_on_device = nl is not None and args.halofit == "device"
     prim_k = M.AnalyticPrimordial(CONFIGS[args.config].get("A_s", 2.215e-9), CONFIGS[args.config].get("n_s", 0.9619))
     B = args.batch
+    prim_pt = np.ascontiguousarray(prim_k.pk_at_k(a["ref.k"]))
 
     # ---- device-resident inputs: one context (own stream) per cosmology of the batch
     ctxs, mods = [], []
@@ -139,7 +140,8 @@ def run_gpu(args):
 
     def step(inputs=None, pk_=None, nl_=None, fetch=False):
         """One pass of the hot path over the batch: every k mode of the B cosmologies in ONE perturbation
-        launch (longest modes first across the batch), then transfer + spectra per cosmology on its own stream.
+        launch (longest modes first across the batch), then halofit, transfer, spectra, lensing and P(k) per cosmology
+        on its own stream.
         With `inputs` (pinned host arrays) the upstream tables are uploaded first and the public result
         members (sources_, cl_) are read back: the end-to-end variant."""
         x, p_, n_ = (inputs or inp), (pk if pk_ is None else pk_), (nl if nl_ is None else nl_)
@@ -159,7 +161,9 @@ def run_gpu(args):
                 nlb = M.NonlinearModule(x, mods[b][0], pts[b], prim_k)
             tr = M.TransferModule(x, mods[b][0], mods[b][1], pts[b], nlb)
             sp = M.SpectraModule(x, pts[b], M.TabulatedPrimordial(p_), nlb, tr)
-            out_bytes = sp.cl_[0].nbytes
+            le = M.LensingModule(x, sp)  # lensed TT/TE/EE/BB on the device: the metric's "lensed C_l"
+            pk_lin = pts[b].pk_linear(prim_pt)  # linear P(k, z=0) on the perturbation k grid
+            out_bytes = sp.cl_[0].nbytes + le.cl_lens_.nbytes + pk_lin.nbytes
             if fetch:  # device -> host: the public members downstream modules read (Nonlinear/Lensing/Output)
                 out_bytes += sum(s_.nbytes for s_ in pts[b].sources_[0])
             results[b] = (pts[b], tr, sp, out_bytes)
@@ -181,7 +185,8 @@ def run_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t0 = time.perf_counter()
-    kms = {"perturb": 0.0, "k_spline": 0.0, "bessel": 0.0, "los": 0.0, "spectra": 0.0, "perturb_tail": 0.0, "halofit": 0.0}
+    kms = {"perturb": 0.0, "k_spline": 0.0, "bessel": 0.0, "los": 0.0, "spectra": 0.0, "perturb_tail": 0.0, "halofit": 0.0,
+           "lensing": 0.0}
     for _ in range(args.steps):
         step()
         for c in ctxs:
@@ -268,6 +273,7 @@ def run_gpu(args):
                    "fixture": "tests/golden/%s.npz" % args.config, "batch_per_gpu": B,
                    "halofit": ("on the device, inside the step (clpp_nonlinear_halofit)" if halofit_on_device else
                                "correction table is an input" if nl is not None else "none"),
+                   "scope": "per cosmology: perturbations -> halofit -> transfer -> spectra -> lensing (fast mode) -> linear P(k)",
                    "k_modes": int(results[0][0].info.k_size), "tau_samples": int(results[0][0].info.tau_size),
                    "q_values": int(tr_info.q_size), "l_values": int(tr_info.l_size),
                    "parallelism": "independent cosmologies per GPU (replicas, no data-path collective); per GPU all k modes "
@@ -284,7 +290,8 @@ def run_gpu(args):
                 "steps": e2e_steps,
                 "note": "per step and per cosmology of the batch: upstream tables from pinned host memory through "
                         "clpp_set_background/clpp_set_thermo (host spline + H2D), grids, batched perturbation launch, "
-                        "transfer, spectra, D2H of sources_ and cl_ (contexts and device buffers are reused across steps)"},
+                        "halofit, transfer, spectra, lensing, P(k), D2H of sources_, cl_, cl_lens_ and P(k) (contexts and "
+                        "device buffers are reused across steps)"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
@@ -304,25 +311,29 @@ def cpu_baseline(config, budget_s=20.0, threads=None):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                 "sample": "oracle/_ref not built on this box"}
     cores = threads or os.cpu_count()
-    times = []
+    times, times3 = [], []
     t_start = time.perf_counter()
     n = 0
     while True:
         ref = refprobe.RefCosmology(CONFIGS[config], threads=cores)
-        ref.compute("spectra")
-        t = ref.scalar("time.perturb") + ref.scalar("time.transfer") + ref.scalar("time.spectra")
+        ref.compute("lensing")
+        t3 = ref.scalar("time.perturb") + ref.scalar("time.transfer") + ref.scalar("time.spectra")
+        t = t3 + ref.scalar("time.nonlinear") + ref.scalar("time.lensing")
         ref.close()
         n += 1
         if n > 1:  # the first run of a process is cold: discard
             times.append(t)
+            times3.append(t3)
         if (time.perf_counter() - t_start > budget_s and len(times) >= 2) or len(times) >= 8:
             break
     best = min(times)
     return {"value": 1.0 / best, "unit": UNIT, "cores": int(cores), "kind": "reference",
             "hot_path_s_best": best, "hot_path_s_mean": float(np.mean(times)),
+            "three_module_s_best": float(min(times3)),
             "sample": "%d full runs of the reference for this config (first discarded); value = 1 / best wall time of "
-                      "the PerturbationsModule+TransferModule+SpectraModule constructors (same scope as the GPU arm; "
-                      "background/thermodynamics/halofit/lensing excluded), thread pool = %d threads" % (n, cores)}
+                      "the Perturbations+Nonlinear+Transfer+Spectra+Lensing module constructors (same scope as the GPU "
+                      "arm; three_module_s_best = Perturbations+Transfer+Spectra alone; background/thermodynamics/"
+                      "primordial excluded), thread pool = %d threads" % (n, cores)}
 
 
 def run_reference(args):
@@ -337,8 +348,9 @@ def run_reference(args):
     cores = os.cpu_count()
     ts = []
     for i in range(args.warmup + args.steps):
-        ref = refprobe.RefCosmology(CONFIGS[args.config], threads=cores).compute("spectra")
-        t = ref.scalar("time.perturb") + ref.scalar("time.transfer") + ref.scalar("time.spectra")
+        ref = refprobe.RefCosmology(CONFIGS[args.config], threads=cores).compute("lensing")
+        t = (ref.scalar("time.perturb") + ref.scalar("time.nonlinear") + ref.scalar("time.transfer") +
+             ref.scalar("time.spectra") + ref.scalar("time.lensing"))
         ref.close()
         if i >= args.warmup:
             ts.append(t)
@@ -348,7 +360,8 @@ def run_reference(args):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(ts) * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": args.config, "note": "unmodified CLASS++ (oracle/_ref) on the host cores; each step = "
-                      "one cosmology, timed = PerturbationsModule+TransferModule+SpectraModule constructors"},
+                      "one cosmology, timed = Perturbations+Nonlinear+Transfer+Spectra+Lensing module constructors "
+                      "(the scope of the GPU arm's step)"},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(cores), "kind": "reference",
                             "sample": "%d steps of 1 cosmology each, thread pool = %d" % (len(ts), cores)},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -9,6 +9,8 @@
 // reference's d[mu][l] tables (12 x num_mu x l_max doubles) never exist. Only the four d's needed for the back-transform
 // are stored, and only at the ~60 multipoles of the output grid. The l-dependent recurrence coefficients are the same for
 // every angle: built once per l_max by a small kernel and read as warp-wide broadcasts.
+#include <cuda_pipeline.h>
+
 #include <cmath>
 #include <vector>
 
@@ -22,14 +24,20 @@ enum { F_00 = 0, F_11, F_1M1, F_2M2, F_22, F_20, F_31, F_3M1, F_3M3, F_40, F_4M2
 __constant__ int c_fam_m[NFAM] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4};
 __constant__ int c_fam_n[NFAM] = {0, 1, -1, -2, 2, 0, 1, -1, -3, 0, -2, -4};
 
-// coef[(f*(lmax+1) + l)*4 + {0,1,2}] = a, b, c of  N_{l+1} = a (mu - b) N_l - c N_{l-1},  N_l = sqrt((2l+1)/2) d^l_mn;
-// zero below the first multipole of the family, so that the recurrence can run unconditionally on N = 0.
-// norm[l] = sqrt(2/(2l+1)).
-__global__ void lens_coef_kernel(int lmax, double* __restrict__ coef, double* __restrict__ norm) {
+// One 512-byte row of l-only quantities per multipole, shared by every angle and every cosmology with this l_max:
+//   row[f*4 + {0,1,2}] = a, b, c of  N_{l+1} = a (mu - b) N_l - c N_{l-1},  N_l = sqrt((2l+1)/2) d^l_mn  (:1261-1935);
+//                        zero below the first multipole of the family, so the recurrence runs unconditionally on N = 0
+//   row[48..55]        = l(l+1)/4, (2l+1)/4pi, 8/(l(l+1)), sqrt1/4, sqrt4/4, -sqrt2/2, -sqrt3/2, 2/sqrt5   (:622-681):
+//                        the angle loop has no square root or division left
+//   row[56]            = sqrt(2/(2l+1)),  row[57] = (2l+1) l (l+1)
+constexpr int LROW = 64;  // doubles per row
+constexpr int LCH = 32;   // rows per shared-memory stage
+
+__global__ void lens_table_kernel(int lmax, double* __restrict__ tab) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l > lmax) return;
   const double ll = (double)l;
-  norm[l] = sqrt(2. / (2. * ll + 1.));
+  double* row = tab + (size_t)l * LROW;
   for (int f = 0; f < NFAM; f++) {
     const int m = c_fam_m[f], n = c_fam_n[f];
     const int l0 = max(max(abs(m), abs(n)), 1);
@@ -41,16 +49,26 @@ __global__ void lens_coef_kernel(int lmax, double* __restrict__ coef, double* __
       b = (double)(m * n) / (ll * l1);
       c = sqrt((2. * ll + 3.) / (2. * ll - 1.)) * sqrt((ll * ll - m2) * (ll * ll - n2)) / den * l1 / ll;
     }
-    double* o = coef + ((size_t)f * (lmax + 1) + l) * 4;
-    o[0] = a; o[1] = b; o[2] = c; o[3] = 0.;
+    row[f * 4 + 0] = a; row[f * 4 + 1] = b; row[f * 4 + 2] = c; row[f * 4 + 3] = 0.;
   }
+  row[48] = ll * (ll + 1.) / 4.;
+  row[49] = (2. * ll + 1.) / (4. * CLPP_PI);
+  row[50] = l > 0 ? 8. / (ll * (ll + 1.)) : 0.;
+  row[51] = l >= 1 ? 0.25 * sqrt((ll + 2.) * (ll + 1.) * ll * (ll - 1.)) : 0.;
+  row[52] = l >= 3 ? 0.25 * sqrt((ll + 4.) * (ll + 3.) * (ll - 2.) * (ll - 3.)) : 0.;
+  row[53] = l >= 1 ? -0.5 * sqrt((ll + 2.) * (ll - 1.)) : 0.;
+  row[54] = l >= 2 ? -0.5 * sqrt((ll + 3.) * (ll - 2.)) : 0.;
+  row[55] = l > 0 ? 2. / sqrt(ll * (ll + 1.)) : 0.;
+  row[56] = sqrt(2. / (2. * ll + 1.));
+  row[57] = (2. * ll + 1.) * ll * (ll + 1.);
+  for (int j = 58; j < LROW; j++) row[j] = 0.;
 }
 
 struct LensParams {
   int lmax, num_mu, n_int;  // n_int: number of integration nodes (num_mu - 1 in both modes; the last mu is 1)
   int l_size;
   int has_te, has_pol, subtract_unlensed;
-  const double *mu, *w8, *coef, *norm;
+  const double *mu, *w8, *tab;
   const double* cl;  // [5][lmax+1]: tt, te, ee, bb, pp
   const int* lgrid;
   double *cgl, *cgl2;  // [num_mu]
@@ -59,137 +77,185 @@ struct LensParams {
   double *out;         // [l_size][4]: tt, te, ee, bb integrals
 };
 
-__device__ __forceinline__ void lens_step(const double* __restrict__ coef, int lmax, int f, int l, double mu, double& cur,
-                                          double& prev) {
-  const double2 ab = *reinterpret_cast<const double2*>(coef + ((size_t)f * (lmax + 1) + l) * 4);
-  const double c = coef[((size_t)f * (lmax + 1) + l) * 4 + 2];
+// The angle kernels are one warp per CTA, every lane walking l = 1..l_max in lock step, so the l-only rows and the C_l are
+// staged through shared memory: asynchronous 16-byte copies of the next LCH rows (double buffered) while the current
+// ones are consumed as warp-wide broadcasts. Without the staging every iteration waits an L2 round trip.
+struct LensStage {
+  double tab[2][LCH * LROW];
+  double cl[2][5][LCH];
+};
+
+__device__ __forceinline__ void lens_prefetch(LensStage& S, int buf, const LensParams& P, int l_begin) {
+  const int lane = threadIdx.x;
+  const int nrow = min(LCH, P.lmax + 1 - l_begin);
+  const double* src = P.tab + (size_t)l_begin * LROW;
+  for (int i = lane; i < nrow * (LROW / 2); i += 32) __pipeline_memcpy_async(&S.tab[buf][2 * i], src + 2 * i, 16);
+  if (lane < nrow) {
+#pragma unroll
+    for (int j = 0; j < 5; j++)
+      __pipeline_memcpy_async(&S.cl[buf][j][lane], P.cl + (size_t)j * (P.lmax + 1) + l_begin + lane, 8);
+  }
+  __pipeline_commit();
+}
+
+__device__ __forceinline__ void lens_step(const double* __restrict__ row, int f, double mu, double& cur, double& prev) {
+  const double2 ab = *reinterpret_cast<const double2*>(row + f * 4);
+  const double c = row[f * 4 + 2];
   const double nxt = ab.x * (mu - ab.y) * cur - c * prev;
   prev = cur;
   cur = nxt;
 }
 
 // Cgl(mu), Cgl2(mu) (lensing_module.cpp:560-575): sums over l of (2l+1) l (l+1) C_l^pp d^l_{11}, d^l_{1-1} / 4 pi
-__global__ void lens_cgl_kernel(LensParams P) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.num_mu) return;
+__global__ void __launch_bounds__(32) lens_cgl_kernel(LensParams P) {
+  __shared__ __align__(16) LensStage S;
+  const int i = min((int)(blockIdx.x * 32 + threadIdx.x), P.num_mu - 1);
   const double mu = P.mu[i];
-  const double* clpp = P.cl + (size_t)4 * (P.lmax + 1);
   double c11 = (1. + mu) / 2. * sqrt(3. / 2.), p11 = 0.;
   double c1m1 = (1. - mu) / 2. * sqrt(3. / 2.), p1m1 = 0.;
-  lens_step(P.coef, P.lmax, F_11, 1, mu, c11, p11);
-  lens_step(P.coef, P.lmax, F_1M1, 1, mu, c1m1, p1m1);
   double s1 = 0., s2 = 0.;
-  for (int l = 2; l <= P.lmax; l++) {
-    const double ll = (double)l;
-    const double w = (2. * ll + 1.) * ll * (ll + 1.) * clpp[l] * P.norm[l];
-    s1 += w * c11;
-    s2 += w * c1m1;
-    if (l < P.lmax) {
-      lens_step(P.coef, P.lmax, F_11, l, mu, c11, p11);
-      lens_step(P.coef, P.lmax, F_1M1, l, mu, c1m1, p1m1);
+  const int nch = P.lmax / LCH + 1;
+  lens_prefetch(S, 0, P, 0);
+  for (int c = 0; c < nch; c++) {
+    if (c + 1 < nch) lens_prefetch(S, (c + 1) & 1, P, (c + 1) * LCH);
+    else __pipeline_commit();
+    __pipeline_wait_prior(1);
+    __syncwarp();
+    const int l_end = min((c + 1) * LCH - 1, P.lmax);
+    for (int l = max(c * LCH, 1); l <= l_end; l++) {
+      const double* row = S.tab[c & 1] + (l - c * LCH) * LROW;
+      if (l >= 2) {
+        const double w = row[57] * S.cl[c & 1][4][l - c * LCH] * row[56];
+        s1 += w * c11;
+        s2 += w * c1m1;
+      }
+      if (l < P.lmax) {
+        lens_step(row, F_11, mu, c11, p11);
+        lens_step(row, F_1M1, mu, c1m1, p1m1);
+      }
     }
+    __syncwarp();
   }
-  P.cgl[i] = s1 / (4. * CLPP_PI);
-  P.cgl2[i] = s2 / (4. * CLPP_PI);
+  if (blockIdx.x * 32 + threadIdx.x < P.num_mu) {
+    P.cgl[i] = s1 / (4. * CLPP_PI);
+    P.cgl2[i] = s2 / (4. * CLPP_PI);
+  }
 }
 
 // lensed (minus unlensed) correlation functions ksi, ksiX, ksi+, ksi- at one angle per thread (:628-738)
-__global__ void lens_ksi_kernel(LensParams P) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.n_int) return;
+__global__ void __launch_bounds__(32) lens_ksi_kernel(LensParams P) {
+  __shared__ __align__(16) LensStage S;
   const int lmax = P.lmax;
+  const bool live = (int)(blockIdx.x * 32 + threadIdx.x) < P.n_int;
+  const int i = min((int)(blockIdx.x * 32 + threadIdx.x), P.n_int - 1);
   const double mu = P.mu[i];
   const double sigma2 = P.cgl[P.num_mu - 1] - P.cgl[i];
   const double cgl2 = P.cgl2[i];
   const double op = 1. + mu, om = 1. - mu;
-  const double *cl_tt = P.cl, *cl_te = P.cl + (lmax + 1), *cl_ee = P.cl + 2 * (size_t)(lmax + 1),
-               *cl_bb = P.cl + 3 * (size_t)(lmax + 1);
 
   double cur[NFAM], prev[NFAM];
 #pragma unroll
   for (int f = 0; f < NFAM; f++) { cur[f] = 0.; prev[f] = 0.; }
-  // first multipoles (closed forms of d^l_mn at l = max(|m|,|n|), times sqrt((2l+1)/2))
+  // first multipoles: closed forms of d^l_mn at l = max(|m|,|n|), times sqrt((2l+1)/2); l = 0 and 1 here
   prev[F_00] = 1. / sqrt(2.);
   cur[F_00] = mu * sqrt(3. / 2.);
   cur[F_11] = op / 2. * sqrt(3. / 2.);
   cur[F_1M1] = om / 2. * sqrt(3. / 2.);
-  lens_step(P.coef, lmax, F_00, 1, mu, cur[F_00], prev[F_00]);
-  lens_step(P.coef, lmax, F_11, 1, mu, cur[F_11], prev[F_11]);
-  lens_step(P.coef, lmax, F_1M1, 1, mu, cur[F_1M1], prev[F_1M1]);
-  cur[F_2M2] = om * om / 4. * sqrt(5. / 2.);
-  cur[F_22] = op * op / 4. * sqrt(5. / 2.);
-  cur[F_20] = sqrt(15.) / 4. * (1. - mu * mu);
 
   double ksi = 0., ksiX = 0., ksip = 0., ksim = 0.;
   int ig = 0;
   int lg = P.l_size > 0 ? P.lgrid[0] : -1;
-  for (int l = 2; l <= lmax; l++) {
-    if (l == 3) {
-      cur[F_31] = sqrt(105. / 2.) * op * op * om / 8.;
-      cur[F_3M1] = sqrt(105. / 2.) * op * om * om / 8.;
-      cur[F_3M3] = sqrt(7. / 2.) * om * om * om / 8.;
-    } else if (l == 4) {
-      cur[F_40] = sqrt(315.) * op * op * om * om / 16.;
-      cur[F_4M2] = sqrt(126.) * op * om * om * om / 16.;
-      cur[F_4M4] = sqrt(9. / 2.) * om * om * om * om / 16.;
-    }
-    const double nl = P.norm[l];
-    const double d00 = cur[F_00] * nl, d11 = cur[F_11] * nl, d1m1 = cur[F_1M1] * nl, d2m2 = cur[F_2M2] * nl;
-    const double d22 = cur[F_22] * nl, d20 = cur[F_20] * nl, d31 = cur[F_31] * nl, d3m1 = cur[F_3M1] * nl;
-    const double d3m3 = cur[F_3M3] * nl, d40 = cur[F_40] * nl, d4m2 = cur[F_4M2] * nl, d4m4 = cur[F_4M4] * nl;
-    if (l == lg) {
-      const size_t st = (size_t)P.l_size * P.n_int;
-      const size_t o = (size_t)ig * P.n_int + i;
-      P.dgrid[o] = d00; P.dgrid[st + o] = d20; P.dgrid[2 * st + o] = d22; P.dgrid[3 * st + o] = d2m2;
-      ig++;
-      lg = ig < P.l_size ? P.lgrid[ig] : -1;
-    }
-    const double ll = (double)l;
-    const double fac = ll * (ll + 1.) / 4.;
-    const double fac1 = (2. * ll + 1.) / (4. * CLPP_PI);
-    const double X_000 = exp(-fac * sigma2);
-    const double X_p000 = -fac * X_000;
-    const double X_220 = 0.25 * sqrt((ll + 2.) * (ll + 1.) * ll * (ll - 1.)) * X_000;
-    {
-      double lens = X_000 * X_000 * d00 + X_p000 * X_p000 * d1m1 * cgl2 * 8. / (ll * (ll + 1.)) +
-                    (X_p000 * X_p000 * d00 + X_220 * X_220 * d2m2) * cgl2 * cgl2;
-      if (P.subtract_unlensed) lens -= d00;
-      ksi += fac1 * cl_tt[l] * lens;
-    }
-    if (P.has_te | P.has_pol) {
-      const double X_022 = X_000 * (1. + sigma2 * (1. + 0.5 * sigma2));
-      const double X_p022 = -(fac - 1.) * X_022;
-      const double X_242 = 0.25 * sqrt((ll + 4.) * (ll + 3.) * (ll - 2.) * (ll - 3.)) * X_000;
-      double X_121 = 0., X_132 = 0.;
-      if (P.has_pol) {
-        X_121 = -0.5 * sqrt((ll + 2.) * (ll - 1.)) * X_000 * (1. + 2. / 3. * sigma2);
-        X_132 = -0.5 * sqrt((ll + 3.) * (ll - 2.)) * X_000 * (1. + 5. / 3. * sigma2);
+  const int nch = lmax / LCH + 1;
+  lens_prefetch(S, 0, P, 0);
+  for (int c = 0; c < nch; c++) {
+    if (c + 1 < nch) lens_prefetch(S, (c + 1) & 1, P, (c + 1) * LCH);
+    else __pipeline_commit();
+    __pipeline_wait_prior(1);
+    __syncwarp();
+    const int l_end = min((c + 1) * LCH - 1, lmax);
+#pragma unroll 1
+    for (int l = max(c * LCH, 1); l <= l_end; l++) {
+      const double* row = S.tab[c & 1] + (l - c * LCH) * LROW;
+      if (l == 2) {
+        cur[F_2M2] = om * om / 4. * sqrt(5. / 2.);
+        cur[F_22] = op * op / 4. * sqrt(5. / 2.);
+        cur[F_20] = sqrt(15.) / 4. * (1. - mu * mu);
+      } else if (l == 3) {
+        cur[F_31] = sqrt(105. / 2.) * op * op * om / 8.;
+        cur[F_3M1] = sqrt(105. / 2.) * op * om * om / 8.;
+        cur[F_3M3] = sqrt(7. / 2.) * om * om * om / 8.;
+      } else if (l == 4) {
+        cur[F_40] = sqrt(315.) * op * op * om * om / 16.;
+        cur[F_4M2] = sqrt(126.) * op * om * om * om / 16.;
+        cur[F_4M4] = sqrt(9. / 2.) * om * om * om * om / 16.;
       }
-      if (P.has_te) {
-        double lens = X_022 * X_000 * d20 + cgl2 * 2. * X_p000 / sqrt(ll * (ll + 1.)) * (X_121 * d11 + X_132 * d3m1) +
-                      0.5 * cgl2 * cgl2 * ((2. * X_p022 * X_p000 + X_220 * X_220) * d20 + X_220 * X_242 * d4m2);
-        if (P.subtract_unlensed) lens -= d20;
-        ksiX += fac1 * cl_te[l] * lens;
+      if (l >= 2) {
+        const double nl = row[56];
+        const double d00 = cur[F_00] * nl, d11 = cur[F_11] * nl, d1m1 = cur[F_1M1] * nl, d2m2 = cur[F_2M2] * nl;
+        const double d22 = cur[F_22] * nl, d20 = cur[F_20] * nl, d31 = cur[F_31] * nl, d3m1 = cur[F_3M1] * nl;
+        const double d3m3 = cur[F_3M3] * nl, d40 = cur[F_40] * nl, d4m2 = cur[F_4M2] * nl, d4m4 = cur[F_4M4] * nl;
+        if (l == lg) {
+          if (live) {
+            const size_t st = (size_t)P.l_size * P.n_int;
+            const size_t o = (size_t)ig * P.n_int + i;
+            P.dgrid[o] = d00; P.dgrid[st + o] = d20; P.dgrid[2 * st + o] = d22; P.dgrid[3 * st + o] = d2m2;
+          }
+          ig++;
+          lg = ig < P.l_size ? P.lgrid[ig] : -1;
+        }
+        const double cl_tt = S.cl[c & 1][0][l - c * LCH], cl_te = S.cl[c & 1][1][l - c * LCH];
+        const double cl_ee = S.cl[c & 1][2][l - c * LCH], cl_bb = S.cl[c & 1][3][l - c * LCH];
+        const double2 lfa = *reinterpret_cast<const double2*>(row + 48), lfb = *reinterpret_cast<const double2*>(row + 50);
+        const double2 lfc = *reinterpret_cast<const double2*>(row + 52), lfd = *reinterpret_cast<const double2*>(row + 54);
+        const double fac = lfa.x, fac1 = lfa.y;
+        const double X_000 = exp(-fac * sigma2);
+        const double X_p000 = -fac * X_000;
+        const double X_220 = lfb.y * X_000;
+        {
+          double lens = X_000 * X_000 * d00 + X_p000 * X_p000 * d1m1 * cgl2 * lfb.x +
+                        (X_p000 * X_p000 * d00 + X_220 * X_220 * d2m2) * cgl2 * cgl2;
+          if (P.subtract_unlensed) lens -= d00;
+          ksi += fac1 * cl_tt * lens;
+        }
+        if (P.has_te | P.has_pol) {
+          const double X_022 = X_000 * (1. + sigma2 * (1. + 0.5 * sigma2));
+          const double X_p022 = -(fac - 1.) * X_022;
+          const double X_242 = lfc.x * X_000;
+          double X_121 = 0., X_132 = 0.;
+          if (P.has_pol) {
+            X_121 = lfc.y * X_000 * (1. + 2. / 3. * sigma2);
+            X_132 = lfd.x * X_000 * (1. + 5. / 3. * sigma2);
+          }
+          if (P.has_te) {
+            double lens = X_022 * X_000 * d20 + cgl2 * X_p000 * lfd.y * (X_121 * d11 + X_132 * d3m1) +
+                          0.5 * cgl2 * cgl2 * ((2. * X_p022 * X_p000 + X_220 * X_220) * d20 + X_220 * X_242 * d4m2);
+            if (P.subtract_unlensed) lens -= d20;
+            ksiX += fac1 * cl_te * lens;
+          }
+          if (P.has_pol) {
+            double lensp = X_022 * X_022 * d22 + 2. * cgl2 * X_132 * X_121 * d31 +
+                           cgl2 * cgl2 * (X_p022 * X_p022 * d22 + X_242 * X_220 * d40);
+            double lensm = X_022 * X_022 * d2m2 + cgl2 * (X_121 * X_121 * d1m1 + X_132 * X_132 * d3m3) +
+                           0.5 * cgl2 * cgl2 * (2. * X_p022 * X_p022 * d2m2 + X_220 * X_220 * d00 + X_242 * X_242 * d4m4);
+            if (P.subtract_unlensed) { lensp -= d22; lensm -= d2m2; }
+            ksip += fac1 * (cl_ee + cl_bb) * lensp;
+            ksim += fac1 * (cl_ee - cl_bb) * lensm;
+          }
+        }
       }
-      if (P.has_pol) {
-        double lensp = X_022 * X_022 * d22 + 2. * cgl2 * X_132 * X_121 * d31 +
-                       cgl2 * cgl2 * (X_p022 * X_p022 * d22 + X_242 * X_220 * d40);
-        double lensm = X_022 * X_022 * d2m2 + cgl2 * (X_121 * X_121 * d1m1 + X_132 * X_132 * d3m3) +
-                       0.5 * cgl2 * cgl2 * (2. * X_p022 * X_p022 * d2m2 + X_220 * X_220 * d00 + X_242 * X_242 * d4m4);
-        if (P.subtract_unlensed) { lensp -= d22; lensm -= d2m2; }
-        ksip += fac1 * (cl_ee[l] + cl_bb[l]) * lensp;
-        ksim += fac1 * (cl_ee[l] - cl_bb[l]) * lensm;
-      }
-    }
-    if (l < lmax) {
+      if (l < lmax) {
 #pragma unroll
-      for (int f = 0; f < NFAM; f++) lens_step(P.coef, lmax, f, l, mu, cur[f], prev[f]);
+        for (int f = 0; f < NFAM; f++) lens_step(row, f, mu, cur[f], prev[f]);
+      }
     }
+    __syncwarp();
   }
-  P.ksi[i] = ksi;
-  P.ksi[P.n_int + i] = ksiX;
-  P.ksi[2 * (size_t)P.n_int + i] = ksip;
-  P.ksi[3 * (size_t)P.n_int + i] = ksim;
+  if (live) {
+    P.ksi[i] = ksi;
+    P.ksi[P.n_int + i] = ksiX;
+    P.ksi[2 * (size_t)P.n_int + i] = ksip;
+    P.ksi[3 * (size_t)P.n_int + i] = ksim;
+  }
 }
 
 // back-transform at the output multipoles (:1152-1230): one CTA per multipole, reduction over the angles
@@ -323,8 +389,8 @@ int clpp_dev_lensing(clpp_ctx* c, const clpp_lensing_desc* ld, clpp_lensing_info
     return CLPP_FAILURE;
   cudaStream_t s = d->stream;
   if (d->lens_lmax != lmax) {
-    if (clpp_dev_reserve(d, &d->lens_coef, (size_t)(NFAM * 4 + 1) * (lmax + 1), err)) return CLPP_FAILURE;
-    lens_coef_kernel<<<(lmax + 128) / 128, 128, 0, s>>>(lmax, d->lens_coef, d->lens_coef + (size_t)NFAM * 4 * (lmax + 1));
+    if (clpp_dev_reserve(d, &d->lens_coef, (size_t)LROW * (lmax + 1), err)) return CLPP_FAILURE;
+    lens_table_kernel<<<(lmax + 128) / 128, 128, 0, s>>>(lmax, d->lens_coef);
     c->launches++;
     d->lens_lmax = lmax;
   }
@@ -335,7 +401,7 @@ int clpp_dev_lensing(clpp_ctx* c, const clpp_lensing_desc* ld, clpp_lensing_info
   P.lmax = lmax; P.num_mu = num_mu; P.n_int = n_int; P.l_size = l_size;
   P.has_te = has_te; P.has_pol = has_pol; P.subtract_unlensed = ld->accurate_lensing ? 0 : 1;
   P.mu = d->lens_stage; P.w8 = P.mu + num_mu; P.cl = P.w8 + n_int;
-  P.coef = d->lens_coef; P.norm = d->lens_coef + (size_t)NFAM * 4 * (lmax + 1);
+  P.tab = d->lens_coef;
   P.lgrid = d->lens_lgrid;
   P.cgl = d->lens_work; P.cgl2 = P.cgl + num_mu; P.ksi = P.cgl2 + num_mu; P.dgrid = P.ksi + 4 * (size_t)n_int;
   P.out = P.dgrid + 4 * (size_t)l_size * n_int;
