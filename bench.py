@@ -125,52 +125,94 @@ def run_gpu(args):
     B = args.batch
     prim_pt = np.ascontiguousarray(prim_k.pk_at_k(a["ref.k"]))
 
-    # ---- device-resident inputs: one context (own stream) per cosmology of the batch
-    ctxs, mods = [], []
-    for b in range(B):
-        ctx = M.Context(local)
-        bg = M.BackgroundModule(inp, ctx)
-        th = M.ThermodynamicsModule(inp, bg)
-        ctxs.append(ctx)
-        mods.append((bg, th))
+    # ---- device-resident inputs: one context (own stream) per cosmology of the batch. Two sets of contexts, used by
+    # alternate steps: the per-cosmology stages of step i (halofit .. P(k), short kernels and host work) run while the
+    # batched perturbation launch of step i+1 already occupies the GPU; everything is drained before the clock stops.
+    NSET = 1 if args.no_pipeline else 2
+    sets = []
+    for s_ in range(NSET):
+        cs_, ms_ = [], []
+        for b in range(B):
+            ctx = M.Context(local)
+            bg = M.BackgroundModule(inp, ctx)
+            th = M.ThermodynamicsModule(inp, bg)
+            cs_.append(ctx)
+            ms_.append((bg, th))
+        sets.append((cs_, ms_))
+    ctxs = [c for cs_, _ in sets for c in cs_]
 
     results = [None] * B
+    import threading
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=min(B, os.cpu_count() or 1))  # host side of independent cosmologies (ctypes drops the GIL)
+    n_workers = min(B, os.cpu_count() or 1)
+    pool = ThreadPoolExecutor(max_workers=n_workers)       # host side of independent cosmologies (ctypes drops the GIL)
+    pool_back = ThreadPoolExecutor(max_workers=n_workers)  # separate queue: step i+1's front must not wait behind step i's back
+    pending = [[] for _ in range(NSET)]
+    step_no = [0]
+    kms = {}
+    kms_lock = threading.Lock()
+
+    def kms_reset():
+        for k_ in ("perturb", "k_spline", "bessel", "los", "spectra", "perturb_tail", "halofit", "lensing"):
+            kms[k_] = 0.0
+
+    kms_reset()
+
+    def kms_add(ctx, keys):
+        t = ctx.kernel_ms()
+        with kms_lock:
+            for k_ in keys:
+                kms[k_] += t[k_]
+
+    def drain(s_=None):
+        for i_ in (range(NSET) if s_ is None else (s_,)):
+            for f in pending[i_]:
+                f.result()
+            pending[i_] = []
 
     def step(inputs=None, pk_=None, nl_=None, fetch=False):
         """One pass of the hot path over the batch: every k mode of the B cosmologies in ONE perturbation
         launch (longest modes first across the batch), then halofit, transfer, spectra, lensing and P(k) per cosmology
-        on its own stream.
+        on its own stream (submitted to worker threads; they overlap the next step's perturbation launch).
         With `inputs` (pinned host arrays) the upstream tables are uploaded first and the public result
         members (sources_, cl_) are read back: the end-to-end variant."""
         x, p_, n_ = (inputs or inp), (pk if pk_ is None else pk_), (nl if nl_ is None else nl_)
+        s_ = step_no[0] % NSET
+        step_no[0] += 1
+        drain(s_)  # this set's previous results have been consumed
+        cs, ms = sets[s_]
 
         def front(b):
             if inputs is not None:  # host -> device copy of this step's inputs
-                bg = M.BackgroundModule(x, ctxs[b])
-                mods[b] = (bg, M.ThermodynamicsModule(x, bg))
-            return M.PerturbationsModule(x, mods[b][0], mods[b][1], solve=False)
+                bg = M.BackgroundModule(x, cs[b])
+                ms[b] = (bg, M.ThermodynamicsModule(x, bg))
+            return M.PerturbationsModule(x, ms[b][0], ms[b][1], solve=False)
 
         pts = list(pool.map(front, range(B)))
         M.PerturbationsModule.solve_batch(pts)
+        for c in cs:
+            kms_add(c, ("perturb", "perturb_tail"))
 
         def back(b):
             nlb = n_
             if halofit_on_device:  # NonlinearModule (halofit) on the device, from the resident delta_m sources
-                nlb = M.NonlinearModule(x, mods[b][0], pts[b], prim_k)
-            tr = M.TransferModule(x, mods[b][0], mods[b][1], pts[b], nlb)
+                nlb = M.NonlinearModule(x, ms[b][0], pts[b], prim_k)
+            tr = M.TransferModule(x, ms[b][0], ms[b][1], pts[b], nlb)
             sp = M.SpectraModule(x, pts[b], M.TabulatedPrimordial(p_), nlb, tr)
             le = M.LensingModule(x, sp)  # lensed TT/TE/EE/BB on the device (SURVEY 8f row 2): the metric's "lensed C_l"
             pk_lin = pts[b].pk_linear(prim_pt)  # linear P(k, z=0) on the perturbation k grid
             out_bytes = sp.cl_[0].nbytes + le.cl_lens_.nbytes + pk_lin.nbytes
             if fetch:  # device -> host: the public members downstream modules read (Nonlinear/Lensing/Output)
-                out_bytes += sum(s_.nbytes for s_ in pts[b].sources_[0])
+                out_bytes += sum(s__.nbytes for s__ in pts[b].sources_[0])
+            kms_add(cs[b], ("k_spline", "bessel", "los", "spectra", "halofit", "lensing"))
             results[b] = (pts[b], tr, sp, out_bytes)
 
-        list(pool.map(back, range(B)))
+        pending[s_] = [pool_back.submit(back, b) for b in range(B)]
+        if NSET == 1:
+            drain(s_)
 
     def barrier():
+        drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -178,6 +220,7 @@ def run_gpu(args):
 
     for _ in range(args.warmup):
         step()
+    drain()
     launches0 = sum(c.launch_count for c in ctxs)
     sampler = ClockSampler(local)
     sampler.start()
@@ -185,14 +228,11 @@ def run_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t0 = time.perf_counter()
-    kms = {"perturb": 0.0, "k_spline": 0.0, "bessel": 0.0, "los": 0.0, "spectra": 0.0, "perturb_tail": 0.0, "halofit": 0.0,
-           "lensing": 0.0}
+    kms_reset()
     for _ in range(args.steps):
         step()
-        for c in ctxs:
-            for k_, v in c.kernel_ms().items():
-                kms[k_] += v
     barrier()
+    kms_timed = dict(kms)  # frozen: the end-to-end passes below keep accumulating into the live dict
     ev1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -246,11 +286,11 @@ def run_gpu(args):
     fp64_peak = ctxs[0].fp64_peak_tflops()
     n_launch = B * args.steps
     # one perturb_kernel launch integrates the whole batch: B cosmologies of algorithmic work each
-    t_perturb = max(kms["perturb"] * 1e-3 / args.steps, 1e-12)
+    t_perturb = max(kms_timed["perturb"] * 1e-3 / args.steps, 1e-12)
     algo = ALGO_FLOP_STAGE1.get(args.config, 1.0e9) * B
     achieved = algo / t_perturb / 1e12
     tr_info = results[0][1].info
-    t_los = max(kms["los"] * 1e-3 / n_launch, 1e-12)
+    t_los = max(kms_timed["los"] * 1e-3 / n_launch, 1e-12)
     sec_achieved = ALGO_FLOP_PER_LOS_POINT * 1.5e8 / t_los / 1e12
     roofline = {"kernel": "perturb_kernel", "bound": "fp64-vector (latency-bound in practice; neither hbm nor tensor)",
                 "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
@@ -258,8 +298,8 @@ def run_gpu(args):
                                "its hbm_gbs=%s bf16_tflops=%s are %s)" % (peaks.get("hbm_gbs"), peaks.get("bf16_tflops"), peaks_kind),
                 "traffic": None,
                 "algorithmic_flop_per_launch": algo,
-                "kernel_ms_per_step": {k_: v / args.steps for k_, v in kms.items()},
-                "kernel_share_of_step": {k_: v * 1e-3 / elapsed for k_, v in kms.items()},
+                "kernel_ms_per_step": {k_: v / args.steps for k_, v in kms_timed.items()},
+                "kernel_share_of_step": {k_: v * 1e-3 / elapsed for k_, v in kms_timed.items()},
                 "secondary": {"kernel": "los_kernel", "bound": "fp64-vector", "achieved": sec_achieved,
                               "peak": fp64_peak, "unit": "TFLOP/s", "frac": sec_achieved / fp64_peak}}
 
@@ -378,6 +418,8 @@ def main():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("CLPP_BENCH_BATCH", 128)),
                     help="cosmologies per GPU and per step (one batched perturbation launch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="one set of contexts: the per-cosmology stages of a step finish before the next step starts")
     ap.add_argument("--halofit", default="device", choices=["device", "input"],
                     help="config with halofit: run it on the device (default) or take the reference's table as input")
     args = ap.parse_args()

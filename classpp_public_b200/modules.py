@@ -232,21 +232,42 @@ class PerturbationsModule:
         self.k_ = [k]
         self.tau_sampling_ = tau
         self._sources = None
-        self.kstat_ = None
+        self._kstat = None
         if solve:
             lo, hi = k_range if k_range is not None else (0, i.k_size)
             ctx.check(L.clpp_perturb_solve(ctx.handle, int(lo), int(hi), ctx.err))
             self._fetch_kstat()
 
     def _fetch_kstat(self):
-        i = self.info
-        ks = (capi.KStat * i.k_size)()
-        self.ctx._lib.clpp_perturb_get_kstat(self.ctx.handle, ks)
-        self.kstat_ = np.array([[s.steps, s.failed, s.fevals, s.jacobians, s.factorizations, s.solves,
-                                 s.intervals, s.status] for s in ks])
-        self.kprofile_ = np.array([[list(s.iv_neq), list(s.iv_steps), list(s.iv_cycles)] for s in ks])
-        self.ksections_ = np.array([list(s.prof) for s in ks])
+        """Work counters of the last solve are fetched lazily (first access of kstat_ / kprofile_ / ksections_)."""
+        self._kstat = None
         self._sources = None
+
+    def _kstat_table(self):
+        if self._kstat is None:
+            ks = (capi.KStat * self.info.k_size)()
+            self.ctx._lib.clpp_perturb_get_kstat(self.ctx.handle, ks)
+            self._kstat = np.frombuffer(ks, dtype=np.dtype(capi.KStat)).copy()
+        return self._kstat
+
+    @property
+    def kstat_(self):
+        """[k][steps, failed, fevals, jacobians, factorizations, solves, intervals, status] (evolver statistics)"""
+        t = self._kstat_table()
+        return np.stack([t[n] for n in ("steps", "failed", "fevals", "jacobians", "factorizations", "solves",
+                                        "intervals", "status")], axis=1).astype(np.int64)
+
+    @property
+    def kprofile_(self):
+        """[k][neq | steps | cycles][interval]: per approximation interval of every mode"""
+        t = self._kstat_table()
+        return np.stack([t["iv_neq"].astype(np.int64), t["iv_steps"].astype(np.int64), t["iv_cycles"].astype(np.int64)],
+                        axis=1)
+
+    @property
+    def ksections_(self):
+        """[k][72]: cycles per code section (only filled by a -DPT_PROF build)"""
+        return self._kstat_table()["prof"].astype(np.int64)
 
     @staticmethod
     def solve_batch(modules):
