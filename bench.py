@@ -97,6 +97,10 @@ def hot_path(M, inp, ctx, bg, th, pk, nl, fetch_tables=False):
     return pt, tr, sp, out_bytes
 
 
+# DRAM bytes one batched perturbation launch moves per cosmology (ncu, see roofline.traffic_source)
+TRAFFIC_BYTES_PER_COSMOLOGY = {"planck18": 36.44e6}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -143,12 +147,7 @@ def run_gpu(args):
 
     results = [None] * B
     import threading
-    from concurrent.futures import ThreadPoolExecutor
-    n_workers = min(B, os.cpu_count() or 1)
-    pool = ThreadPoolExecutor(max_workers=n_workers)       # host side of independent cosmologies (ctypes drops the GIL)
-    pool_back = ThreadPoolExecutor(max_workers=n_workers)  # separate queue: step i+1's front must not wait behind step i's back
-    pending = [[] for _ in range(NSET)]
-    step_no = [0]
+    from classpp_public_b200.sweep import SweepPipeline
     kms = {}
     kms_lock = threading.Lock()
 
@@ -164,52 +163,46 @@ def run_gpu(args):
             for k_ in keys:
                 kms[k_] += t[k_]
 
-    def drain(s_=None):
-        for i_ in (range(NSET) if s_ is None else (s_,)):
-            for f in pending[i_]:
-                f.result()
-            pending[i_] = []
-
-    def step(inputs=None, pk_=None, nl_=None, fetch=False):
-        """One pass of the hot path over the batch: every k mode of the B cosmologies in ONE perturbation
-        launch (longest modes first across the batch), then halofit, transfer, spectra, lensing and P(k) per cosmology
-        on its own stream (submitted to worker threads; they overlap the next step's perturbation launch).
-        With `inputs` (pinned host arrays) the upstream tables are uploaded first and the public result
-        members (sources_, cl_) are read back: the end-to-end variant."""
-        x, p_, n_ = (inputs or inp), (pk if pk_ is None else pk_), (nl if nl_ is None else nl_)
-        s_ = step_no[0] % NSET
-        step_no[0] += 1
-        drain(s_)  # this set's previous results have been consumed
+    # One pass of the hot path over a batch ("step"): every k mode of the B cosmologies in ONE perturbation launch
+    # (longest modes first across the batch), then halofit, transfer, spectra, lensing and P(k) per cosmology on its own
+    # stream. With `inputs` (pinned host arrays) the upstream tables are uploaded first and the public result members
+    # (sources_, cl_, cl_lens_, P(k)) are read back: the end-to-end variant.
+    def front(s_, b, inputs, p_, n_, fetch):
         cs, ms = sets[s_]
+        if inputs is not None:  # host -> device copy of this step's inputs
+            bg = M.BackgroundModule(inputs, cs[b])
+            ms[b] = (bg, M.ThermodynamicsModule(inputs, bg))
+        return M.PerturbationsModule(inputs or inp, ms[b][0], ms[b][1], solve=False)
 
-        def front(b):
-            if inputs is not None:  # host -> device copy of this step's inputs
-                bg = M.BackgroundModule(x, cs[b])
-                ms[b] = (bg, M.ThermodynamicsModule(x, bg))
-            return M.PerturbationsModule(x, ms[b][0], ms[b][1], solve=False)
-
-        pts = list(pool.map(front, range(B)))
-        M.PerturbationsModule.solve_batch(pts)
-        for c in cs:
+    def on_solved(s_):
+        for c in sets[s_][0]:
             kms_add(c, ("perturb", "perturb_tail"))
 
-        def back(b):
-            nlb = n_
-            if halofit_on_device:  # NonlinearModule (halofit) on the device, from the resident delta_m sources
-                nlb = M.NonlinearModule(x, ms[b][0], pts[b], prim_k)
-            tr = M.TransferModule(x, ms[b][0], ms[b][1], pts[b], nlb)
-            sp = M.SpectraModule(x, pts[b], M.TabulatedPrimordial(p_), nlb, tr)
-            le = M.LensingModule(x, sp)  # lensed TT/TE/EE/BB on the device (SURVEY 8f row 2): the metric's "lensed C_l"
-            pk_lin = pts[b].pk_linear(prim_pt)  # linear P(k, z=0) on the perturbation k grid
-            out_bytes = sp.cl_[0].nbytes + le.cl_lens_.nbytes + pk_lin.nbytes
-            if fetch:  # device -> host: the public members downstream modules read (Nonlinear/Lensing/Output)
-                out_bytes += sum(s__.nbytes for s__ in pts[b].sources_[0])
-            kms_add(cs[b], ("k_spline", "bessel", "los", "spectra", "halofit", "lensing"))
-            results[b] = (pts[b], tr, sp, out_bytes)
+    def back(s_, b, pt, inputs, p_, n_, fetch):
+        cs, ms = sets[s_]
+        x = inputs or inp
+        nlb = n_
+        if halofit_on_device:  # NonlinearModule (halofit) on the device, from the resident delta_m sources
+            nlb = M.NonlinearModule(x, ms[b][0], pt, prim_k)
+        tr = M.TransferModule(x, ms[b][0], ms[b][1], pt, nlb)
+        sp = M.SpectraModule(x, pt, M.TabulatedPrimordial(p_), nlb, tr)
+        le = M.LensingModule(x, sp)  # lensed TT/TE/EE/BB on the device: the metric's "lensed C_l"
+        pk_lin = pt.pk_linear(prim_pt)  # linear P(k, z=0) on the perturbation k grid
+        out_bytes = sp.cl_[0].nbytes + le.cl_lens_.nbytes + pk_lin.nbytes
+        if fetch:  # device -> host: the public members downstream modules read (Nonlinear/Lensing/Output)
+            out_bytes += sum(s__.nbytes for s__ in pt.sources_[0])
+        kms_add(cs[b], ("k_spline", "bessel", "los", "spectra", "halofit", "lensing"))
+        results[b] = (pt, tr, sp, out_bytes)
+        return out_bytes
 
-        pending[s_] = [pool_back.submit(back, b) for b in range(B)]
+    pipe = SweepPipeline(B, front, back, n_sets=NSET, on_solved=on_solved)
+
+    def step(inputs=None, pk_=None, nl_=None, fetch=False):
+        pipe.submit(inputs, pk if pk_ is None else pk_, nl if nl_ is None else nl_, fetch)
         if NSET == 1:
-            drain(s_)
+            pipe.drain()
+
+    drain = pipe.drain
 
     def barrier():
         drain()
@@ -218,8 +211,12 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for w_ in range(args.warmup):
         step()
+        if w_ == 0:  # the first launch runs alone: its duration sets the stagger between overlapping launches
+            drain()
+            if NSET > 1 and args.stagger >= 0:
+                pipe.stagger = args.stagger * pipe.solve_seconds[-1]
     drain()
     launches0 = sum(c.launch_count for c in ctxs)
     sampler = ClockSampler(local)
@@ -232,6 +229,8 @@ def run_gpu(args):
     for _ in range(args.steps):
         step()
     barrier()
+    if os.environ.get("CLPP_VERBOSE"):
+        print("launch log (set, start, end):", [(s_, round(a_ - t0, 2), round(b_ - t0, 2)) for s_, a_, b_ in pipe.launch_log[-args.steps:]], file=sys.stderr)
     kms_timed = dict(kms)  # frozen: the end-to-end passes below keep accumulating into the live dict
     ev1.record()
     torch.cuda.synchronize()
@@ -286,7 +285,9 @@ def run_gpu(args):
     fp64_peak = ctxs[0].fp64_peak_tflops()
     n_launch = B * args.steps
     # one perturb_kernel launch integrates the whole batch: B cosmologies of algorithmic work each
-    t_perturb = max(kms_timed["perturb"] * 1e-3 / args.steps, 1e-12)
+    # overlapping launches (pipeline): the device time the perturbation kernels occupy is at most the timed region itself
+    perturb_busy = min(kms_timed["perturb"] * 1e-3, elapsed)
+    t_perturb = max(perturb_busy / args.steps, 1e-12)
     algo = ALGO_FLOP_STAGE1.get(args.config, 1.0e9) * B
     achieved = algo / t_perturb / 1e12
     tr_info = results[0][1].info
@@ -296,8 +297,15 @@ def run_gpu(args):
                 "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "peak_source": "DFMA microbenchmark run live in bench.py (MEASURED_PEAKS.json has no FP64 entry; "
                                "its hbm_gbs=%s bf16_tflops=%s are %s)" % (peaks.get("hbm_gbs"), peaks.get("bf16_tflops"), peaks_kind),
-                "traffic": None,
+                "traffic": TRAFFIC_BYTES_PER_COSMOLOGY.get(args.config, 0.0) * B or None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of perturb_kernel + perturb_tail_kernel from the ncu "
+                                  "launch list profiles/r01_launches_v3_bench_b16.csv (bench.py --batch 16: 36.4 MB per cosmology "
+                                  "per step, scaled to this batch); algorithmic: 24.3 MB of S(k,tau) written once + 6 MB of tables",
                 "algorithmic_flop_per_launch": algo,
+                "launch_duration_ms_avg": kms_timed["perturb"] / args.steps,
+                "launches_in_flight_avg": kms_timed["perturb"] * 1e-3 / elapsed,
+                "note": "achieved = algorithmic flop of the K launches / device time they occupy (= min(sum of launch "
+                        "durations, timed region): launches of consecutive steps overlap on purpose)",
                 "kernel_ms_per_step": {k_: v / args.steps for k_, v in kms_timed.items()},
                 "kernel_share_of_step": {k_: v * 1e-3 / elapsed for k_, v in kms_timed.items()},
                 "secondary": {"kernel": "los_kernel", "bound": "fp64-vector", "achieved": sec_achieved,
@@ -316,6 +324,10 @@ def run_gpu(args):
                    "scope": "per cosmology: perturbations -> halofit -> transfer -> spectra -> lensing (fast mode) -> linear P(k)",
                    "k_modes": int(results[0][0].info.k_size), "tau_samples": int(results[0][0].info.tau_size),
                    "q_values": int(tr_info.q_size), "l_values": int(tr_info.l_size),
+                   "pipeline": ("%d context sets: the per-cosmology stages of step i run under the batched launch of step "
+                                "i+1 (%s); all drained before the clock stops" %
+                                (NSET, "launches overlap, %.2f x solo duration apart" % args.stagger if args.stagger >= 0
+                                 else "one batched launch at a time")) if NSET > 1 else "off",
                    "parallelism": "independent cosmologies per GPU (replicas, no data-path collective); per GPU all k modes "
                                   "of the batch in one batched launch: long-tail modes on a high-priority stream, the bulk in "
                                   "chunks on low-priority streams, generic kernel -> radiation-streaming tail kernel",
@@ -418,6 +430,9 @@ def main():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("CLPP_BENCH_BATCH", 128)),
                     help="cosmologies per GPU and per step (one batched perturbation launch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stagger", type=float, default=-1.0,
+                    help="pipeline: >= 0 lets the batched launches of consecutive steps overlap, this fraction of a solo "
+                         "launch duration apart (default: one launch at a time, only the per-cosmology stages overlap it)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="one set of contexts: the per-cosmology stages of a step finish before the next step starts")
     ap.add_argument("--halofit", default="device", choices=["device", "input"],

@@ -92,27 +92,39 @@ struct PtParams {
   int evolver;        // 0 = rk (Cash-Karp), 1 = ndf15
   double rk_stepsize; // perturb_integration_stepsize (rk only)
   int force_generic;  // developer/test switch: integrate every interval with the generic shared-memory NDF
+  int wpc, wstride;   // warps (k modes) per CTA; doubles of shared memory per warp
   int neq_max, np, nh_max, ldh;
   int o_mode, o_hubtmp, o_nw, o_i2l1, n_i2l1, o_tabc, ncol, o_vec, o_sinv, o_int;
 };
 
-extern __shared__ double smem[];
+extern __shared__ double smem_all[];
+// A CTA is a COHORT of P.wpc warps (1..PT_MAX_WPC), one k mode per warp, each with its own shared-memory region.
+// The warps of a cohort integrate similar modes (adjacent in the cost-sorted issue order: the same k of neighbouring
+// cosmologies of a batch) and meet at a CTA barrier at the top of every step, so that they walk through the same code at
+// the same time: the per-step code footprint (~70 KB) exceeds the 32 KB instruction cache, and instruction fetch, not
+// issue slots, is what saturates an SM (profiles/r01_perturb_kernel_loaded_v3_footprint.txt).
+#define PT_MAX_WPC 8
+#define PT_LANE ((int)(threadIdx.x & 31))
+#define PT_WARP ((int)(threadIdx.x >> 5))
+#define PT_SLOT(P) ((int)(blockIdx.x * (P).wpc) + PT_WARP)
+#define SMEM(P) (smem_all + (size_t)PT_WARP * (P).wstride)
+#define PT_COHORT_SYNC(P) do { if ((P).wpc > 1) asm volatile("bar.sync 0;" ::: "memory"); } while (0)
 // every shared-memory access goes through these, so that the compiler sees the shared address
 // space (LDS/STS with 32-bit addresses) instead of generic pointers
-#define s_pvb(P) (smem)
-#define s_pvt(P) (smem + 32)
-#define s_hubtmp(P) (smem + (P).o_hubtmp)
-#define s_nw(P) (smem + (P).o_nw)
-#define s_vec(P, slot) (smem + ((P).o_vec + (slot) * (P).np))
-#define s_sinv(P) (smem + (P).o_sinv)
+#define s_pvb(P) (SMEM(P))
+#define s_pvt(P) (SMEM(P) + 32)
+#define s_hubtmp(P) (SMEM(P) + (P).o_hubtmp)
+#define s_nw(P) (SMEM(P) + (P).o_nw)
+#define s_vec(P, slot) (SMEM(P) + ((P).o_vec + (slot) * (P).np))
+#define s_sinv(P) (SMEM(P) + (P).o_sinv)
 // bracketing rows of table `tab` (0 background, 1 thermodynamics), cache set `set`: [4][ncol] = y0, y1, dd0, dd1
-#define s_tabc(P, tab, set) (smem + (P).o_tabc + (((set) * 2 + (tab)) * 4) * (P).ncol)
-#define s_i2l1(P) (smem + (P).o_i2l1)
-#define s_hub_idx(P) ((int*)(smem + (P).o_int))
-#define s_piv(P) ((int*)(smem + (P).o_int) + (P).nh_max)
-#define s_ch_start(P) ((int*)(smem + (P).o_int) + 2 * (P).nh_max)
-#define s_ch_len(P) ((int*)(smem + (P).o_int) + 2 * (P).nh_max + PT_MAX_CHAINS)
-#define s_ch_rootslot(P) ((int*)(smem + (P).o_int) + 2 * (P).nh_max + 2 * PT_MAX_CHAINS)
+#define s_tabc(P, tab, set) (SMEM(P) + (P).o_tabc + (((set) * 2 + (tab)) * 4) * (P).ncol)
+#define s_i2l1(P) (SMEM(P) + (P).o_i2l1)
+#define s_hub_idx(P) ((int*)(SMEM(P) + (P).o_int))
+#define s_piv(P) ((int*)(SMEM(P) + (P).o_int) + (P).nh_max)
+#define s_ch_start(P) ((int*)(SMEM(P) + (P).o_int) + 2 * (P).nh_max)
+#define s_ch_len(P) ((int*)(SMEM(P) + (P).o_int) + 2 * (P).nh_max + PT_MAX_CHAINS)
+#define s_ch_rootslot(P) ((int*)(SMEM(P) + (P).o_int) + 2 * (P).nh_max + 2 * PT_MAX_CHAINS)
 
 // NDF constants (evolver_ndf15.cpp:86-100), indexed by order-1
 __constant__ double c_G[5] = {1.0, 3.0 / 2.0, 11.0 / 6.0, 25.0 / 12.0, 137.0 / 60.0};
@@ -230,7 +242,7 @@ __device__ __forceinline__ int locate_closeby(const double* __restrict__ X, int 
 #ifdef PT_PROF
 #define PROF_DECL long long prof_t0_
 #define PROF_BEGIN() (prof_t0_ = clock64())
-#define PROF_END(slot) do { if (threadIdx.x == 0) M.prof[slot] += clock64() - prof_t0_; } while (0)
+#define PROF_END(slot) do { if (PT_LANE == 0) M.prof[slot] += clock64() - prof_t0_; } while (0)
 #else
 #define PROF_DECL
 #define PROF_BEGIN()
@@ -270,7 +282,7 @@ struct Mode {
   Stat st;
   int ik, need_nw, nh, nch, status, next;
 };
-#define MODE(P) (*(Mode*)(smem + (P).o_mode))
+#define MODE(P) (*(Mode*)(SMEM(P) + (P).o_mode))
 
 
 
@@ -284,7 +296,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 
 __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby, int set) {
   Mode& M = MODE(P);
-  const int lane = (int)threadIdx.x;
+  const int lane = PT_LANE;
   double* pvb = s_pvb(P);
   double* pvt = s_pvt(P);
   PROF_DECL;
@@ -541,7 +553,7 @@ __device__ __noinline__ void make_structure(const PtParams& P) {
   Mode& M = MODE(P);
   const Layout& L = M.L;
   const Approx& ap = M.ap;
-  if ((int)threadIdx.x == 0) {
+  if (PT_LANE == 0) {
     int nch = 0;
     if (L.l3_g >= 0) {
       s_ch_start(P)[nch] = L.l3_g; s_ch_len(P)[nch] = P.l_max_g - 2; nch++;
@@ -591,7 +603,7 @@ __device__ __noinline__ void rhs_apply(const PtParams& P, int slot_y, int slot_d
   const Layout& L = M.L;
   const Approx ap = M.ap;
   const Env& e = M.e;
-  const int lane = threadIdx.x;
+  const int lane = PT_LANE;
   const double k = M.k, k2 = M.k2, ik2 = M.inv_k2;
   const double* pvb = s_pvb(P);
   const double* pvt = s_pvt(P);
@@ -882,7 +894,7 @@ __device__ __noinline__ void write_sources(const PtParams& P, double tau, int sl
   const double* dy = s_vec(P, slot_dy);
   env_at(P, tau, true, 1);
   rhs_apply(P, slot_y, -1, 1);
-  if ((int)threadIdx.x != 0) return;
+  if (PT_LANE != 0) return;
   const Layout& L = M.L;
   const Approx& ap = M.ap;
   const Env& e = M.e;
@@ -926,7 +938,7 @@ __device__ __noinline__ void write_sources(const PtParams& P, double tau, int sl
 // (the environment M.e must be set at tau)
 __device__ __noinline__ void jacobian(const PtParams& P) {
   Mode& M = MODE(P);
-  const int n = M.L.neq, lane = (int)threadIdx.x, nh = M.nh, nch = M.nch;
+  const int n = M.L.neq, lane = PT_LANE, nh = M.nh, nch = M.nch;
   double* e_j = s_vec(P, V_TMP);
   double* col = s_vec(P, V_DEL);
   double *Jd = s_vec(P, V_JD), *Jl = s_vec(P, V_JL), *Ju = s_vec(P, V_JU);
@@ -966,8 +978,8 @@ __device__ __noinline__ void jacobian(const PtParams& P) {
       __syncwarp();
     }
   }
-  if (threadIdx.x == 0) M.st.jacobians++;
-  if (threadIdx.x == 0) M.st.fevals += nh + (nch > 0 ? 3 : 0);
+  if (PT_LANE == 0) M.st.jacobians++;
+  if (PT_LANE == 0) M.st.fevals += nh + (nch > 0 ? 3 : 0);
 }
 
 // Gauss-Jordan inversion with partial pivoting of an n x n matrix held one row per lane in registers
@@ -1033,7 +1045,7 @@ __device__ __forceinline__ void hub_inverse_rows(const PtParams& P, Mode& M, dou
 // complement on the hub block, explicit inverse of the hub block (Gauss-Jordan, partial pivoting).
 __device__ __noinline__ void factor(const PtParams& P, double c) {
   Mode& M = MODE(P);
-  const int lane = (int)threadIdx.x, nh = M.nh, nch = M.nch, ldh = P.ldh;
+  const int lane = PT_LANE, nh = M.nh, nch = M.nch, ldh = P.ldh;
   const double *Jd = s_vec(P, V_JD), *Jl = s_vec(P, V_JL), *Ju = s_vec(P, V_JU);
   double *ip = s_vec(P, V_IP), *mu = s_vec(P, V_MU), *lo = s_vec(P, V_LO);
   double* W = s_sinv(P);
@@ -1125,13 +1137,13 @@ __device__ __noinline__ void factor(const PtParams& P, double c) {
       __syncwarp();
     }
   }
-  if (threadIdx.x == 0) M.st.factorizations++;
+  if (PT_LANE == 0) M.st.factorizations++;
 }
 
 // solve A x = b in place (b in shared memory) with the factors of `factor`
 __device__ __forceinline__ void solve(const PtParams& P, double* __restrict__ b) {
   Mode& M = MODE(P);
-  const int lane = (int)threadIdx.x, nh = M.nh, nch = M.nch, ldh = P.ldh;
+  const int lane = PT_LANE, nh = M.nh, nch = M.nch, ldh = P.ldh;
   const double *ip = s_vec(P, V_IP), *mu = s_vec(P, V_MU), *lo = s_vec(P, V_LO);
   if (nch > 0) {
     if (lane < nch) {
@@ -1191,7 +1203,7 @@ __device__ __forceinline__ void solve(const PtParams& P, double* __restrict__ b)
     }
     __syncwarp();
   }
-  if (threadIdx.x == 0) M.st.solves++;
+  if (PT_LANE == 0) M.st.solves++;
 }
 
 // rescale the backward differences when the step changes by the factor r (k = current order)
@@ -1199,8 +1211,8 @@ __device__ __noinline__ void adjust_stepsize(const PtParams& P, double r, int k)
   Mode& M = MODE(P);
   // RU = R(r) * U; lane t < 25 computes entry (t/5, t%5) and parks it in shared memory
   double* RU = s_hubtmp(P);  // >= 32 doubles
-  if ((int)threadIdx.x < 25) {
-    const int ii = (int)threadIdx.x / 5, jj = (int)threadIdx.x % 5;
+  if (PT_LANE < 25) {
+    const int ii = PT_LANE / 5, jj = PT_LANE % 5;
     double s = 0.;
 #pragma unroll
     for (int kk = 0; kk < 5; kk++) {
@@ -1209,12 +1221,12 @@ __device__ __noinline__ void adjust_stepsize(const PtParams& P, double r, int k)
       for (int mm = 1; mm <= ii + 1; mm++) Rv *= ((mm - 1) - (kk + 1) * r) / mm;
       s += Rv * c_U[kk][jj];
     }
-    RU[(int)threadIdx.x] = s;
+    RU[PT_LANE] = s;
   }
   __syncwarp();
   const int n = M.L.neq, np = P.np;
   double* dif = s_vec(P, V_DIF0);
-  for (int i = (int)threadIdx.x; i < n; i += 32) {
+  for (int i = PT_LANE; i < n; i += 32) {
     double row[5];
 #pragma unroll
     for (int kk = 0; kk < 5; kk++) row[kk] = (kk < k) ? dif[kk * np + i] : 0.;
@@ -1240,7 +1252,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
   const double abstol = 1e-15, eps = 1e-16, threshold = abstol;
   const int maxit = 4, maxk = 5;
   const double rtol = P.rtol;
-  const int n = M.L.neq, np = P.np, lane = (int)threadIdx.x;
+  const int n = M.L.neq, np = P.np, lane = PT_LANE;
   double *y = s_vec(P, V_Y), *ynew = s_vec(P, V_YNEW), *f0 = s_vec(P, V_F0), *pred = s_vec(P, V_PRED), *psi = s_vec(P, V_PSI),
          *difkp1 = s_vec(P, V_DIFKP1), *del = s_vec(P, V_DEL), *invwt = s_vec(P, V_INVWT), *dif = s_vec(P, V_DIF0);
   const double* t_vec = M.C->tau;
@@ -1256,7 +1268,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
   double t = t0, tnew = t0;
   env_at(P, t0, true, 0);
   rhs_apply(P, V_Y, V_F0, 0);
-  if (threadIdx.x == 0) M.st.fevals++;
+  if (PT_LANE == 0) M.st.fevals++;
   const double hmax = (tfinal - t0) / 10.0;
   jacobian(P);
   bool Jcurrent = true;
@@ -1276,11 +1288,11 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
   {
     // J*f0 = f(t0, f0): the system is linear and homogeneous
     rhs_apply(P, V_F0, V_PSI, 0);
-    if (threadIdx.x == 0) M.st.fevals++;
+    if (PT_LANE == 0) M.st.fevals++;
     const double tdel = (t + fmin(sqrt(eps) * fmax(fabs(t), fabs(t + h)), absh)) - t;
     env_at(P, t + tdel, true, 0);
     rhs_apply(P, V_Y, V_DEL, 0);  // f(t+tdel, y)
-    if (threadIdx.x == 0) M.st.fevals++;
+    if (PT_LANE == 0) M.st.fevals++;
     rh = 0.0;
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) {
@@ -1307,6 +1319,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
   double rate = 0., oldnrm = 0., err = 0.;
 
   while (!done) {
+    PT_COHORT_SYNC(P);
     hmin = P.hmin_allowed;
     absh = fmin(hmax, fmax(hmin, absh));
     if (fabs(absh - hmin) < 100 * eps) {
@@ -1372,7 +1385,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
           rhs_apply(P, V_YNEW, V_F0, 0);
           PROF_END(PF_RHS);
           if (!M.ap.tca_off) M.tca_shear_last = M.m.tca_shear_g;
-          if (threadIdx.x == 0) M.st.fevals++;
+          if (PT_LANE == 0) M.st.fevals++;
           PROF_BEGIN();
 #pragma unroll 1
           for (int i = lane; i < n; i += 32) del[i] = hinvGak * f0[i] - (psi[i] + difkp1[i]);
@@ -1414,11 +1427,11 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
           oldnrm = newnrm;
         }
         if (tooslow) {
-          if (threadIdx.x == 0) M.st.failed++;
+          if (PT_LANE == 0) M.st.failed++;
           if (!Jcurrent) {
             env_at(P, t, true, 0);
             rhs_apply(P, V_Y, V_F0, 0);
-            if (threadIdx.x == 0) M.st.fevals++;
+            if (PT_LANE == 0) M.st.fevals++;
             jacobian(P);
             Jcurrent = true;
           } else if (absh <= hmin) {
@@ -1443,7 +1456,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
       for (int i = lane; i < n; i += 32) err = fmax(err, fabs(difkp1[i] * invwt[i]));
       err = wmax(err) * c_erconst[k - 1];
       if (err > rtol) {
-        if (threadIdx.x == 0) M.st.failed++;
+        if (PT_LANE == 0) M.st.failed++;
         if (absh <= hmin) {
           M.status = 2;
           return false;
@@ -1478,7 +1491,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
         break;
       }
     }
-    if (threadIdx.x == 0) M.st.steps++;
+    if (PT_LANE == 0) M.st.steps++;
     PROF_BEGIN();
     // update the difference array
 #pragma unroll 1
@@ -1575,7 +1588,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
   env_at(P, tnew, true, 0);
   rhs_apply(P, V_Y, V_F0, 0);
   if (!M.ap.tca_off) M.tca_shear_last = M.m.tca_shear_g;
-  if (threadIdx.x == 0) M.st.fevals++;
+  if (PT_LANE == 0) M.st.fevals++;
   M.next = next;
   return true;
 }
@@ -1600,7 +1613,7 @@ __device__ __noinline__ bool ndf15_hub(const PtParams& P, double t0, double tfin
   const double abstol = 1e-15, eps = 1e-16, threshold = abstol;
   const int maxit = 4, maxk = 5;
   const double rtol = P.rtol;
-  const int n = M.L.neq, lane = threadIdx.x, ldh = P.ldh;
+  const int n = M.L.neq, lane = PT_LANE, ldh = P.ldh;
   const bool act = lane < n;
   const int li = act ? lane : 0;  // safe shared-memory index for idle lanes
   double *YX = s_vec(P, V_YNEW), *F = s_vec(P, V_F0), *B = s_vec(P, V_DEL), *Ys = s_vec(P, V_Y);
@@ -1686,6 +1699,7 @@ __device__ __noinline__ bool ndf15_hub(const PtParams& P, double t0, double tfin
   };
 
   while (!done) {
+    PT_COHORT_SYNC(P);
     hmin = P.hmin_allowed;
     absh = fmin(hmax, fmax(hmin, absh));
     if (fabs(absh - hmin) < 100 * eps) {
@@ -2047,7 +2061,7 @@ __device__ __noinline__ bool ndf15_rsa(const PtParams& P, double t0, double tfin
   const double abstol = 1e-15, eps = 1e-16, threshold = abstol;
   const int maxit = 4, maxk = 5;
   const double rtol = P.rtol;
-  const int n = M.L.neq, lane = threadIdx.x, n_ncdm = P.has_ncdm ? P.N_ncdm : 0;
+  const int n = M.L.neq, lane = PT_LANE, n_ncdm = P.has_ncdm ? P.N_ncdm : 0;
   const bool act = lane < n;
   const int li = act ? lane : 0;
   const double k2 = M.k2, ik2 = M.inv_k2;
@@ -2158,6 +2172,7 @@ __device__ __noinline__ bool ndf15_rsa(const PtParams& P, double t0, double tfin
   };
 
   while (!done) {
+    PT_COHORT_SYNC(P);
     hmin = P.hmin_allowed;
     absh = fmin(hmax, fmax(hmin, absh));
     if (fabs(absh - hmin) < 100 * eps) {
@@ -2407,7 +2422,7 @@ __device__ __noinline__ bool ndf15_rsa(const PtParams& P, double t0, double tfin
 // on the path, with the same driver logic: every sample time of the source grid is hit exactly.
 __device__ __noinline__ bool rk_interval(const PtParams& P, double t0, double tfinal) {
   Mode& M = MODE(P);
-  const int n = M.L.neq, lane = threadIdx.x;
+  const int n = M.L.neq, lane = PT_LANE;
   const double eps_tol = P.rtol;
   const double SAFETY = 0.9, PGROW = -0.2, PSHRNK = -0.25, ERRCON = 1.89e-4, TINY = 1.0e-30;
   const int MAXSTP = 100000;
@@ -2542,7 +2557,7 @@ __device__ __noinline__ void initial_conditions(const PtParams& P, double tau) {
   env_at(P, tau, false, 0);
   const Env& e = M.e;
   const Layout& L = M.L;
-  const int lane = (int)threadIdx.x;
+  const int lane = PT_LANE;
   const double k = M.k, a = e.a;
   double* y = s_vec(P, V_Y);
   const double* pvb0 = s_pvb(P);
@@ -2610,7 +2625,7 @@ __device__ __noinline__ void remap_state(const PtParams& P) {
   const Layout& Ln = M.L;
   const Approx& apo = M.apprev;
   const Approx& apn = M.ap;
-  const int lane = (int)threadIdx.x;
+  const int lane = PT_LANE;
   double* yo = s_vec(P, V_Y);
   double* yn = s_vec(P, V_YNEW);
   const double k = M.k;
@@ -2693,9 +2708,9 @@ __device__ __noinline__ void remap_state(const PtParams& P) {
 // common set-up of the shared-memory mode state
 __device__ __forceinline__ void mode_init(const PtParams& P, const PtCosmo* C, int ik) {
   Mode& M = MODE(P);
-  const int lane = (int)threadIdx.x;
+  const int lane = PT_LANE;
   if (lane == 0) {
-    M.Jhh = P.hub_jac + (size_t)blockIdx.x * P.nh_max * P.nh_max;
+    M.Jhh = P.hub_jac + (size_t)PT_SLOT(P) * P.nh_max * P.nh_max;
     M.C = C;
     M.ik = ik;
     M.k = C->k[ik];
@@ -2728,7 +2743,7 @@ __device__ __forceinline__ void mode_init(const PtParams& P, const PtCosmo* C, i
 // end of a mode: zero-fill the samples that were not reached (failure only) and publish the counters
 __device__ __forceinline__ void mode_finish(const PtParams& P, const PtCosmo* C, int ik, int n_int, int status, double tau_ini) {
   Mode& M = MODE(P);
-  if (threadIdx.x == 0) {
+  if (PT_LANE == 0) {
     const int tau_size = C->tau_size;
     const size_t stride_tp = (size_t)C->k_size * tau_size;
     double* out = C->sources + (size_t)ik * tau_size;
@@ -2750,11 +2765,11 @@ enum { TL_VALID = 0, TL_T0, TL_TF, TL_NEXT, TL_IV, TL_NINT, TL_TAU_INI, TL_FLAGS
 #ifndef PT_MIN_BLOCKS
 #define PT_MIN_BLOCKS 8
 #endif
-__global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid_constant__ PtParams P) {
-  if ((int)blockIdx.x >= P.n_modes) return;
+__global__ void __launch_bounds__(32 * PT_MAX_WPC, 1) perturb_kernel(const __grid_constant__ PtParams P) {
+  if (PT_SLOT(P) >= P.n_modes) return;
   Mode& M = MODE(P);
-  const int lane = (int)threadIdx.x;
-  const int2 md = P.modes[blockIdx.x];
+  const int lane = PT_LANE;
+  const int2 md = P.modes[PT_SLOT(P)];
   const PtCosmo* C = P.cosmo + md.x;
   mode_init(P, C, md.y);
   const double tau_first = C->tau[0];
@@ -2881,7 +2896,7 @@ __global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid
     if (!ok) break;
   }
   if (tail && status == 0) {
-    double* T = P.tail + (size_t)blockIdx.x * TL_STRIDE;
+    double* T = P.tail + (size_t)PT_SLOT(P) * TL_STRIDE;
     const int n = M.L.neq;
     if (lane < n) T[TL_Y + lane] = s_vec(P, V_Y)[lane];
     if (lane == 0) {
@@ -2899,16 +2914,17 @@ __global__ void __launch_bounds__(32, PT_MIN_BLOCKS) perturb_kernel(const __grid
 
 // Tail kernel: the radiation-streaming interval of every mode that perturb_kernel handed off.  Small
 // shared-memory footprint and register budget (16+ warps per SM), compact hot loop (ndf15_rsa).
+#define PT_TAIL_MAX_WPC 4
 #ifndef PT_TAIL_MIN_BLOCKS
 #define PT_TAIL_MIN_BLOCKS 12  // 168 registers: no spills in ndf15_rsa (16 -> 128 registers spills and is 25 % slower)
 #endif
-__global__ void __launch_bounds__(32, PT_TAIL_MIN_BLOCKS) perturb_tail_kernel(const __grid_constant__ PtParams P) {
-  if ((int)blockIdx.x >= P.n_modes) return;
-  const double* T = P.tail + (size_t)blockIdx.x * TL_STRIDE;
+__global__ void __launch_bounds__(32 * PT_TAIL_MAX_WPC, PT_TAIL_MIN_BLOCKS / PT_TAIL_MAX_WPC) perturb_tail_kernel(const __grid_constant__ PtParams P) {
+  if (PT_SLOT(P) >= P.n_modes) return;
+  const double* T = P.tail + (size_t)PT_SLOT(P) * TL_STRIDE;
   if (T[TL_VALID] != 1.) return;
   Mode& M = MODE(P);
-  const int lane = (int)threadIdx.x;
-  const int2 md = P.modes[blockIdx.x];
+  const int lane = PT_LANE;
+  const int2 md = P.modes[PT_SLOT(P)];
   const PtCosmo* C = P.cosmo + md.x;
   mode_init(P, C, md.y);
   const int iv = (int)T[TL_IV], n_int = (int)T[TL_NINT];
@@ -3036,11 +3052,12 @@ static void set_geometry(PtParams& P, int neq_max, int nh_max, const clpp_pertur
   P.o_vec = P.o_tabc + 16 * P.ncol;
   P.o_sinv = P.o_vec + V_COUNT * P.np;
   P.o_int = P.o_sinv + ((P.nh_max * P.ldh + 1) & ~1);
+  P.wpc = 1;
+  P.wstride = (int)((((size_t)P.o_int * sizeof(double) + (size_t)(2 * P.nh_max + 3 * PT_MAX_CHAINS) * sizeof(int)) + 15) / 16 * 2);
 }
 
-static size_t perturb_smem_bytes(const PtParams& P) {
-  return (size_t)P.o_int * sizeof(double) + (size_t)(2 * P.nh_max + 3 * PT_MAX_CHAINS) * sizeof(int);
-}
+// dynamic shared memory of one warp (one k mode); a CTA of P.wpc warps takes wpc times this
+static size_t perturb_smem_bytes(const PtParams& P) { return (size_t)P.wstride * sizeof(double); }
 
 // Integrates modes [k_begin[i], k_end[i]) of every context in ONE kernel launch on the stream of
 // the first context (all contexts must live on the same device).
@@ -3137,6 +3154,14 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     if (n_long == n_modes) n_long = 0;  // nothing to overlap with
   }
   const int n_bulk = n_modes - n_long;
+  // cohort width: modes per CTA. Batches of several cosmologies put the same k of neighbouring cosmologies side by side in
+  // the sorted order (near-identical step sequences); a single cosmology is a latency problem and keeps one mode per CTA.
+  const size_t smem1 = perturb_smem_bytes(P);
+  int wpc = getenv("CLPP_COHORT") ? atoi(getenv("CLPP_COHORT")) : (n_ctx >= 4 ? 4 : 1);
+  wpc = std::max(1, std::min(wpc, PT_MAX_WPC));
+  while (wpc > 1 && smem1 * wpc > 227 * 1024) wpc--;
+  int wpc_tail = getenv("CLPP_COHORT_TAIL") ? atoi(getenv("CLPP_COHORT_TAIL")) : std::min(wpc, PT_TAIL_MAX_WPC);
+  wpc_tail = std::max(1, std::min(wpc_tail, PT_TAIL_MAX_WPC));
   const int chunk_modes = getenv("CLPP_CHUNK_MODES") ? atoi(getenv("CLPP_CHUNK_MODES")) : 4000;  // developer knob
   const int n_chunks = use_tail ? std::max(1, std::min(PT_MAX_CHUNKS, n_bulk / std::max(chunk_modes, 1))) : 1;
   std::vector<int2> sorted(n_modes);
@@ -3146,7 +3171,8 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     int pos = n_long;
     for (int c = 0; c < n_chunks; c++) {
       chunk_first[c] = pos;
-      for (int i = n_long + c; i < n_modes; i += n_chunks) sorted[pos++] = modes[perm[i]];
+      for (int i = n_long; i < n_modes; i++)  // cohorts (wpc consecutive modes of the sorted order) stay together
+        if (((i - n_long) / wpc) % n_chunks == c) sorted[pos++] = modes[perm[i]];
     }
     chunk_first[n_chunks] = pos;
   }
@@ -3173,14 +3199,16 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   CLPP_CHECK(smem <= 227 * 1024, err,
              "state vector of %d equations needs %zu bytes of shared memory per k-mode (> 227 KB): reduce l_max_ncdm / "
              "the number of ncdm momentum bins", P.neq_max, smem);
-  CLPP_CUDA(cudaFuncSetAttribute(perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
+  CLPP_CUDA(cudaFuncSetAttribute(perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * wpc)), err);
+  P.wpc = wpc;
   PtParams Pt = P;  // geometry of the tail kernel: at most 16 equations, all hub
   set_geometry(Pt, 16, 16, c0->pd);
   const size_t smem_tail = perturb_smem_bytes(Pt);
-  CLPP_CUDA(cudaFuncSetAttribute(perturb_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tail), err);
+  CLPP_CUDA(cudaFuncSetAttribute(perturb_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_tail * wpc_tail)), err);
+  Pt.wpc = wpc_tail;
   if (getenv("CLPP_VERBOSE"))
-    fprintf(stderr, "[clpp] perturb: %d modes, shared memory per mode %zu B (tail %zu B), sizeof(Mode) %zu, neq_max %d, hub %d\n",
-            n_modes, smem, smem_tail, sizeof(Mode), P.neq_max, P.nh_max);
+    fprintf(stderr, "[clpp] perturb: %d modes, shared memory per mode %zu B (tail %zu B), sizeof(Mode) %zu, neq_max %d, hub %d, "
+            "modes per CTA %d (tail %d)\n", n_modes, smem, smem_tail, sizeof(Mode), P.neq_max, P.nh_max, wpc, wpc_tail);
   for (int i = 0; i < 6; i++)
     if (!d0->ev2[i]) cudaEventCreate(&d0->ev2[i]);
   if (!d0->stream2) {
@@ -3200,11 +3228,11 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     G.modes = P.modes + first; G.n_modes = count;
     G.hub_jac = P.hub_jac + (size_t)first * P.nh_max * P.nh_max;
     G.tail = P.tail ? P.tail + (size_t)first * TL_STRIDE : nullptr;
-    perturb_kernel<<<count, 32, smem, s>>>(G);
+    perturb_kernel<<<(count + wpc - 1) / wpc, 32 * wpc, smem * wpc, s>>>(G);
     c0->launches++;
     if (use_tail) {
       Gt.modes = G.modes; Gt.n_modes = count; Gt.tail = G.tail; Gt.hub_jac = G.hub_jac;
-      perturb_tail_kernel<<<count, 32, smem_tail, s>>>(Gt);
+      perturb_tail_kernel<<<(count + wpc_tail - 1) / wpc_tail, 32 * wpc_tail, smem_tail * wpc_tail, s>>>(Gt);
       c0->launches++;
     }
   };

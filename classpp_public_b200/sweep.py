@@ -66,3 +66,81 @@ def gather_tables(local, n_items, rank, world, group=None):
         for j, i in enumerate(shard_indices(n_items, r, world)):
             out[i] = g[j].copy()
     return out
+
+
+class SweepPipeline:
+    """Throughput scheduler for a sweep of independent cosmologies on ONE GPU (BASELINE config 5).
+
+    A batch of B cosmologies goes through `front(set, b)` (host: upstream tables -> PerturbationsModule without solving),
+    ONE batched perturbation launch (`PerturbationsModule.solve_batch`) and `back(set, b, pt)` (halofit, transfer, spectra,
+    lensing, P(k) on the cosmology's own stream).  The per-cosmology stages are short kernels and host work that leave
+    the GPU mostly idle, so the pipeline keeps `n_sets` batches in flight on separate sets of contexts: `front` and `back`
+    of one batch run under the batched launch of another.  By default the batched launches themselves do not overlap
+    (`stagger=None`): measured on B200, two launches in flight finish no sooner than back to back, because the
+    perturbation kernel saturates the SMs' instruction delivery at about half of the warp slots
+    (profiles/README.md); `stagger=s` lets launches overlap, at least s seconds apart.  `submit()` returns at once;
+    `drain()` waits for everything submitted so far.  No collective, no shared state between the sets: every context
+    owns its streams and buffers."""
+
+    def __init__(self, batch, front, back, n_sets=2, stagger=None, workers=None, on_solved=None):
+        import os
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        self.batch, self.front, self.back, self.n_sets = int(batch), front, back, int(n_sets)
+        self.stagger = None if stagger is None else float(stagger)
+        self.on_solved = on_solved
+        w = workers or min(self.batch, os.cpu_count() or 1)
+        self._front_pool = ThreadPoolExecutor(max_workers=w)
+        self._back_pool = ThreadPoolExecutor(max_workers=w)  # own queue: the next front never waits behind a back
+        self._step_pool = ThreadPoolExecutor(max_workers=self.n_sets)
+        self._tasks = [None] * self.n_sets
+        self._n = 0
+        self._gate = threading.Lock()
+        self._t_last_launch = -1e30
+        self.solve_seconds = []  # wall time of every batched launch, in order of completion
+        self.launch_log = []     # (set, start, end) of every batched launch (time.perf_counter)
+
+    def _run(self, s, args):
+        import time
+        from .modules import PerturbationsModule
+        pts = list(self._front_pool.map(lambda b: self.front(s, b, *args), range(self.batch)))
+        if self.stagger is None:  # one batched launch at a time; only `front`/`back` overlap it
+            with self._gate:
+                t0 = time.perf_counter()
+                PerturbationsModule.solve_batch(pts)
+        else:  # launches overlap, at least `stagger` seconds apart
+            with self._gate:
+                wait = self._t_last_launch + self.stagger - time.perf_counter()
+                if wait > 0:
+                    time.sleep(wait)
+                self._t_last_launch = time.perf_counter()
+            t0 = time.perf_counter()
+            PerturbationsModule.solve_batch(pts)
+        self.solve_seconds.append(time.perf_counter() - t0)
+        self.launch_log.append((s, t0, time.perf_counter()))
+        if self.on_solved is not None:
+            self.on_solved(s)
+        futs = [self._back_pool.submit(self.back, s, b, pts[b], *args) for b in range(self.batch)]
+        return [f.result() for f in futs]
+
+    def submit(self, *args):
+        """Queue one batch on the next context set (waits only if that set is still busy with an older batch)."""
+        s = self._n % self.n_sets
+        self._n += 1
+        if self._tasks[s] is not None:
+            self._tasks[s].result()
+        self._tasks[s] = self._step_pool.submit(self._run, s, args)
+        return s
+
+    def drain(self):
+        """Wait for every submitted batch; returns the list of `back` results of the last batch of each set."""
+        out = []
+        for s in range(self.n_sets):
+            if self._tasks[s] is not None:
+                out.append(self._tasks[s].result())
+        return out
+
+    def close(self):
+        self.drain()
+        for p in (self._front_pool, self._back_pool, self._step_pool):
+            p.shutdown(wait=True)
