@@ -2914,7 +2914,7 @@ __global__ void __launch_bounds__(32 * PT_MAX_WPC, 1) perturb_kernel(const __gri
 
 // Tail kernel: the radiation-streaming interval of every mode that perturb_kernel handed off.  Small
 // shared-memory footprint and register budget (16+ warps per SM), compact hot loop (ndf15_rsa).
-#define PT_TAIL_MAX_WPC 4
+#define PT_TAIL_MAX_WPC 6
 #ifndef PT_TAIL_MIN_BLOCKS
 #define PT_TAIL_MIN_BLOCKS 12  // 168 registers: no spills in ndf15_rsa (16 -> 128 registers spills and is 25 % slower)
 #endif
@@ -3162,6 +3162,10 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   while (wpc > 1 && smem1 * wpc > 227 * 1024) wpc--;
   int wpc_tail = getenv("CLPP_COHORT_TAIL") ? atoi(getenv("CLPP_COHORT_TAIL")) : std::min(wpc, PT_TAIL_MAX_WPC);
   wpc_tail = std::max(1, std::min(wpc_tail, PT_TAIL_MAX_WPC));
+  // the long-tail group is the latency-critical path: lockstep only pays for it once the batch is throughput-bound
+  // (measured, scripts/sweep_varied.py: 32 different cosmologies lose 15 % with cohorts there, 96 gain 4 %)
+  int wpc_long = getenv("CLPP_COHORT_LONG") ? atoi(getenv("CLPP_COHORT_LONG")) : (n_ctx >= 64 ? wpc : 1);
+  wpc_long = std::max(1, std::min(wpc_long, wpc));
   const int chunk_modes = getenv("CLPP_CHUNK_MODES") ? atoi(getenv("CLPP_CHUNK_MODES")) : 4000;  // developer knob
   const int n_chunks = use_tail ? std::max(1, std::min(PT_MAX_CHUNKS, n_bulk / std::max(chunk_modes, 1))) : 1;
   std::vector<int2> sorted(n_modes);
@@ -3222,9 +3226,10 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     }
   }
   cudaStream_t sth = d0->stream_hi;
-  auto launch_group = [&](cudaStream_t s, int first, int count) {
+  auto launch_group = [&](cudaStream_t s, int first, int count, int wpc, int wpc_tail) {
     if (count <= 0) return;
     PtParams G = P, Gt = Pt;
+    G.wpc = wpc; Gt.wpc = wpc_tail;
     G.modes = P.modes + first; G.n_modes = count;
     G.hub_jac = P.hub_jac + (size_t)first * P.nh_max * P.nh_max;
     G.tail = P.tail ? P.tail + (size_t)first * TL_STRIDE : nullptr;
@@ -3241,14 +3246,14 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     cudaEventRecord(d0->ev2[4], st);        // uploads on st are complete before the other streams start
     if (n_long > 0) {
       cudaStreamWaitEvent(sth, d0->ev2[4], 0);
-      launch_group(sth, 0, n_long);  // high priority: its tail CTAs take the slots as they free up
+      launch_group(sth, 0, n_long, wpc_long, std::min(wpc_long, wpc_tail));  // high priority: its tail CTAs take the slots as they free up
       cudaEventRecord(d0->ev2[5], sth);
       cudaStreamWaitEvent(st, d0->ev2[5], 0);
     }
     for (int c = 0; c < n_chunks; c++) {
       cudaStream_t sc = d0->chunk_stream[c];
       cudaStreamWaitEvent(sc, d0->ev2[4], 0);
-      launch_group(sc, chunk_first[c], chunk_first[c + 1] - chunk_first[c]);
+      launch_group(sc, chunk_first[c], chunk_first[c + 1] - chunk_first[c], wpc, wpc_tail);
       cudaEventRecord(d0->chunk_done[c], sc);
       cudaStreamWaitEvent(st, d0->chunk_done[c], 0);
     }
