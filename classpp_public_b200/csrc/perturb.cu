@@ -93,6 +93,7 @@ struct PtParams {
   double rk_stepsize; // perturb_integration_stepsize (rk only)
   int force_generic;  // developer/test switch: integrate every interval with the generic shared-memory NDF
   int wpc, wstride;   // warps (k modes) per CTA; doubles of shared memory per warp
+  int scr_stride;     // doubles of global scratch per mode (hub Jacobian + 4 vectors)
   int neq_max, np, nh_max, ldh;
   int o_mode, o_hubtmp, o_nw, o_i2l1, n_i2l1, o_tabc, ncol, o_vec, o_sinv, o_int;
 };
@@ -118,7 +119,7 @@ extern __shared__ double smem_all[];
 #define s_vec(P, slot) (SMEM(P) + ((P).o_vec + (slot) * (P).np))
 #define s_sinv(P) (SMEM(P) + (P).o_sinv)
 // bracketing rows of table `tab` (0 background, 1 thermodynamics), cache set `set`: [4][ncol] = y0, y1, dd0, dd1
-#define s_tabc(P, tab, set) (SMEM(P) + (P).o_tabc + (((set) * 2 + (tab)) * 4) * (P).ncol)
+#define s_tabc(P, tab, set) (SMEM(P) + (P).o_tabc + ((tab) * 4) * (P).ncol)
 #define s_i2l1(P) (SMEM(P) + (P).o_i2l1)
 #define s_hub_idx(P) ((int*)(SMEM(P) + (P).o_int))
 #define s_piv(P) ((int*)(SMEM(P) + (P).o_int) + (P).nh_max)
@@ -178,11 +179,14 @@ struct Metric {
 enum {
   V_Y = 0, V_YNEW, V_F0, V_PRED, V_PSI, V_DIFKP1, V_DEL, V_INVWT,
   V_TMP = V_PSI, V_YPI = V_PRED,  // scratch of the Jacobian probes / source output: psi and pred are dead there
-  V_DIF0 = V_INVWT + 1,  // 7 slots: dif[0..6]
-  V_JD = V_DIF0 + 7, V_JL, V_JU,  // chain rows of J: diagonal, sub-diagonal J[i,i-1], super-diagonal J[i,i+1]
-  V_IP, V_MU, V_LO,               // chain factors: 1/pivot, T[i,i+1]/p[i+1], T[i,i-1]
+  V_DIF0 = V_INVWT + 1,  // 5 slots: dif[0..4]; dif[5], dif[6] (orders 4 and 5 only) live in the mode's global scratch
+  V_JL = V_DIF0 + 5,     // chain rows of J: sub-diagonal J[i,i-1] (T[i,i-1] = -c J[i,i-1] is formed on the fly by solve);
+                         // the diagonal and the super-diagonal are only read by factor(): global scratch (Mode::gJd, gJu)
+  V_IP, V_MU,            // chain factors: 1/pivot, T[i,i+1]/p[i+1]
   V_COUNT
 };
+// Shared memory per mode decides how many cohorts fit on an SM: 16 slots (17.4 KB for 136 equations) instead of 21 puts
+// two 4-mode cohorts of the largest Planck-18 system (136 equations, 28 hub variables) on one SM.
 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double wmax_any(double v) {
@@ -262,6 +266,8 @@ struct Stat {
 struct Mode {
   const PtCosmo* C;
   double* Jhh;  // global scratch [nh][nh], column-major: Jhh[i + j*nh] = J[hub i, hub j]
+  double *gJd, *gJu, *gdif;  // global scratch [np] each: chain diagonal / super-diagonal of J; dif[5], dif[6] ([2][np])
+  double fac_c;              // c of the current factorisation of I - c J
   double k, k2, inv_k, inv_k2;
   double nf[PT_MAX_NCDM][8];  // ncdm fluid constants at the current time (env_at)
   TabCache bgc[2], thc[2];  // [0] time stepping, [1] source output
@@ -296,6 +302,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 
 __device__ __noinline__ void env_at(const PtParams& P, double tau, bool closeby, int set) {
   Mode& M = MODE(P);
+  set = 0;  // one interval cache: the output times lie inside the current step, i.e. (almost always) in the cached interval
   const int lane = PT_LANE;
   double* pvb = s_pvb(P);
   double* pvt = s_pvt(P);
@@ -941,7 +948,7 @@ __device__ __noinline__ void jacobian(const PtParams& P) {
   const int n = M.L.neq, lane = PT_LANE, nh = M.nh, nch = M.nch;
   double* e_j = s_vec(P, V_TMP);
   double* col = s_vec(P, V_DEL);
-  double *Jd = s_vec(P, V_JD), *Jl = s_vec(P, V_JL), *Ju = s_vec(P, V_JU);
+  double *Jd = M.gJd, *Jl = s_vec(P, V_JL), *Ju = M.gJu;
 #pragma unroll 1
   for (int i = lane; i < n; i += 32) { e_j[i] = 0.; Jd[i] = 0.; Jl[i] = 0.; Ju[i] = 0.; }
   __syncwarp();
@@ -1046,8 +1053,9 @@ __device__ __forceinline__ void hub_inverse_rows(const PtParams& P, Mode& M, dou
 __device__ __noinline__ void factor(const PtParams& P, double c) {
   Mode& M = MODE(P);
   const int lane = PT_LANE, nh = M.nh, nch = M.nch, ldh = P.ldh;
-  const double *Jd = s_vec(P, V_JD), *Jl = s_vec(P, V_JL), *Ju = s_vec(P, V_JU);
-  double *ip = s_vec(P, V_IP), *mu = s_vec(P, V_MU), *lo = s_vec(P, V_LO);
+  const double *Jd = M.gJd, *Jl = s_vec(P, V_JL), *Ju = M.gJu;
+  double *ip = s_vec(P, V_IP), *mu = s_vec(P, V_MU);
+  if (lane == 0) M.fac_c = c;
   double* W = s_sinv(P);
 #pragma unroll 1
   for (int i = lane; i < nh; i += 32) s_hubtmp(P)[i] = 0.;
@@ -1057,13 +1065,12 @@ __device__ __noinline__ void factor(const PtParams& P, double c) {
     double ipn = 1.0 / (1.0 - c * Jd[last]);
     ip[last] = ipn;
     double lon = -c * Jl[last];
-    lo[last] = lon;
     for (int i = last - 1; i >= s; i--) {
       const double mui = -c * Ju[i] * ipn;
       const double p = (1.0 - c * Jd[i]) - mui * lon;
       ipn = 1.0 / p;
       lon = -c * Jl[i];
-      ip[i] = ipn; mu[i] = mui; lo[i] = lon;
+      ip[i] = ipn; mu[i] = mui;
     }
     const double mur = -c * Ju[s - 1] * ipn;
     mu[s - 1] = mur;
@@ -1144,7 +1151,8 @@ __device__ __noinline__ void factor(const PtParams& P, double c) {
 __device__ __forceinline__ void solve(const PtParams& P, double* __restrict__ b) {
   Mode& M = MODE(P);
   const int lane = PT_LANE, nh = M.nh, nch = M.nch, ldh = P.ldh;
-  const double *ip = s_vec(P, V_IP), *mu = s_vec(P, V_MU), *lo = s_vec(P, V_LO);
+  const double *ip = s_vec(P, V_IP), *mu = s_vec(P, V_MU), *Jl = s_vec(P, V_JL);
+  const double c = M.fac_c;
   if (nch > 0) {
     if (lane < nch) {
       const int s = s_ch_start(P)[lane], last = s + s_ch_len(P)[lane] - 1;
@@ -1197,7 +1205,8 @@ __device__ __forceinline__ void solve(const PtParams& P, double* __restrict__ b)
       const int s = s_ch_start(P)[lane], last = s + s_ch_len(P)[lane] - 1;
       double xp = b[s - 1];
       for (int i = s; i <= last; i++) {
-        xp = (b[i] - lo[i] * xp) * ip[i];
+        const double lo = -c * Jl[i];  // T[i,i-1]
+        xp = (b[i] - lo * xp) * ip[i];
         b[i] = xp;
       }
     }
@@ -1261,9 +1270,13 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
   while (next < tres && __ldg(t_vec + next) < t0) next++;
   double tnext = (next < tres) ? __ldg(t_vec + next) : 1e300;
 
-  for (int j = 0; j < 7; j++)
+  double* const gdif = M.gdif;
+#define DIF_SLOT(j) ((j) < 5 ? dif + (j) * np : gdif + ((j) - 5) * np)
+  for (int j = 0; j < 7; j++) {
+    double* dj = DIF_SLOT(j);
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) dif[j * np + i] = 0.;
+    for (int i = lane; i < n; i += 32) dj[i] = 0.;
+  }
   const double htspan = fabs(tfinal - t0);
   double t = t0, tnew = t0;
   env_at(P, t0, true, 0);
@@ -1494,12 +1507,14 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
     if (PT_LANE == 0) M.st.steps++;
     PROF_BEGIN();
     // update the difference array
+    double* const difk = DIF_SLOT(k);
+    double* const difk1 = DIF_SLOT(k + 1);
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) {
       const double dk = difkp1[i];
-      dif[(k + 1) * np + i] = dk - dif[k * np + i];
+      difk1[i] = dk - difk[i];
       double acc = dk;
-      dif[k * np + i] = acc;
+      difk[i] = acc;
       for (int j = k - 1; j >= 0; j--) {
         acc += dif[j * np + i];
         dif[j * np + i] = acc;
@@ -1553,8 +1568,9 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
         e_km1 = wmax(e_km1) * c_erconst[k - 2];
       }
       if (k < maxk) {
+        const double* difk1 = DIF_SLOT(k + 1);
 #pragma unroll 1
-        for (int i = lane; i < n; i += 32) e_kp1 = fmax(e_kp1, fabs(dif[(k + 1) * np + i] * invwt[i]));
+        for (int i = lane; i < n; i += 32) e_kp1 = fmax(e_kp1, fabs(difk1[i] * invwt[i]));
         e_kp1 = wmax(e_kp1) * c_erconst[k];
       }
       const double my_e = lane == 0 ? err : lane == 1 ? e_km1 : e_kp1;
@@ -2710,7 +2726,8 @@ __device__ __forceinline__ void mode_init(const PtParams& P, const PtCosmo* C, i
   Mode& M = MODE(P);
   const int lane = PT_LANE;
   if (lane == 0) {
-    M.Jhh = P.hub_jac + (size_t)PT_SLOT(P) * P.nh_max * P.nh_max;
+    M.Jhh = P.hub_jac + (size_t)PT_SLOT(P) * P.scr_stride;
+    M.gJd = M.Jhh + (size_t)P.nh_max * P.nh_max; M.gJu = M.gJd + P.np; M.gdif = M.gJu + P.np;
     M.C = C;
     M.ik = ik;
     M.k = C->k[ik];
@@ -3049,10 +3066,11 @@ static void set_geometry(PtParams& P, int neq_max, int nh_max, const clpp_pertur
   P.n_i2l1 = (std::max(std::max(pd.l_max_g, pd.l_max_pol_g), std::max(pd.l_max_ur, pd.l_max_ncdm)) + 2 + 1) & ~1;
   P.ncol = (std::max(P.bg_size_normal, P.th_size) <= 16) ? 16 : 32;
   P.o_tabc = P.o_i2l1 + P.n_i2l1;
-  P.o_vec = P.o_tabc + 16 * P.ncol;
+  P.o_vec = P.o_tabc + 8 * P.ncol;
   P.o_sinv = P.o_vec + V_COUNT * P.np;
   P.o_int = P.o_sinv + ((P.nh_max * P.ldh + 1) & ~1);
   P.wpc = 1;
+  P.scr_stride = P.nh_max * P.nh_max + 4 * P.np;
   P.wstride = (int)((((size_t)P.o_int * sizeof(double) + (size_t)(2 * P.nh_max + 3 * PT_MAX_CHAINS) * sizeof(int)) + 15) / 16 * 2);
 }
 
@@ -3183,7 +3201,7 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
 
   if (clpp_dev_reserve(d0, &d0->pt_cosmo, n_ctx * sizeof(PtCosmo), err)) return CLPP_FAILURE;
   if (clpp_dev_reserve(d0, &d0->pt_modes, (size_t)std::max(n_modes, 1) * sizeof(int2), err)) return CLPP_FAILURE;
-  if (clpp_dev_reserve(d0, &d0->jac_scratch, (size_t)std::max(n_modes, 1) * P.nh_max * P.nh_max, err))
+  if (clpp_dev_reserve(d0, &d0->jac_scratch, (size_t)std::max(n_modes, 1) * P.scr_stride, err))
     return CLPP_FAILURE;
   CLPP_CUDA(cudaMemcpyAsync(d0->pt_cosmo, cosmo.data(), n_ctx * sizeof(PtCosmo), cudaMemcpyHostToDevice, st), err);
   CLPP_CUDA(cudaMemcpyAsync(d0->pt_modes, sorted.data(), n_modes * sizeof(int2), cudaMemcpyHostToDevice, st), err);
@@ -3203,7 +3221,14 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   CLPP_CHECK(smem <= 227 * 1024, err,
              "state vector of %d equations needs %zu bytes of shared memory per k-mode (> 227 KB): reduce l_max_ncdm / "
              "the number of ncdm momentum bins", P.neq_max, smem);
-  CLPP_CUDA(cudaFuncSetAttribute(perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * wpc)), err);
+  // developer knob: extra dynamic shared memory per CTA of the generic kernel (limits the CTAs per SM)
+  // Two unsynchronised cohorts on one SM share the instruction cache again: measured (bench.py --batch 64) the large
+  // Planck-18 system (136 equations) runs 4 % faster with ONE 4-mode cohort per SM, the small LCDM one (46 equations,
+  // smaller hot code) 1.7x faster with two. Large systems therefore claim more than half of the SM's shared memory.
+  size_t smem_pad = 0;
+  if (wpc > 1 && P.neq_max >= 100 && smem * wpc <= 114 * 1024) smem_pad = 115 * 1024 - smem * wpc;
+  if (getenv("CLPP_SMEM_PAD_KB")) smem_pad = (size_t)atoi(getenv("CLPP_SMEM_PAD_KB")) * 1024;  // developer knob
+  CLPP_CUDA(cudaFuncSetAttribute(perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * wpc + smem_pad)), err);
   P.wpc = wpc;
   PtParams Pt = P;  // geometry of the tail kernel: at most 16 equations, all hub
   set_geometry(Pt, 16, 16, c0->pd);
@@ -3231,9 +3256,9 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     PtParams G = P, Gt = Pt;
     G.wpc = wpc; Gt.wpc = wpc_tail;
     G.modes = P.modes + first; G.n_modes = count;
-    G.hub_jac = P.hub_jac + (size_t)first * P.nh_max * P.nh_max;
+    G.hub_jac = P.hub_jac + (size_t)first * P.scr_stride;
     G.tail = P.tail ? P.tail + (size_t)first * TL_STRIDE : nullptr;
-    perturb_kernel<<<(count + wpc - 1) / wpc, 32 * wpc, smem * wpc, s>>>(G);
+    perturb_kernel<<<(count + wpc - 1) / wpc, 32 * wpc, smem * wpc + smem_pad, s>>>(G);
     c0->launches++;
     if (use_tail) {
       Gt.modes = G.modes; Gt.n_modes = count; Gt.tail = G.tail; Gt.hub_jac = G.hub_jac;
