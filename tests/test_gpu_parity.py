@@ -419,6 +419,74 @@ def test_batched_solve_equals_individual_solves(golden):
         c.close()
 
 
+def test_cohorts_of_modes_per_cta_are_bit_identical(golden, monkeypatch):
+    """Cohorts (several k modes per CTA, one warp each, CTA barrier at every step) only change WHEN a warp runs, never
+    what it computes: sources and work counters are bit-identical to the one-mode-per-CTA launch, for a batch (same k
+    of neighbouring cosmologies side by side) and for a single cosmology (adjacent k in one cohort, ragged last CTA)."""
+    inp = golden("lcdm_coarse")
+    out = {}
+    for W in ("1", "4", "3"):
+        monkeypatch.setenv("CLPP_COHORT", W)
+        monkeypatch.setenv("CLPP_COHORT_LONG", W)
+        ctxs, pts = [], []
+        for _ in range(5):
+            c = M.Context(0)
+            b = M.BackgroundModule(inp, c)
+            t = M.ThermodynamicsModule(inp, b)
+            ctxs.append(c)
+            pts.append(M.PerturbationsModule(inp, b, t, solve=False))
+        M.PerturbationsModule.solve_batch(pts)
+        single = M.PerturbationsModule(inp, *_tables(inp, ctxs[0]))  # one cosmology, cohorts of adjacent k
+        out[W] = (np.stack(pts[3].sources_[0]), pts[3].kstat_[:, :6].copy(), np.stack(single.sources_[0]))
+        for p in pts:
+            assert np.array_equal(np.stack(p.sources_[0]), out[W][0])
+        for c in ctxs:
+            c.close()
+    for W in ("4", "3"):
+        assert np.array_equal(out[W][0], out["1"][0]) and np.array_equal(out[W][1], out["1"][1])
+        assert np.array_equal(out[W][2], out["1"][2])
+    assert np.array_equal(out["1"][0], out["1"][2])
+
+
+def _tables(inp, ctx):
+    bg = M.BackgroundModule(inp, ctx)
+    return bg, M.ThermodynamicsModule(inp, bg)
+
+
+def test_sweep_pipeline_equals_direct_calls(golden):
+    """sweep.SweepPipeline (two context sets, per-cosmology stages of batch i under the launch of batch i+1) returns, for
+    every batch, exactly what the direct module calls return."""
+    from classpp_public_b200.sweep import SweepPipeline
+    inp = golden("lcdm_coarse")
+    a = inp.arrays
+    ctx, pt, tr, sp = run_pipeline(inp)
+    cl_direct = sp.cl_[0].copy()
+    ctx.close()
+    B, NSET = 3, 2
+    sets = [[_tables(inp, M.Context(0)) for _ in range(B)] for _ in range(NSET)]
+
+    def front(s, b):
+        return M.PerturbationsModule(inp, sets[s][b][0], sets[s][b][1], solve=False)
+
+    def back(s, b, p):
+        t = M.TransferModule(inp, sets[s][b][0], sets[s][b][1], p, None)
+        return M.SpectraModule(inp, p, M.TabulatedPrimordial(a["pm.pk_at_transfer_k"]), None, t).cl_[0].copy()
+
+    pipe = SweepPipeline(B, front, back, n_sets=NSET)
+    for _ in range(3):
+        pipe.submit()
+    res = pipe.drain()
+    assert len(res) == NSET and len(pipe.solve_seconds) == 3
+    for batch in res:
+        assert len(batch) == B
+        for cl in batch:
+            assert np.array_equal(cl, cl_direct)
+    pipe.close()
+    for s in sets:
+        for bg, th in s:
+            bg.ctx.close()
+
+
 def test_tail_kernel_equals_single_kernel_path(golden, monkeypatch):
     """The specialised integrators (perturb_tail_kernel: registers + shuffles; hub-only register path) and the
     generic shared-memory NDF (CLPP_GENERIC_ONLY=1, the fallback for very large systems) follow the same
