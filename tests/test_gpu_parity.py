@@ -334,6 +334,16 @@ def test_lensed_cl_on_device_vs_golden(golden, name, rtol):
         ratio_mine = mine[sel, c] / sp.cl_[0].reshape(-1, lt)[rows, c]
         ratio_ref = ref[sel, c] / ref_unl[rows, c]
         assert np.max(np.abs(ratio_mine / ratio_ref - 1.0)) < 2e-5
+    # stage isolation: the numpy restatement of lensing_init fed with OUR unlensed table (oracle/restate.py, itself pinned
+    # to the reference at 1e-9 by tests/test_oracle_restatement.py) -> the device kernels agree to rounding
+    from oracle import restate
+    idx = {n: getattr(le, "index_lt_%s_" % n) for n in ("tt", "ee", "te", "bb", "pp")}
+    l_np, cl_np, _ = restate.lensed_cl(sp.l_, sp.cl_[0].reshape(-1, lt), idx, 500, int(inp.meta["pt.l_scalar_max"]))
+    assert np.array_equal(l_np, le.l_)
+    dev = le.cl_lens_.reshape(-1, lt)
+    for c in (tt, ee, bb):
+        assert np.max(np.abs(dev[:, c] / cl_np[:, c] - 1.0)) < 1e-9
+    assert np.max(np.abs(dev[:, te] - cl_np[:, te]) / np.sqrt(cl_np[:, tt] * cl_np[:, ee])) < 1e-9
     with pytest.raises(M.CosmoComputationError, match="you asked for lensed Cls at l="):
         le.lensing_cl_at_l(le.l_lensed_max_ + 1)
     assert ctx.kernel_ms()["lensing"] > 0
