@@ -157,7 +157,7 @@ SYMBOLS = [
     "clpp_transfer_get_transfer", "clpp_transfer_set_transfer", "clpp_transfer_device_transfer",
     "clpp_transfer_get_bessel",
     "clpp_spectra_compute", "clpp_spectra_compute_range", "clpp_spectra_cl_at_l", "clpp_spectra_cl_output", "clpp_pk_linear", "clpp_nonlinear_halofit",
-    "clpp_lensing_compute", "clpp_lensing_cl_at_l",
+    "clpp_lensing_compute", "clpp_lensing_cl_at_l", "clpp_perturb_sources_at_tau",
 ]
 
 _lib = None
@@ -208,6 +208,7 @@ def lib():
         L.clpp_spectra_compute_range.argtypes = [vp, dp, C.c_int, C.c_int, P(SpectraInfo), dp, cp]
         L.clpp_pk_linear.argtypes = [vp, dp, C.c_int, C.c_int, dp, cp]
         L.clpp_nonlinear_halofit.argtypes = [vp, P(HalofitDesc), dp, dp, ip, cp]
+        L.clpp_perturb_sources_at_tau.argtypes = [vp, C.c_int, C.c_double, dp, cp]
         L.clpp_lensing_compute.argtypes = [vp, P(LensingDesc), P(LensingInfo), dp, dp, cp]
         L.clpp_lensing_cl_at_l.argtypes = [vp, C.c_int, dp, cp]
         L.clpp_spectra_cl_at_l.argtypes = [vp, C.c_double, dp, cp]

@@ -20,6 +20,7 @@ int clpp_host_cl_at_l(const clpp_ctx* c, double l, double* cl_tot, char* err);
 int clpp_dev_halofit(clpp_ctx* c, const clpp_halofit_desc* hd, const double* primordial_pk, double* nl_corr_out,
                      int* index_tau_min_nl, char* err);
 int clpp_dev_pk_linear(clpp_ctx* c, const double* primordial_pk, int index_tau, int cb, double* pk_out, char* err);
+int clpp_dev_sources_at_tau(clpp_ctx* c, int index_tp, double tau, double* psource, char* err);
 int clpp_dev_lensing(clpp_ctx* c, const clpp_lensing_desc* ld, clpp_lensing_info* info, double* l_out, double* cl_lens_out,
                      char* err);
 int clpp_host_lensing_cl_at_l(const clpp_ctx* c, int l, double* cl_lensed, char* err);
@@ -400,6 +401,14 @@ int clpp_pk_linear(clpp_ctx* c, const double* primordial_pk, int index_tau, int 
   CLPP_CHECK(c->has_sources, err, "no sources: run clpp_perturb_solve first");
   cudaSetDevice(c->device);
   return clpp_dev_pk_linear(c, primordial_pk, index_tau, cb, pk_out, err);
+}
+
+int clpp_perturb_sources_at_tau(clpp_ctx* c, int index_tp, double tau, double* psource, char* err) {
+  CLPP_CHECK(c && psource, err, "null argument");
+  CLPP_CHECK(c->dev, err, "this context has no CUDA device: the B200 path has no CPU fallback");
+  CLPP_CHECK(c->has_sources, err, "no sources: run clpp_perturb_solve first");
+  cudaSetDevice(c->device);
+  return clpp_dev_sources_at_tau(c, index_tp, tau, psource, err);
 }
 
 int clpp_nonlinear_halofit(clpp_ctx* c, const clpp_halofit_desc* desc, const double* primordial_pk, double* nl_corr_out,

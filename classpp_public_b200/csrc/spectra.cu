@@ -271,3 +271,42 @@ int clpp_dev_pk_linear(clpp_ctx* c, const double* primordial_pk, int index_tau, 
   CLPP_CUDA(cudaStreamSynchronize(d->stream), err);
   return CLPP_SUCCESS;
 }
+
+
+// =============================================================================================
+// PerturbationsModule::perturb_sources_at_tau (perturbations_module.cpp:79-131), the branch every default run takes
+// (z_max_pk = 0: ln_tau_size_ <= 1): linear interpolation in tau of one source type at all k (array_interpolate_two_bis,
+// tools/arrays.c:2380-2436), read from the device-resident table [tp][k][tau].
+// =============================================================================================
+__global__ void sources_at_tau_kernel(int nk, int nt, int inf, int sup, double weight, const double* __restrict__ src_tp,
+                                      double* __restrict__ out) {
+  const int ik = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ik >= nk) return;
+  const double* row = src_tp + (size_t)ik * nt;
+  // no FMA contraction: same rounding as the reference's CPU expression
+  out[ik] = __dadd_rn(__dmul_rn(row[inf], 1. - weight), __dmul_rn(weight, row[sup]));
+}
+
+int clpp_dev_sources_at_tau(clpp_ctx* c, int index_tp, double tau, double* psource, char* err) {
+  clpp_ctx::Dev* d = c->dev;
+  const clpp_perturb_info& I = c->pinfo;
+  const int nk = I.k_size, nt = I.tau_size;
+  CLPP_CHECK(index_tp >= 0 && index_tp < I.tp_size, err, "source type %d outside [0,%d)", index_tp, I.tp_size);
+  const std::vector<double>& x = c->tau;
+  int inf = 0, sup = nt - 1;
+  CLPP_CHECK(tau >= x[inf], err, "x=%e < x_min=%e", tau, x[inf]);
+  CLPP_CHECK(tau <= x[sup], err, "x=%e > x_max=%e", tau, x[sup]);
+  while (sup - inf > 1) {
+    const int mid = (int)(0.5 * (inf + sup));
+    if (tau < x[mid]) sup = mid;
+    else inf = mid;
+  }
+  const double weight = (tau - x[inf]) / (x[sup] - x[inf]);
+  if (clpp_dev_reserve(d, &d->pk, (size_t)2 * nk, err)) return CLPP_FAILURE;
+  sources_at_tau_kernel<<<(nk + 127) / 128, 128, 0, d->stream>>>(nk, nt, inf, sup, weight, d->sources + (size_t)index_tp * nk * nt, d->pk);
+  c->launches++;
+  CLPP_CUDA(cudaGetLastError(), err);
+  CLPP_CUDA(cudaMemcpyAsync(psource, d->pk, nk * sizeof(double), cudaMemcpyDeviceToHost, d->stream), err);
+  CLPP_CUDA(cudaStreamSynchronize(d->stream), err);
+  return CLPP_SUCCESS;
+}

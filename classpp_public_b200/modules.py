@@ -306,6 +306,16 @@ class PerturbationsModule:
                                                     capi.dptr(out), self.ctx.err))
         return out
 
+    def perturb_sources_at_tau(self, index_md, index_ic, index_tp, tau):
+        """S^{tp}(k, tau) at all k, linear in tau between the sampling times (reference: perturbations_module.cpp:79;
+        z_max_pk = 0 branch). index_md / index_ic must be 0 (scalars, adiabatic)."""
+        if index_md != 0 or index_ic != 0:
+            raise CosmoSevereError("only the scalar adiabatic mode is computed (index_md = index_ic = 0)")
+        out = np.empty(self.info.k_size)
+        self.ctx.check(self.ctx._lib.clpp_perturb_sources_at_tau(self.ctx.handle, int(index_tp), float(tau), capi.dptr(out),
+                                                                 self.ctx.err))
+        return out
+
     @property
     def sources_(self):
         """sources_[index_md][index_ic*tp_size+index_tp][index_tau*k_size+index_k] (perturbations.h:20)."""

@@ -230,6 +230,11 @@ int clpp_spectra_compute(clpp_ctx* ctx, const double* primordial_pk, clpp_spectr
 int clpp_spectra_compute_range(clpp_ctx* ctx, const double* primordial_pk, int q_begin, int q_end,
                                clpp_spectra_info* info, double* cl_out, char* err);
 
+/* replaces PerturbationsModule::perturb_sources_at_tau (perturbations_module.cpp:79-131; scalars, adiabatic mode) for the
+ * default z_max_pk = 0 (ln_tau_size_ <= 1): psource[k_size] = S^{index_tp}(k, tau), linear in tau between the sampling
+ * times; fails like array_interpolate_two_bis outside [tau_sampling_[0], tau_sampling_[tau_size-1]]. */
+int clpp_perturb_sources_at_tau(clpp_ctx* ctx, int index_tp, double tau, double* psource, char* err);
+
 /* ---- P(k): first "next" row of SURVEY 8f ---------------------------------------------------- */
 /* replaces NonlinearModule::nonlinear_pk_linear (nonlinear_module.cpp:1886-2024, adiabatic mode):
  * pk_out[i] = 2 pi^2 / k_i^3 * primordial_pk[i] * delta(k_i, tau)^2 on the perturbation k grid, read from the

@@ -274,6 +274,38 @@ def test_linear_matter_power_spectrum_vs_live_reference(reference):
         ctx.close()
 
 
+def test_perturb_sources_at_tau(golden):
+    """SURVEY 8 row a11: PerturbationsModule::perturb_sources_at_tau (z_max_pk = 0 branch: linear in tau,
+    array_interpolate_two_bis). The unmodified reference cannot be run as the checker here: with z_max_pk = 0 it reads
+    ln_tau_[0] of a never-allocated ln_tau_ (perturbations_module.cpp:95 vs :1555) and segfaults, so the check is the
+    defining formula on our own table (bit-identical), whose columns are pinned to the reference by the golden test, plus
+    the reference's out-of-range failure."""
+    inp = golden("lcdm_coarse")
+    a = inp.arrays
+    ctx = M.Context(0)
+    bg = M.BackgroundModule(inp, ctx)
+    th = M.ThermodynamicsModule(inp, bg)
+    pt = M.PerturbationsModule(inp, bg, th)
+    tau_s, nk = pt.tau_sampling_, pt.info.k_size
+    cols = a["ref.k_cols"].astype(int)
+    for tp in (pt.info.index_tp_delta_m, pt.info.index_tp_phi_plus_psi):
+        tab = pt.sources_[0][tp].reshape(-1, nk)
+        for j, frac in ((3, 0.25), (len(tau_s) // 2, 0.5), (len(tau_s) - 2, 0.9)):
+            tau = tau_s[j] + frac * (tau_s[j + 1] - tau_s[j])
+            mine = pt.perturb_sources_at_tau(0, 0, tp, tau)
+            w = (tau - tau_s[j]) / (tau_s[j + 1] - tau_s[j])
+            assert np.array_equal(mine, tab[j] * (1.0 - w) + w * tab[j + 1])
+        at_node = pt.perturb_sources_at_tau(0, 0, tp, tau_s[-1])
+        assert np.array_equal(at_node, tab[-1])
+        r = a["ref.sources_cols"][tp][-1]  # the reference's S(k, tau_0) at the sub-sampled k columns
+        assert np.max(np.abs(at_node[cols] - r)) < 1e-3 * np.max(np.abs(r))
+    with pytest.raises(M.CosmoComputationError, match="x_max"):
+        pt.perturb_sources_at_tau(0, 0, 0, tau_s[-1] * 1.01)
+    with pytest.raises(M.CosmoSevereError):
+        pt.perturb_sources_at_tau(1, 0, 0, tau_s[-1])
+    ctx.close()
+
+
 def test_halofit_on_device_vs_golden(golden):
     """`non linear = halofit` (BASELINE config 2) with the NonlinearModule step on the device: the
     correction table R_NL(k,tau) against the reference's nl_corr_density_, and the C_l of the fully device-resident
