@@ -4,12 +4,17 @@
 Metric (BASELINE.json): lensed-C_l spectra / s for the Planck-2018 LambdaCDM configuration
 (base_2018_plikHM_TTTEEE_lowl_lowE_lensing.ini: 1 massive neutrino species, halofit,
 l_max_scalars=2500, P(k) to 1 h/Mpc), measured on the hot path this repository replaces:
-PerturbationsModule -> TransferModule -> SpectraModule.
+PerturbationsModule -> (halofit) -> TransferModule -> SpectraModule -> LensingModule + P(k)
+(SURVEY.md section 8 with its two "next" rows).
 
-A "step" = one pass of the hot path over one batch of `--batch` cosmologies per GPU.  Upstream
-inputs (background/thermodynamics tables, ncdm grids, halofit correction, primordial spectrum)
-are synthetic-by-construction: they were generated once from the reference for the named
-configuration and are stored in tests/golden/planck18.npz.
+A "step" = one pass of the hot path over one batch of `--batch` cosmologies per GPU: ONE batched
+perturbation launch, then the per-cosmology stages.  Steps are scheduled by sweep.SweepPipeline on two
+sets of contexts (per-cosmology stages of step i under the launch of step i+1; --no-pipeline: strictly
+one step after the other); everything is drained before the clock stops.  Upstream inputs
+(background/thermodynamics tables, ncdm grids, primordial spectrum) are synthetic-by-construction: they
+were generated once from the reference for the named configuration and are stored in
+tests/golden/planck18.npz.  The reference arm times the same five module constructors of the unmodified
+reference (oracle/_ref) on all host cores.
 
   python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU)
   python bench.py --impl reference --steps K --warmup W    the reference's CPU implementation

@@ -1,9 +1,10 @@
 // Stage 1: per-wavenumber Einstein-Boltzmann integration on the device.
 //
-// One WARP integrates one (cosmology, k) mode from its initial time to today.  One CTA = one
-// warp, so the hardware block scheduler is the work queue; modes of all cosmologies of a batch
+// One WARP integrates one (cosmology, k) mode from its initial time to today.  A CTA is a cohort
+// of 1..8 such warps working on similar modes in lockstep (see PT_COHORT_SYNC below), and the
+// hardware block scheduler is the work queue; modes of all cosmologies of a batch
 // are issued in decreasing-cost order (longest chains first).  Everything of a mode lives in
-// shared memory (~190 B per equation + the hub inverse): the state vector, the NDF
+// shared memory (~150 B per equation + the hub inverse): the state vector, the NDF
 // backward-difference array and the factors of the Newton matrix (I - h/(G(1-alpha)) J).
 // Error norms / step control use warp-shuffle reductions; the approximation state machine
 // (tight coupling -> full hierarchy -> ur fluid / ncdm fluid -> radiation streaming) is per-mode
@@ -260,7 +261,7 @@ struct Stat {
   double tau_ini;
 };
 
-// State of the mode a warp integrates.  It lives in SHARED memory (one per CTA = warp): every
+// State of the mode a warp integrates.  It lives in SHARED memory (one per warp of the CTA): every
 // field is warp-uniform except the table caches, which hold one column per lane.  Keeping it out
 // of local memory matters: with several warps per SM the per-thread stack frames thrash the L1.
 struct Mode {
@@ -294,7 +295,8 @@ struct Mode {
 
 // ---------------------------------------------------------------------------------------------
 // background_at_tau (normal_info columns) + thermodynamics_at_z, cooperative over lanes.
-// `set` selects one of two interval caches: 0 = the time stepping, 1 = the source output (both
+// `set` used to select one of two interval caches (0 = the time stepping, 1 = the source output); there is one
+// cache now (shared memory per mode decides how many cohorts fit on an SM) and the argument is ignored (both
 // sweep the tables monotonically, at different times).  Entering a new interval also prefetches
 // the row the sweep will need next into L1.  Everything that only depends on time and that the RHS
 // would otherwise divide by is computed here ONCE per step, the divisions side by side in lanes.
