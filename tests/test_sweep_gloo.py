@@ -70,3 +70,78 @@ def test_cost_balanced_k_partition(golden):
         cost = [float(np.sum(k[p] + np.median(k))) for p in parts]
         # the longest chain (k_max) bounds the balance; everything else is spread evenly
         assert max(cost) <= max(1.05 * np.mean(cost), float(k[-1] + np.median(k)) * 1.001)
+
+
+def test_sweep_pipeline_scheduling_on_cpu(monkeypatch):
+    """Host logic of sweep.SweepPipeline without a GPU (the batched launch is stubbed): every batch passes through
+    front -> solve -> back on alternating context sets, launches never overlap by default, a set is only reused after
+    its previous batch has been consumed, and drain() returns the last results of every set."""
+    import threading
+    import time
+    from classpp_public_b200 import modules as M
+    from classpp_public_b200.sweep import SweepPipeline
+
+    log, lock = [], threading.Lock()
+    in_launch = [0]
+
+    def fake_solve_batch(pts):
+        with lock:
+            in_launch[0] += 1
+            assert in_launch[0] == 1, "two batched launches in flight"
+            log.append(("solve", pts[0][0], pts[0][2]))
+        time.sleep(0.02)
+        with lock:
+            in_launch[0] -= 1
+
+    monkeypatch.setattr(M.PerturbationsModule, "solve_batch", staticmethod(fake_solve_batch))
+    busy = {0: False, 1: False}
+
+    def front(s, b, tag):
+        if b == 0:
+            with lock:
+                assert not busy[s], "context set reused while its previous batch is still in flight"
+                busy[s] = True
+        return (s, b, tag)
+
+    def back(s, b, pt, tag):
+        assert pt == (s, b, tag)
+        time.sleep(0.005)
+        return tag * 100 + b
+
+    solved = []
+
+    def on_solved(s):
+        solved.append(s)
+
+    B = 4
+    pipe = SweepPipeline(B, front, back, n_sets=2, workers=4, on_solved=on_solved)
+    orig_run = pipe._run
+
+    def run_and_release(s, args):
+        out = orig_run(s, args)
+        with lock:
+            busy[s] = False
+        return out
+
+    pipe._run = run_and_release
+    for tag in range(5):
+        assert pipe.submit(tag) == tag % 2
+    res = pipe.drain()
+    assert sorted(t for _, _, t in log) == [0, 1, 2, 3, 4]
+    assert [s for _, s, _ in log].count(0) == 3 and solved.count(1) == 2
+    assert res == [[400 + b for b in range(B)], [300 + b for b in range(B)]]
+    assert len(pipe.solve_seconds) == 5
+    # overlapping mode: launches may be concurrent but are at least `stagger` apart
+    pipe.close()
+    starts = []
+
+    def fake_solve_batch2(pts):
+        starts.append(time.perf_counter())
+        time.sleep(0.05)
+
+    monkeypatch.setattr(M.PerturbationsModule, "solve_batch", staticmethod(fake_solve_batch2))
+    pipe = SweepPipeline(2, lambda s, b: (s, b), lambda s, b, pt: 0, n_sets=2, stagger=0.03, workers=2)
+    pipe.submit(); pipe.submit()
+    pipe.drain()
+    assert len(starts) == 2 and abs(starts[1] - starts[0]) >= 0.029 and abs(starts[1] - starts[0]) < 0.05
+    pipe.close()
