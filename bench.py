@@ -259,7 +259,8 @@ def run_gpu(args):
     nl_h = _NL(pinned(nl.nl_corr_density_m)) if nl is not None else None
     h2d = sum(inp_h.arrays[k].nbytes for k in ("bg.tau_table", "bg.background_table", "th.z_table",
                                                "th.thermodynamics_table")) * 2  # tables + their spline tables
-    h2d += (nl_h.nl_corr_density_m.nbytes if nl_h is not None else 0) + pk_h.nbytes
+    # the halofit table is an input only with --halofit input; on the device it is computed from the resident sources
+    h2d += (nl_h.nl_corr_density_m.nbytes if (nl_h is not None and not halofit_on_device) else 0) + pk_h.nbytes
     e2e_steps = max(1, min(args.steps, 3))
     h2d *= B
     step(inp_h, pk_h, nl_h, fetch=True)  # one untimed pass: first-touch allocations of the result buffers
