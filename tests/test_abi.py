@@ -41,9 +41,10 @@ def test_struct_sizes_match_header():
     src = textwrap.dedent("""
         #include <stdio.h>
         #include "clpp.h"
-        int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(clpp_background_desc), sizeof(clpp_thermo_desc),
+        int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(clpp_background_desc), sizeof(clpp_thermo_desc),
           sizeof(clpp_perturb_desc), sizeof(clpp_perturb_info), sizeof(clpp_kstat), sizeof(clpp_transfer_desc),
-          sizeof(clpp_transfer_info), sizeof(clpp_spectra_info)); return 0; }""")
+          sizeof(clpp_transfer_info), sizeof(clpp_spectra_info), sizeof(clpp_halofit_desc), sizeof(clpp_lensing_desc),
+          sizeof(clpp_lensing_info)); return 0; }""")
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
@@ -51,5 +52,6 @@ def test_struct_sizes_match_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     mine = [ctypes.sizeof(t) for t in (capi.BackgroundDesc, capi.ThermoDesc, capi.PerturbDesc, capi.PerturbInfo,
-                                       capi.KStat, capi.TransferDesc, capi.TransferInfo, capi.SpectraInfo)]
+                                       capi.KStat, capi.TransferDesc, capi.TransferInfo, capi.SpectraInfo,
+                                       capi.HalofitDesc, capi.LensingDesc, capi.LensingInfo)]
     assert sizes == mine
