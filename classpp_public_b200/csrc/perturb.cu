@@ -105,6 +105,9 @@ extern __shared__ double smem_all[];
 // cosmologies of a batch) and meet at a CTA barrier at the top of every step, so that they walk through the same code at
 // the same time: the per-step code footprint (~70 KB) exceeds the 32 KB instruction cache, and instruction fetch, not
 // issue slots, is what saturates an SM (profiles/r01_perturb_kernel_loaded_v3_footprint.txt).
+// The barrier is bar.sync 0 over the whole CTA, reached from different call sites (three integrators) by warps that are
+// each fully converged; a warp that finishes its mode (or hands it to the tail kernel) simply exits, which the hardware
+// counts as arrived, so cohorts may be ragged (last CTA of a launch, modes of different length).
 #define PT_MAX_WPC 8
 #define PT_LANE ((int)(threadIdx.x & 31))
 #define PT_WARP ((int)(threadIdx.x >> 5))
