@@ -51,11 +51,27 @@ LCDM_COARSE = dict(LCDM, **{
 # fallbacks of the device path (generic NDF, shared-memory Gauss-Jordan, 18 chains)
 NCDM3_COARSE = dict(LCDM_COARSE, **{"N_ur": 0.00641, "N_ncdm": 3, "m_ncdm": "0.02,0.02,0.02"})
 
+# config 3 stand-in (cl_permille.pre is not in the reference tree): denser k sampling, larger photon / ur
+# hierarchies, tighter integration tolerance, finer time sampling and l grid
+LCDM_DENSE = dict(LCDM, **{
+    "k_step_sub": 0.025,
+    "k_step_super": 0.001,
+    "l_max_g": 30,
+    "l_max_pol_g": 20,
+    "l_max_ur": 30,
+    "tol_perturb_integration": 1.0e-6,
+    "perturb_sampling_stepsize": 0.05,
+    "l_logstep": 1.06,
+    "l_linstep": 25,
+    "q_linstep": 0.3,
+})
+
 CONFIGS = {
     "lcdm": LCDM,
     "planck18": PLANCK18,
     "planck18_linear": PLANCK18_LINEAR,
     "ncdm3_deg": NCDM3_DEG,
     "lcdm_coarse": LCDM_COARSE,
+    "lcdm_dense": LCDM_DENSE,
     "ncdm3_coarse": NCDM3_COARSE,
 }

@@ -94,6 +94,24 @@ def test_planck18_ncdm_halofit_pipeline_vs_golden(golden):
     ctx.close()
 
 
+def test_dense_precision_config_vs_golden(golden):
+    """BASELINE config 3 stand-in (cl_permille.pre is not in the reference tree): denser k sampling (1200 modes), photon /
+    ur hierarchies up to l = 30, tol_perturb_integration = 1e-6, half the time-sampling step, finer l and q grids.
+    Unlensed C_l within 1e-4 and lensed TT/EE within 1e-4 of the reference."""
+    inp = golden("lcdm_dense")
+    a = inp.arrays
+    ctx, pt, tr, sp = run_pipeline(inp)
+    assert np.array_equal(pt.k_[0], a["ref.k"]) and np.array_equal(pt.tau_sampling_, a["ref.tau"])
+    assert pt.info.k_size == 1200 and int(pt.kprofile_[:, 0, :].max()) > 80  # equations of the largest interval
+    check_cl(sp, a["ref.cl"])
+    le = M.LensingModule(inp, sp)
+    ref = a["ref.cl_lensed"].reshape(-1, le.lt_size_)
+    mine = np.array([le.lensing_cl_at_l(l) for l in range(2, le.l_lensed_max_ + 1)])
+    for c in (le.index_lt_tt_, le.index_lt_ee_):
+        assert np.max(np.abs(mine[:, c] / ref[2:, c] - 1.0)) < CL_RTOL
+    ctx.close()
+
+
 def test_massive_neutrinos_degenerate_pipeline_vs_golden(golden):
     """BASELINE config 4 (degenerate form): 3 degenerate massive neutrinos, m = 0.02 eV."""
     inp = golden("ncdm3_deg")

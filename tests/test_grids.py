@@ -15,7 +15,7 @@ def build_grids(inp):
     return pt, tr
 
 
-@pytest.mark.parametrize("name", ["lcdm_coarse", "lcdm", "planck18", "ncdm3_deg", "ncdm3_coarse"])
+@pytest.mark.parametrize("name", ["lcdm_coarse", "lcdm", "planck18", "ncdm3_deg", "ncdm3_coarse", "lcdm_dense"])
 def test_grids_bit_exact_vs_golden(golden, name):
     inp = golden(name)
     a = inp.arrays
