@@ -48,6 +48,33 @@ def test_grids_bit_exact_vs_live_reference(reference, name):
     assert np.array_equal(tr.l_, ref.get("tr.l").astype(np.int32))
 
 
+def test_grids_bit_exact_for_a_latin_hypercube_sweep(reference):
+    """BASELINE config 5: the grids stay bit-exact when the cosmology moves (k_min, k_rec, tau_rec, angular rescaling,
+    q period ... all change): 5 points of the sweep's Latin hypercube on the coarse settings, against the live reference."""
+    if reference is None:
+        pytest.skip("oracle/_ref not built")
+    import os
+    from scipy.stats import qmc
+    from oracle import refprobe
+    from classpp_public_b200.configs import CONFIGS
+    from refutil import inputs_from_reference
+    lo = np.array([0.020, 0.10, 0.60, 2.9, 0.92, 0.03])   # omega_b, omega_cdm, h, ln(1e10 A_s), n_s, tau_reio
+    hi = np.array([0.024, 0.14, 0.75, 3.2, 1.00, 0.09])
+    sizes = set()
+    for x in qmc.scale(qmc.LatinHypercube(d=6, seed=0).random(5), lo, hi):
+        par = dict(CONFIGS["lcdm_coarse"], omega_b=x[0], omega_cdm=x[1], h=x[2], A_s=1e-10 * np.exp(x[3]), n_s=x[4],
+                   tau_reio=x[5])
+        ref = refprobe.RefCosmology(par, threads=os.cpu_count()).compute("transfer")
+        pt, tr = build_grids(inputs_from_reference(ref))
+        assert np.array_equal(pt.k_[0], ref.get("pt.k"))
+        assert np.array_equal(pt.tau_sampling_, ref.get("pt.tau_sampling"))
+        assert np.array_equal(tr.q_, ref.get("tr.q"))
+        assert np.array_equal(tr.l_, ref.get("tr.l").astype(np.int32))
+        sizes.add((pt.info.k_size, pt.info.tau_size, tr.info.q_size))
+        ref.close()
+    assert len(sizes) > 1  # the grids really differ from point to point
+
+
 def test_spline_tables_match_private_reference_tables(reference):
     """Our rebuilt second-derivative tables equal the reference's private ones bit for bit; checked
     indirectly (tau grid) above and directly here through the host interpolator."""
