@@ -60,6 +60,8 @@ struct HostTable {
   std::vector<double> ddy;  // [n_lines*n_cols]
 };
 
+// Gauss-Legendre nodes (ascending) and weights on [-1,1] (quadrature_gauss_legendre, tools/quadrature.c:752-788)
+int clpp_gauss_legendre(double* mu, double* w8, int n, double tol, char* err);
 void clpp_spline_table_lines(const double* x, int x_size, const double* y, int y_size, double* ddy);
 // array_interpolate_spline (bisection) / _growing_closeby (cursor)
 int clpp_interp_spline(const HostTable& t, double x, int* last_index, double* result, int result_size, char* err);

@@ -199,3 +199,33 @@ int clpp_thermodynamics_at_z(const clpp_ctx* c, double z, int mode, int* last_in
   if (mode == CLPP_INTER_NORMAL) return clpp_interp_spline(t, z, last_index, pv, t.n_cols, err);
   return clpp_interp_spline_closeby(t, z, last_index, pv, t.n_cols, err);
 }
+
+
+// Gauss-Legendre rule with n nodes on [-1,1] for the accurate lensing mode (lensing_module.cpp:237-248 calls
+// quadrature_gauss_legendre, tools/quadrature.c:752-788): each root of P_n in the upper half is refined by Newton's method
+// from the Chebyshev-like guess cos(pi (i - 1/4) / (n + 1/2)) until the update is below `tol`; the rule is symmetric.
+// Nodes are returned in ascending order, weights w = 2 / ((1 - x^2) P_n'(x)^2).
+int clpp_gauss_legendre(double* mu, double* w8, int n, double tol, char* err) {
+  const int half = (n + 1) / 2;
+  for (int i = 0; i < half; i++) {
+    double x = cos(CLPP_PI * ((double)(i + 1) - 0.25) / ((double)n + 0.5));
+    double dpn = 0.;
+    for (int it = 0;; it++) {
+      if (it == 10000) return clpp_fail(err, "maximum number of iteration reached: increase either _MAX_IT_ or tol\n");
+      double pn = 1., pnm1 = 0.;  // P_j(x), P_{j-1}(x) by the three-term recurrence
+      for (int j = 1; j <= n; j++) {
+        const double pnm2 = pnm1;
+        pnm1 = pn;
+        pn = ((2.0 * j - 1.0) * x * pnm1 - (j - 1.0) * pnm2) / j;
+      }
+      dpn = n * (x * pn - pnm1) / (x * x - 1.0);
+      const double x_old = x;
+      x = x_old - pn / dpn;
+      if (fabs(x - x_old) <= tol) break;
+    }
+    mu[i] = -x;
+    mu[n - 1 - i] = x;
+    w8[i] = w8[n - 1 - i] = 2.0 / ((1.0 - x * x) * dpn * dpn);
+  }
+  return CLPP_SUCCESS;
+}

@@ -292,32 +292,6 @@ __global__ void lens_cl_kernel(LensParams P) {
   }
 }
 
-// Gauss-Legendre nodes and weights on [-1,1] by Newton iteration on P_n (tools/quadrature.c:752-788)
-int gauss_legendre(double* mu, double* w8, int n, double tol, char* err) {
-  const int m = (n + 1) / 2;
-  for (int i = 1; i <= m; i++) {
-    double z = cos(CLPP_PI * ((double)i - 0.25) / ((double)n + 0.5)), z1, pp;
-    int counter = 0;
-    do {
-      double p1 = 1., p2 = 0.;
-      for (int j = 1; j <= n; j++) {
-        const double p3 = p2;
-        p2 = p1;
-        p1 = ((2. * j - 1.) * z * p2 - (j - 1.) * p3) / j;
-      }
-      pp = n * (z * p1 - p2) / (z * z - 1.);
-      z1 = z;
-      z = z1 - p1 / pp;
-      if (++counter == 10000) return clpp_fail(err, "maximum number of iteration reached: increase either _MAX_IT_ or tol\n");
-    } while (fabs(z - z1) > tol);
-    mu[i - 1] = -z;
-    mu[n - i] = z;
-    w8[i - 1] = 2. / ((1. - z * z) * pp * pp);
-    w8[n - i] = w8[i - 1];
-  }
-  return CLPP_SUCCESS;
-}
-
 }  // namespace
 
 int clpp_dev_lensing(clpp_ctx* c, const clpp_lensing_desc* ld, clpp_lensing_info* info, double* l_out, double* cl_lens_out,
@@ -358,7 +332,7 @@ int clpp_dev_lensing(clpp_ctx* c, const clpp_lensing_desc* ld, clpp_lensing_info
   if (ld->accurate_lensing) {
     if (c->gl_n != n_int || c->gl_tol != ld->tol_gauss_legendre) {
       c->gl_nodes.resize(2 * (size_t)n_int);
-      if (gauss_legendre(c->gl_nodes.data(), c->gl_nodes.data() + n_int, n_int, ld->tol_gauss_legendre, err)) return CLPP_FAILURE;
+      if (clpp_gauss_legendre(c->gl_nodes.data(), c->gl_nodes.data() + n_int, n_int, ld->tol_gauss_legendre, err)) return CLPP_FAILURE;
       c->gl_n = n_int;
       c->gl_tol = ld->tol_gauss_legendre;
     }

@@ -102,3 +102,36 @@ def test_unsupported_inputs_fail_loudly(golden):
     th = M.ThermodynamicsModule(bad, bg)
     with pytest.raises(M.CosmoComputationError, match="flat"):
         M.PerturbationsModule(bad, bg, th, solve=False)
+
+
+def test_gauss_legendre_host_routine_vs_numpy(tmp_path):
+    """The host routine behind accurate_lensing = 1 (csrc/host_tables.cpp: clpp_gauss_legendre, restating
+    tools/quadrature.c:752-788): nodes against numpy's leggauss, weights positive, symmetric and summing to 2."""
+    import os
+    import subprocess
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(ROOT, "classpp_public_b200", "csrc")
+    src = tmp_path / "gl.cpp"
+    src.write_text("""
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "clpp_internal.h"
+int main(int argc, char** argv) {
+  const int n = atoi(argv[1]);
+  std::vector<double> mu(n), w(n);
+  char err[2048];
+  if (clpp_gauss_legendre(mu.data(), w.data(), n, 2.220446049250313e-16, err)) return 1;
+  for (int i = 0; i < n; i++) printf("%.17g %.17g\\n", mu[i], w[i]);
+  return 0;
+}
+""")
+    exe = str(tmp_path / "gl")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-I", csrc,
+                           str(src), os.path.join(csrc, "host_tables.cpp"), "-o", exe])
+    for n in (7, 64, 1169):
+        out = np.array(subprocess.check_output([exe, str(n)]).split(), dtype=float).reshape(-1, 2)
+        x, w = np.polynomial.legendre.leggauss(n)
+        assert np.max(np.abs(out[:, 0] - x)) < 5e-16
+        assert np.all(out[:, 1] > 0) and np.array_equal(out[:, 1], out[::-1, 1])
+        assert abs(out[:, 1].sum() - 2.0) < 1e-14 and np.max(np.abs(out[:, 1] / w - 1.0)) < 1e-7
