@@ -31,6 +31,8 @@ struct clpp_ctx::Dev {
   int* queue_head = nullptr;  // atomic cursor into k_order
   double* jac_scratch = nullptr;  // per-CTA global workspace: hub block of the Jacobian
   double* ncdm = nullptr;         // [3][nq_tot]: q, w, dlnf0/dlnq
+  double* lane_scratch = nullptr; // per-thread slabs of the lane kernel (lane.cuh)
+  double* i2l1 = nullptr;         // 1/(2l+1)
   double* pt_tail = nullptr;      // hand-off records perturb_kernel -> perturb_tail_kernel
   size_t pt_tail_cap = 0;
   unsigned char *pt_cosmo = nullptr, *pt_modes = nullptr;  // batch descriptors of the last solve (PtCosmo[], int2[])

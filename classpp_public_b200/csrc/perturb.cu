@@ -42,62 +42,7 @@
 
 #include "device.h"
 
-#define PT_MAX_NCDM 3
-#define PT_MAX_INTERVALS 6
-#define PT_MAX_CHAINS 32
-#define PT_MAX_CHUNKS CLPP_PT_MAX_CHUNKS
-#define PT_FULL 0xffffffffu
-
-// ---------------------------------------------------------------------------------------------
-// per-cosmology inputs (global memory, one entry per context of the batch)
-struct PtCosmo {
-  const double *bg_tau, *bg_y, *bg_dd;
-  const double *th_z, *th_y, *th_dd;
-  const double *ncdm_q, *ncdm_w, *ncdm_dlnf0;
-  const double *k, *tau;
-  double* sources;  // [tp][k][tau]
-  clpp_kstat* kstat;
-  int bt_size, tt_size, k_size, tau_size;
-  double th_linear_below_z;  // < 0: never use linear interpolation
-  double n_e, YHe, T_cmb, tau_free_streaming, a_today;
-  double ncdm_M[PT_MAX_NCDM], ncdm_factor[PT_MAX_NCDM];
-};
-
-// settings common to every cosmology of a batch (kernel parameter -> constant bank)
-struct PtParams {
-  const PtCosmo* cosmo;
-  const int2* modes;  // (cosmology index, k index), decreasing expected cost
-  int n_modes;
-  double* hub_jac;  // per-CTA global scratch [nh_max*nh_max]: hub block of the Jacobian
-  double* tail;     // per-mode hand-off records for perturb_tail_kernel (nullptr: no tail kernel)
-  int bg_size, bg_size_normal, th_size;
-  // background column indices
-  int ia, iH, iHp, irho_g, irho_b, irho_cdm, irho_ur, irho_ncdm1, ip_ncdm1, ipseudo_p_ncdm1;
-  // thermo column indices
-  int ixe, idkappa, iddkappa, idddkappa, iexp_m_kappa, ig, idg, iddg, icb2, iwb, iTb, itau_d, irate, ir_d, idcb2, iddcb2;
-  int compute_cb2_derivatives, compute_damping_scale;
-  int has_ur, has_ncdm, N_ncdm;
-  int ncdm_q_size[PT_MAX_NCDM], ncdm_q_off[PT_MAX_NCDM], nq_tot;
-  // precision
-  double start_small_k_at_tau_c_over_tau_h, start_large_k_at_tau_h_over_tau_k;
-  double tca_trigger_tau_c_over_tau_h, tca_trigger_tau_c_over_tau_k;
-  int tca_method, rsa_method, ufa_method, ncdmfa_method;
-  double rsa_trigger, ufa_trigger, ncdmfa_trigger;
-  int l_max_g, l_max_pol_g, l_max_ur, l_max_ncdm;
-  double tol_ncdm_initial_w, tol_tau_approx, rtol, hmin_allowed;
-  double curvature_ini, three_ceff2_ur, three_cvis2_ur;
-  int switch_sw, switch_eisw, switch_lisw, switch_dop, switch_pol;
-  double eisw_lisw_split_z;
-  int tp_t0, tp_t1, tp_t2, tp_p, tp_delta_m, tp_delta_cb, tp_phi_plus_psi;
-  // shared-memory geometry (offsets in doubles into the CTA's dynamic shared memory)
-  int evolver;        // 0 = rk (Cash-Karp), 1 = ndf15
-  double rk_stepsize; // perturb_integration_stepsize (rk only)
-  int force_generic;  // developer/test switch: integrate every interval with the generic shared-memory NDF
-  int wpc, wstride;   // warps (k modes) per CTA; doubles of shared memory per warp
-  int scr_stride;     // doubles of global scratch per mode (hub Jacobian + 4 vectors)
-  int neq_max, np, nh_max, ldh;
-  int o_mode, o_hubtmp, o_nw, o_i2l1, n_i2l1, o_tabc, ncol, o_vec, o_sinv, o_int;
-};
+#include "pt_types.h"
 
 extern __shared__ double smem_all[];
 // A CTA is a COHORT of P.wpc warps (1..PT_MAX_WPC), one k mode per warp, each with its own shared-memory region.
@@ -144,9 +89,6 @@ __constant__ double c_erconst[5] = {-37.0 / 200 * 1.0 + 1.0 / 2.0, -1.0 / 9.0 * 
 __constant__ double c_invint[7] = {0., 1.0, 0.5, 1.0 / 3.0, 0.25, 0.2, 1.0 / 6.0};
 __constant__ double c_U[5][5] = {{-1, -2, -3, -4, -5}, {0, 1, 3, 6, 10}, {0, 0, -1, -4, -10}, {0, 0, 0, 1, 5}, {0, 0, 0, 0, -1}};
 
-struct Approx {
-  int tca_off, rsa_on, ufa_on, ncdmfa_on;  // monotone flags (0 -> 1 in time)
-};
 
 struct Layout {
   int neq;
@@ -2985,6 +2927,19 @@ __global__ void __launch_bounds__(32 * PT_TAIL_MAX_WPC, PT_TAIL_MIN_BLOCKS / PT_
 }
 
 // =============================================================================================
+// LANE KERNEL: one THREAD per mode (lane.cuh).  The default path for evolver = ndf15.
+// =============================================================================================
+#include "lane.cuh"
+
+__global__ void __launch_bounds__(LN_CTA) perturb_lane_kernel(const __grid_constant__ PtParams P) {
+  const int slot = blockIdx.x * LN_CTA + threadIdx.x;
+  if (slot >= P.n_modes) return;
+  const int2 md = P.modes[slot];
+  double* mem = P.lane_scratch + (size_t)blockIdx.x * P.ln_words * LN_CTA + threadIdx.x;
+  ln_mode(P, mem, P.cosmo + md.x, md.y);
+}
+
+// =============================================================================================
 // host side
 // =============================================================================================
 
@@ -3077,7 +3032,18 @@ static void set_geometry(PtParams& P, int neq_max, int nh_max, const clpp_pertur
   P.wpc = 1;
   P.scr_stride = P.nh_max * P.nh_max + 4 * P.np;
   P.wstride = (int)((((size_t)P.o_int * sizeof(double) + (size_t)(2 * P.nh_max + 3 * PT_MAX_CHAINS) * sizeof(int)) + 15) / 16 * 2);
+  // per-thread slab of the lane kernels (lane.cuh)
+  P.lo_vec = 0;
+  P.lo_nw = LV_COUNT * P.np;
+  P.lo_jhh = P.lo_nw + 4 * P.nq_tot;
+  P.lo_lu = P.lo_jhh + P.nh_max * P.nh_max;
+  P.lo_piv = P.lo_lu + P.nh_max * P.nh_max;
+  P.lo_ch = P.lo_piv + P.nh_max;
+  P.ln_words = P.lo_ch + 2 * PT_MAX_CHAINS;
 }
+
+// the common block of a context, for the developer harness tests/hostsim (CPU execution of the lane program)
+extern "C" int clpp_pt_fill_common(const clpp_ctx* c, PtParams* P, char* err) { return fill_common(c, *P, err); }
 
 // dynamic shared memory of one warp (one k mode); a CTA of P.wpc warps takes wpc times this
 static size_t perturb_smem_bytes(const PtParams& P) { return (size_t)P.wstride * sizeof(double); }
@@ -3162,132 +3128,164 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   std::vector<int> perm(n_modes);
   for (int i = 0; i < n_modes; i++) perm[i] = i;
   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-  // Launch groups.  Group L: the modes with long radiation-streaming tails (k >= 3 % of k_max: measured optimum), high-priority
-  // stream, issued first: they finish their early phases quickly and run their tails -- the serial critical
-  // path -- while the bulk is still in the generic kernel.  The bulk is dealt round-robin into chunks, one
-  // low-priority stream each (generic kernel -> tail kernel), so that the tails of a chunk overlap the
-  // generic phases of the next ones instead of all waiting for the last generic CTA.
-  const bool force_generic = getenv("CLPP_GENERIC_ONLY") != nullptr;
-  const bool use_tail = getenv("CLPP_NO_TAIL") == nullptr && !force_generic && c0->pd.evolver == 1;
-  int n_long = 0;
-  if (use_tail && n_modes > 0) {
-    const double kcut_frac = getenv("CLPP_KCUT") ? atof(getenv("CLPP_KCUT")) : 0.03;  // developer knob
-    const double kcut = kcut_frac * cost[perm[0]];
-    while (n_long < n_modes && cost[perm[n_long]] >= kcut) n_long++;
-    if (n_long == n_modes) n_long = 0;  // nothing to overlap with
-  }
-  const int n_bulk = n_modes - n_long;
-  // cohort width: modes per CTA. Batches of several cosmologies put the same k of neighbouring cosmologies side by side in
-  // the sorted order (near-identical step sequences); a single cosmology is a latency problem and keeps one mode per CTA.
-  const size_t smem1 = perturb_smem_bytes(P);
-  int wpc = getenv("CLPP_COHORT") ? atoi(getenv("CLPP_COHORT")) : (n_ctx >= 4 ? 4 : 1);
-  wpc = std::max(1, std::min(wpc, PT_MAX_WPC));
-  while (wpc > 1 && smem1 * wpc > 227 * 1024) wpc--;
-  int wpc_tail = getenv("CLPP_COHORT_TAIL") ? atoi(getenv("CLPP_COHORT_TAIL")) : std::min(wpc, PT_TAIL_MAX_WPC);
-  wpc_tail = std::max(1, std::min(wpc_tail, PT_TAIL_MAX_WPC));
-  // the long-tail group is the latency-critical path: lockstep only pays for it once the batch is throughput-bound
-  // (measured, scripts/sweep_varied.py: 32 different cosmologies lose 15 % with cohorts there, 96 gain 4 %)
-  int wpc_long = getenv("CLPP_COHORT_LONG") ? atoi(getenv("CLPP_COHORT_LONG")) : (n_ctx >= 64 ? wpc : 1);
-  wpc_long = std::max(1, std::min(wpc_long, wpc));
-  const int chunk_modes = getenv("CLPP_CHUNK_MODES") ? atoi(getenv("CLPP_CHUNK_MODES")) : 4000;  // developer knob
-  const int n_chunks = use_tail ? std::max(1, std::min(PT_MAX_CHUNKS, n_bulk / std::max(chunk_modes, 1))) : 1;
-  std::vector<int2> sorted(n_modes);
-  std::vector<int> chunk_first(n_chunks + 1, n_long);
-  for (int i = 0; i < n_long; i++) sorted[i] = modes[perm[i]];
-  {
-    int pos = n_long;
-    for (int c = 0; c < n_chunks; c++) {
-      chunk_first[c] = pos;
-      for (int i = n_long; i < n_modes; i++)  // cohorts (wpc consecutive modes of the sorted order) stay together
-        if (((i - n_long) / wpc) % n_chunks == c) sorted[pos++] = modes[perm[i]];
-    }
-    chunk_first[n_chunks] = pos;
-  }
-
-  if (clpp_dev_reserve(d0, &d0->pt_cosmo, n_ctx * sizeof(PtCosmo), err)) return CLPP_FAILURE;
-  if (clpp_dev_reserve(d0, &d0->pt_modes, (size_t)std::max(n_modes, 1) * sizeof(int2), err)) return CLPP_FAILURE;
-  if (clpp_dev_reserve(d0, &d0->jac_scratch, (size_t)std::max(n_modes, 1) * P.scr_stride, err))
-    return CLPP_FAILURE;
-  CLPP_CUDA(cudaMemcpyAsync(d0->pt_cosmo, cosmo.data(), n_ctx * sizeof(PtCosmo), cudaMemcpyHostToDevice, st), err);
-  CLPP_CUDA(cudaMemcpyAsync(d0->pt_modes, sorted.data(), n_modes * sizeof(int2), cudaMemcpyHostToDevice, st), err);
-  P.cosmo = (const PtCosmo*)d0->pt_cosmo;
-  P.modes = (const int2*)d0->pt_modes;
-  P.n_modes = n_modes;
-  P.hub_jac = d0->jac_scratch;
-  // hand-off records of the tail (radiation-streaming) kernel
-  P.force_generic = force_generic;
-  if (use_tail) {
-    if (clpp_dev_reserve(d0, &d0->pt_tail, (size_t)std::max(n_modes, 1) * TL_STRIDE, err)) return CLPP_FAILURE;
-    CLPP_CUDA(cudaMemsetAsync(d0->pt_tail, 0, (size_t)std::max(n_modes, 1) * TL_STRIDE * sizeof(double), st), err);
-    P.tail = d0->pt_tail;
-  }
-
-  const size_t smem = perturb_smem_bytes(P);
-  CLPP_CHECK(smem <= 227 * 1024, err,
-             "state vector of %d equations needs %zu bytes of shared memory per k-mode (> 227 KB): reduce l_max_ncdm / "
-             "the number of ncdm momentum bins", P.neq_max, smem);
-  // developer knob: extra dynamic shared memory per CTA of the generic kernel (limits the CTAs per SM)
-  // Two unsynchronised cohorts on one SM share the instruction cache again: measured (bench.py --batch 64) the large
-  // Planck-18 system (136 equations) runs 4 % faster with ONE 4-mode cohort per SM, the small LCDM one (46 equations,
-  // smaller hot code) 1.7x faster with two. Large systems therefore claim more than half of the SM's shared memory.
-  size_t smem_pad = 0;
-  if (wpc > 1 && P.neq_max >= 100 && smem * wpc <= 114 * 1024) smem_pad = 115 * 1024 - smem * wpc;
-  if (getenv("CLPP_SMEM_PAD_KB")) smem_pad = (size_t)atoi(getenv("CLPP_SMEM_PAD_KB")) * 1024;  // developer knob
-  CLPP_CUDA(cudaFuncSetAttribute(perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * wpc + smem_pad)), err);
-  P.wpc = wpc;
-  PtParams Pt = P;  // geometry of the tail kernel: at most 16 equations, all hub
-  set_geometry(Pt, 16, 16, c0->pd);
-  const size_t smem_tail = perturb_smem_bytes(Pt);
-  CLPP_CUDA(cudaFuncSetAttribute(perturb_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_tail * wpc_tail)), err);
-  Pt.wpc = wpc_tail;
-  if (getenv("CLPP_VERBOSE"))
-    fprintf(stderr, "[clpp] perturb: %d modes, shared memory per mode %zu B (tail %zu B), sizeof(Mode) %zu, neq_max %d, hub %d, "
-            "modes per CTA %d (tail %d)\n", n_modes, smem, smem_tail, sizeof(Mode), P.neq_max, P.nh_max, wpc, wpc_tail);
-  for (int i = 0; i < 6; i++)
-    if (!d0->ev2[i]) cudaEventCreate(&d0->ev2[i]);
-  if (!d0->stream2) {
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority
-    CLPP_CUDA(cudaStreamCreateWithPriority(&d0->stream2, cudaStreamNonBlocking, prio_lo), err);
-    CLPP_CUDA(cudaStreamCreateWithPriority(&d0->stream_hi, cudaStreamNonBlocking, prio_hi), err);
-    for (int c = 0; c < PT_MAX_CHUNKS; c++) {
-      CLPP_CUDA(cudaStreamCreateWithPriority(&d0->chunk_stream[c], cudaStreamNonBlocking, prio_lo), err);
-      CLPP_CUDA(cudaEventCreateWithFlags(&d0->chunk_done[c], cudaEventDisableTiming), err);
-    }
-  }
-  cudaStream_t sth = d0->stream_hi;
-  auto launch_group = [&](cudaStream_t s, int first, int count, int wpc, int wpc_tail) {
-    if (count <= 0) return;
-    PtParams G = P, Gt = Pt;
-    G.wpc = wpc; Gt.wpc = wpc_tail;
-    G.modes = P.modes + first; G.n_modes = count;
-    G.hub_jac = P.hub_jac + (size_t)first * P.scr_stride;
-    G.tail = P.tail ? P.tail + (size_t)first * TL_STRIDE : nullptr;
-    perturb_kernel<<<(count + wpc - 1) / wpc, 32 * wpc, smem * wpc + smem_pad, s>>>(G);
-    c0->launches++;
-    if (use_tail) {
-      Gt.modes = G.modes; Gt.n_modes = count; Gt.tail = G.tail; Gt.hub_jac = G.hub_jac;
-      perturb_tail_kernel<<<(count + wpc_tail - 1) / wpc_tail, 32 * wpc_tail, smem_tail * wpc_tail, s>>>(Gt);
+  // ---- default path: one THREAD per mode (lane.cuh).  The warp-per-mode kernels below remain for evolver = rk and as
+  // a cross-check (CLPP_WARP_PATH=1, or any of their developer knobs).
+  const bool use_lane = c0->pd.evolver == 1 && !getenv("CLPP_WARP_PATH") && !getenv("CLPP_GENERIC_ONLY") &&
+                        !getenv("CLPP_NO_TAIL") && !getenv("CLPP_COHORT");
+  if (use_lane) {
+    std::vector<int2> sorted(n_modes);
+    for (int i = 0; i < n_modes; i++) sorted[i] = modes[perm[i]];
+    if (clpp_dev_reserve(d0, &d0->pt_cosmo, n_ctx * sizeof(PtCosmo), err)) return CLPP_FAILURE;
+    if (clpp_dev_reserve(d0, &d0->pt_modes, (size_t)std::max(n_modes, 1) * sizeof(int2), err)) return CLPP_FAILURE;
+    CLPP_CUDA(cudaMemcpyAsync(d0->pt_cosmo, cosmo.data(), n_ctx * sizeof(PtCosmo), cudaMemcpyHostToDevice, st), err);
+    CLPP_CUDA(cudaMemcpyAsync(d0->pt_modes, sorted.data(), n_modes * sizeof(int2), cudaMemcpyHostToDevice, st), err);
+    std::vector<double> i2l1(P.n_i2l1);
+    for (int l = 0; l < P.n_i2l1; l++) i2l1[l] = 1.0 / (2.0 * l + 1.0);
+    if (clpp_dev_reserve(d0, &d0->i2l1, (size_t)P.n_i2l1, err)) return CLPP_FAILURE;
+    CLPP_CUDA(cudaMemcpyAsync(d0->i2l1, i2l1.data(), P.n_i2l1 * sizeof(double), cudaMemcpyHostToDevice, st), err);
+    const int n_cta = (n_modes + LN_CTA - 1) / LN_CTA;
+    if (clpp_dev_reserve(d0, &d0->lane_scratch, (size_t)std::max(n_cta, 1) * P.ln_words * LN_CTA, err)) return CLPP_FAILURE;
+    P.cosmo = (const PtCosmo*)d0->pt_cosmo;
+    P.modes = (const int2*)d0->pt_modes;
+    P.n_modes = n_modes;
+    P.lane_scratch = d0->lane_scratch;
+    P.i2l1 = d0->i2l1;
+    if (getenv("CLPP_VERBOSE"))
+      fprintf(stderr, "[clpp] perturb (lane kernel): %d modes, %d CTAs of %d threads, %d doubles of scratch per mode, neq_max %d, hub %d\n",
+              n_modes, n_cta, LN_CTA, P.ln_words, P.neq_max, P.nh_max);
+    cudaEventRecord(d0->ev[0], st);
+    if (n_modes > 0) {
+      perturb_lane_kernel<<<n_cta, LN_CTA, 0, st>>>(P);
       c0->launches++;
     }
-  };
-  cudaEventRecord(d0->ev[0], st);
-  if (n_modes > 0) {
-    cudaEventRecord(d0->ev2[4], st);        // uploads on st are complete before the other streams start
-    if (n_long > 0) {
-      cudaStreamWaitEvent(sth, d0->ev2[4], 0);
-      launch_group(sth, 0, n_long, wpc_long, std::min(wpc_long, wpc_tail));  // high priority: its tail CTAs take the slots as they free up
-      cudaEventRecord(d0->ev2[5], sth);
-      cudaStreamWaitEvent(st, d0->ev2[5], 0);
+  } else {
+    // Launch groups.  Group L: the modes with long radiation-streaming tails (k >= 3 % of k_max: measured optimum), high-priority
+    // stream, issued first: they finish their early phases quickly and run their tails -- the serial critical
+    // path -- while the bulk is still in the generic kernel.  The bulk is dealt round-robin into chunks, one
+    // low-priority stream each (generic kernel -> tail kernel), so that the tails of a chunk overlap the
+    // generic phases of the next ones instead of all waiting for the last generic CTA.
+    const bool force_generic = getenv("CLPP_GENERIC_ONLY") != nullptr;
+    const bool use_tail = getenv("CLPP_NO_TAIL") == nullptr && !force_generic && c0->pd.evolver == 1;
+    int n_long = 0;
+    if (use_tail && n_modes > 0) {
+      const double kcut_frac = getenv("CLPP_KCUT") ? atof(getenv("CLPP_KCUT")) : 0.03;  // developer knob
+      const double kcut = kcut_frac * cost[perm[0]];
+      while (n_long < n_modes && cost[perm[n_long]] >= kcut) n_long++;
+      if (n_long == n_modes) n_long = 0;  // nothing to overlap with
     }
-    for (int c = 0; c < n_chunks; c++) {
-      cudaStream_t sc = d0->chunk_stream[c];
-      cudaStreamWaitEvent(sc, d0->ev2[4], 0);
-      launch_group(sc, chunk_first[c], chunk_first[c + 1] - chunk_first[c], wpc, wpc_tail);
-      cudaEventRecord(d0->chunk_done[c], sc);
-      cudaStreamWaitEvent(st, d0->chunk_done[c], 0);
+    const int n_bulk = n_modes - n_long;
+    // cohort width: modes per CTA. Batches of several cosmologies put the same k of neighbouring cosmologies side by side in
+    // the sorted order (near-identical step sequences); a single cosmology is a latency problem and keeps one mode per CTA.
+    const size_t smem1 = perturb_smem_bytes(P);
+    int wpc = getenv("CLPP_COHORT") ? atoi(getenv("CLPP_COHORT")) : (n_ctx >= 4 ? 4 : 1);
+    wpc = std::max(1, std::min(wpc, PT_MAX_WPC));
+    while (wpc > 1 && smem1 * wpc > 227 * 1024) wpc--;
+    int wpc_tail = getenv("CLPP_COHORT_TAIL") ? atoi(getenv("CLPP_COHORT_TAIL")) : std::min(wpc, PT_TAIL_MAX_WPC);
+    wpc_tail = std::max(1, std::min(wpc_tail, PT_TAIL_MAX_WPC));
+    // the long-tail group is the latency-critical path: lockstep only pays for it once the batch is throughput-bound
+    // (measured, scripts/sweep_varied.py: 32 different cosmologies lose 15 % with cohorts there, 96 gain 4 %)
+    int wpc_long = getenv("CLPP_COHORT_LONG") ? atoi(getenv("CLPP_COHORT_LONG")) : (n_ctx >= 64 ? wpc : 1);
+    wpc_long = std::max(1, std::min(wpc_long, wpc));
+    const int chunk_modes = getenv("CLPP_CHUNK_MODES") ? atoi(getenv("CLPP_CHUNK_MODES")) : 4000;  // developer knob
+    const int n_chunks = use_tail ? std::max(1, std::min(PT_MAX_CHUNKS, n_bulk / std::max(chunk_modes, 1))) : 1;
+    std::vector<int2> sorted(n_modes);
+    std::vector<int> chunk_first(n_chunks + 1, n_long);
+    for (int i = 0; i < n_long; i++) sorted[i] = modes[perm[i]];
+    {
+      int pos = n_long;
+      for (int c = 0; c < n_chunks; c++) {
+        chunk_first[c] = pos;
+        for (int i = n_long; i < n_modes; i++)  // cohorts (wpc consecutive modes of the sorted order) stay together
+          if (((i - n_long) / wpc) % n_chunks == c) sorted[pos++] = modes[perm[i]];
+      }
+      chunk_first[n_chunks] = pos;
     }
-  }
+  
+    if (clpp_dev_reserve(d0, &d0->pt_cosmo, n_ctx * sizeof(PtCosmo), err)) return CLPP_FAILURE;
+    if (clpp_dev_reserve(d0, &d0->pt_modes, (size_t)std::max(n_modes, 1) * sizeof(int2), err)) return CLPP_FAILURE;
+    if (clpp_dev_reserve(d0, &d0->jac_scratch, (size_t)std::max(n_modes, 1) * P.scr_stride, err))
+      return CLPP_FAILURE;
+    CLPP_CUDA(cudaMemcpyAsync(d0->pt_cosmo, cosmo.data(), n_ctx * sizeof(PtCosmo), cudaMemcpyHostToDevice, st), err);
+    CLPP_CUDA(cudaMemcpyAsync(d0->pt_modes, sorted.data(), n_modes * sizeof(int2), cudaMemcpyHostToDevice, st), err);
+    P.cosmo = (const PtCosmo*)d0->pt_cosmo;
+    P.modes = (const int2*)d0->pt_modes;
+    P.n_modes = n_modes;
+    P.hub_jac = d0->jac_scratch;
+    // hand-off records of the tail (radiation-streaming) kernel
+    P.force_generic = force_generic;
+    if (use_tail) {
+      if (clpp_dev_reserve(d0, &d0->pt_tail, (size_t)std::max(n_modes, 1) * TL_STRIDE, err)) return CLPP_FAILURE;
+      CLPP_CUDA(cudaMemsetAsync(d0->pt_tail, 0, (size_t)std::max(n_modes, 1) * TL_STRIDE * sizeof(double), st), err);
+      P.tail = d0->pt_tail;
+    }
+  
+    const size_t smem = perturb_smem_bytes(P);
+    CLPP_CHECK(smem <= 227 * 1024, err,
+               "state vector of %d equations needs %zu bytes of shared memory per k-mode (> 227 KB): reduce l_max_ncdm / "
+               "the number of ncdm momentum bins", P.neq_max, smem);
+    // developer knob: extra dynamic shared memory per CTA of the generic kernel (limits the CTAs per SM)
+    // Two unsynchronised cohorts on one SM share the instruction cache again: measured (bench.py --batch 64) the large
+    // Planck-18 system (136 equations) runs 4 % faster with ONE 4-mode cohort per SM, the small LCDM one (46 equations,
+    // smaller hot code) 1.7x faster with two. Large systems therefore claim more than half of the SM's shared memory.
+    size_t smem_pad = 0;
+    if (wpc > 1 && P.neq_max >= 100 && smem * wpc <= 114 * 1024) smem_pad = 115 * 1024 - smem * wpc;
+    if (getenv("CLPP_SMEM_PAD_KB")) smem_pad = (size_t)atoi(getenv("CLPP_SMEM_PAD_KB")) * 1024;  // developer knob
+    CLPP_CUDA(cudaFuncSetAttribute(perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * wpc + smem_pad)), err);
+    P.wpc = wpc;
+    PtParams Pt = P;  // geometry of the tail kernel: at most 16 equations, all hub
+    set_geometry(Pt, 16, 16, c0->pd);
+    const size_t smem_tail = perturb_smem_bytes(Pt);
+    CLPP_CUDA(cudaFuncSetAttribute(perturb_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_tail * wpc_tail)), err);
+    Pt.wpc = wpc_tail;
+    if (getenv("CLPP_VERBOSE"))
+      fprintf(stderr, "[clpp] perturb: %d modes, shared memory per mode %zu B (tail %zu B), sizeof(Mode) %zu, neq_max %d, hub %d, "
+              "modes per CTA %d (tail %d)\n", n_modes, smem, smem_tail, sizeof(Mode), P.neq_max, P.nh_max, wpc, wpc_tail);
+    for (int i = 0; i < 6; i++)
+      if (!d0->ev2[i]) cudaEventCreate(&d0->ev2[i]);
+    if (!d0->stream2) {
+      int prio_lo = 0, prio_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority
+      CLPP_CUDA(cudaStreamCreateWithPriority(&d0->stream2, cudaStreamNonBlocking, prio_lo), err);
+      CLPP_CUDA(cudaStreamCreateWithPriority(&d0->stream_hi, cudaStreamNonBlocking, prio_hi), err);
+      for (int c = 0; c < PT_MAX_CHUNKS; c++) {
+        CLPP_CUDA(cudaStreamCreateWithPriority(&d0->chunk_stream[c], cudaStreamNonBlocking, prio_lo), err);
+        CLPP_CUDA(cudaEventCreateWithFlags(&d0->chunk_done[c], cudaEventDisableTiming), err);
+      }
+    }
+    cudaStream_t sth = d0->stream_hi;
+    auto launch_group = [&](cudaStream_t s, int first, int count, int wpc, int wpc_tail) {
+      if (count <= 0) return;
+      PtParams G = P, Gt = Pt;
+      G.wpc = wpc; Gt.wpc = wpc_tail;
+      G.modes = P.modes + first; G.n_modes = count;
+      G.hub_jac = P.hub_jac + (size_t)first * P.scr_stride;
+      G.tail = P.tail ? P.tail + (size_t)first * TL_STRIDE : nullptr;
+      perturb_kernel<<<(count + wpc - 1) / wpc, 32 * wpc, smem * wpc + smem_pad, s>>>(G);
+      c0->launches++;
+      if (use_tail) {
+        Gt.modes = G.modes; Gt.n_modes = count; Gt.tail = G.tail; Gt.hub_jac = G.hub_jac;
+        perturb_tail_kernel<<<(count + wpc_tail - 1) / wpc_tail, 32 * wpc_tail, smem_tail * wpc_tail, s>>>(Gt);
+        c0->launches++;
+      }
+    };
+    cudaEventRecord(d0->ev[0], st);
+    if (n_modes > 0) {
+      cudaEventRecord(d0->ev2[4], st);        // uploads on st are complete before the other streams start
+      if (n_long > 0) {
+        cudaStreamWaitEvent(sth, d0->ev2[4], 0);
+        launch_group(sth, 0, n_long, wpc_long, std::min(wpc_long, wpc_tail));  // high priority: its tail CTAs take the slots as they free up
+        cudaEventRecord(d0->ev2[5], sth);
+        cudaStreamWaitEvent(st, d0->ev2[5], 0);
+      }
+      for (int c = 0; c < n_chunks; c++) {
+        cudaStream_t sc = d0->chunk_stream[c];
+        cudaStreamWaitEvent(sc, d0->ev2[4], 0);
+        launch_group(sc, chunk_first[c], chunk_first[c + 1] - chunk_first[c], wpc, wpc_tail);
+        cudaEventRecord(d0->chunk_done[c], sc);
+        cudaStreamWaitEvent(st, d0->chunk_done[c], 0);
+      }
+    }
+}
   cudaEventRecord(d0->ev[1], st);
   CLPP_CUDA(cudaGetLastError(), err);
   for (int b = 0; b < n_ctx; b++) {
