@@ -3,9 +3,11 @@
 // A warp therefore advances 32 modes at once -- the same k of 32 neighbouring cosmologies of a sweep, or 32 neighbouring
 // k of one cosmology -- and every instruction does useful work for 32 modes (the warp-per-mode kernels of perturb.cu
 // evaluate all scalar "hub" mathematics once per warp).  The per-mode state (state vector, NDF backward differences,
-// Newton-matrix factors; 20..100 KB) lives in a per-thread slab of GLOBAL memory laid out element-major
-// (element e of the 64 threads of a CTA are 512 contiguous bytes), so every access of a warp is coalesced; the
-// working set streams through L1/L2.  The time stepping is a flat state machine -- one step ATTEMPT per loop
+// Newton-matrix factors; 10..100 KB) lives in a per-thread slab of LOCAL memory (a stack array of the kernel): the
+// hardware interleaves local memory by thread, so element e of the 32 lanes of a warp is 256 contiguous bytes and
+// every access of a warp is coalesced, and -- unlike global memory, whose stores write through and invalidate the
+// line -- local memory is cached WRITE-BACK in L1 (a global-memory slab made every load after a store an L2 round
+// trip: 120 k cycles per step for a 7-equation system).  The working set streams through L1/L2.  The time stepping is a flat state machine -- one step ATTEMPT per loop
 // iteration, rejected attempts simply come round again -- so that lanes whose steps fail or whose Newton iteration
 // needs a new Jacobian do not stall the other 31 lanes of the warp.
 //
@@ -52,7 +54,7 @@ static inline double ln_root_n(double x, double n) { return (double)exp2f(log2f(
 #else
 #define LN_FN __device__ __forceinline__
 #define LN_NOINLINE __device__ __noinline__
-#define LN_STRIDE LN_CTA
+#define LN_STRIDE 1
 #define LN_LDG(p) __ldg(p)
 #define LN_CLOCK() clock64()
 // x^(1/n) for the step-size heuristics: float accuracy is ample for a controller that only compares and clamps the result
@@ -72,10 +74,14 @@ enum {
   LV_IP, LV_MU,                       // chain factors: 1/pivot, T[i,i+1]/p[i+1]
   LV_COUNT
 };
-#define LVEC(slot, i) LM(P.lo_vec + (slot) * P.np + (i))
+#define LVP(slot) (mem + (size_t)(P.lo_vec + (slot) * P.np))
 // per-chain scalars: J[root, first], its eliminated multiplier
 #define LCH_JUR(c) LM(P.lo_ch + (c))
 #define LCH_MUR(c) LM(P.lo_ch + PT_MAX_CHAINS + (c))
+// The vector loops below are written as small functions over __restrict__ pointers, one per vector: with a single
+// base pointer the compiler must assume that every store may alias every later load and serialises the loop on the
+// load latency; a lone warp (single-cosmology runs, the long high-k chains of a batch) has nothing else to hide it.
+#define LN_UNROLL _Pragma("unroll 4")
 // metric scalars the hub rows depend on (the low-rank part of the hub Jacobian)
 enum { MS_HP = 0, MS_EP, MS_AP, MS_ETA, MS_COUNT };
 #define LN_BS_MAX 8  // largest diagonal block of the hub (photon-baryon plasma: delta_g theta_g shear_g pol0 pol1 pol2 delta_b theta_b)
@@ -339,15 +345,12 @@ LN_FN void ln_chain(const LnLayout& L, int c, int& start, int& len, int& root) {
 // -------------------------------------------------------------------------------------------------
 // Right-hand side f(tau, y) for the environment in M.e.  Fills M.m (metric and by-products).
 //  LR_MATTER: also delta_m, delta_cb.  LR_HUB / LR_CHAINS: which rows of dy to write (none: metric only).
-//  LR_GIVEN_METRIC: the four metric scalars ms[] are imposed instead of being computed from y (Jacobian probes:
-//  the hub block is D + U V^T with V^T = d(metric)/dy, U = d(rows)/d(metric), D = d(rows)/dy at fixed metric).
-LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, double* __restrict__ mem, int sy, int sdy, int flags, const double* ms_in) {
+LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, const double* __restrict__ y, double* __restrict__ dy,
+                        const double* __restrict__ nw, int flags) {
   const LnLayout& L = M.L;
   const Approx ap = M.ap;
   const LnEnv& e = M.e;
   const double k = M.k, k2 = M.k2, ik2 = M.ik2;
-#define Y(i) LVEC(sy, i)
-#define DY(i) LVEC(sdy, i)
   const double a2 = e.a * e.a, aH = e.H * e.a, R = e.R;
   const double rho_g = e.rho_g, rho_b = e.rho_b, rho_cdm = e.rho_cdm, rho_ur = e.rho_ur;
   const double dkappa = e.dkappa, cb2 = e.cb2;
@@ -355,20 +358,21 @@ LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, double* __restrict__ mem, in
   const bool has_g = !ap.rsa_on;
   const bool has_ur = P.has_ur && !ap.rsa_on;
   const bool full_g = has_g && ap.tca_off;
+  const int nqt = P.nq_tot;
 
   double delta_g = 0., theta_g = 0., shear_g = 0.;
-  if (has_g) { delta_g = Y(L.delta_g); theta_g = Y(L.theta_g); }
+  if (has_g) { delta_g = y[L.delta_g]; theta_g = y[L.theta_g]; }
   double g3 = 0., p0 = 0., p1 = 0., p2 = 0., p3 = 0.;
   if (full_g) {
-    shear_g = Y(L.shear_g); g3 = Y(L.c_g);
-    p0 = Y(L.pol0_g); p1 = Y(L.pol0_g + 1); p2 = Y(L.pol0_g + 2); p3 = Y(L.c_pol);
+    shear_g = y[L.shear_g]; g3 = y[L.c_g];
+    p0 = y[L.pol0_g]; p1 = y[L.pol0_g + 1]; p2 = y[L.pol0_g + 2]; p3 = y[L.c_pol];
   }
   double delta_ur = 0., theta_ur = 0., shear_ur = 0., u3 = 0.;
   if (has_ur) {
-    delta_ur = Y(L.delta_ur); theta_ur = Y(L.theta_ur); shear_ur = Y(L.shear_ur);
-    if (!ap.ufa_on) u3 = Y(L.c_ur);
+    delta_ur = y[L.delta_ur]; theta_ur = y[L.theta_ur]; shear_ur = y[L.shear_ur];
+    if (!ap.ufa_on) u3 = y[L.c_ur];
   }
-  const double delta_b = Y(L.delta_b), theta_b = Y(L.theta_b), delta_cdm = Y(L.delta_cdm), eta_y = Y(L.eta);
+  const double delta_b = y[L.delta_b], theta_b = y[L.theta_b], delta_cdm = y[L.delta_cdm], eta = y[L.eta];
   const double delta_p_b_over_rho_b = cb2 * delta_b;
 
   // ---- perturb_total_stress_energy
@@ -389,7 +393,7 @@ LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, double* __restrict__ mem, in
       for (int s = 0; s < P.N_ncdm; s++) {
         const double* nf = e.nf[s];
         const int idx = L.psi0_ncdm1 + 3 * s;
-        const double y0 = Y(idx), y1 = Y(idx + 1), y2 = Y(idx + 2);
+        const double y0 = y[idx], y1 = y[idx + 1], y2 = y[idx + 2];
         delta_rho += nf[0] * y0;
         rpt += nf[1] * y1;
         rps += nf[1] * y2;
@@ -397,18 +401,18 @@ LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, double* __restrict__ mem, in
         rpt_m += nf[1] * y1; rpm += nf[1];
       }
     } else {
-      const int nqt = P.nq_tot;
       for (int s = 0; s < P.N_ncdm; s++) {
         const double rho_n = e.rho_n[s], p_n = e.p_n[s];
         const double factor = M.C->ncdm_factor[s] * e.fac_ncdm;
         double s_rho = 0., s_theta = 0., s_shear = 0.;
         const int nq = P.ncdm_q_size[s], q0 = P.ncdm_q_off[s];
+        LN_UNROLL
         for (int iq = 0; iq < nq; iq++) {
           const int idx = L.psi0_ncdm1 + 3 * (q0 + iq);
-          const double y0 = Y(idx), y1 = Y(idx + 1), y2 = Y(idx + 2);
-          s_rho += LM(P.lo_nw + nqt + q0 + iq) * y0;
-          s_theta += LM(P.lo_nw + 2 * nqt + q0 + iq) * y1;
-          s_shear += LM(P.lo_nw + 3 * nqt + q0 + iq) * y2;
+          const double y0 = y[idx], y1 = y[idx + 1], y2 = y[idx + 2];
+          s_rho += nw[nqt + q0 + iq] * y0;
+          s_theta += nw[2 * nqt + q0 + iq] * y1;
+          s_shear += nw[3 * nqt + q0 + iq] * y2;
         }
         s_rho *= factor;
         s_theta *= k * factor;
@@ -422,9 +426,7 @@ LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, double* __restrict__ mem, in
   if (flags & LR_MATTER) m.delta_m = delta_rho_m / rho_m + 3. * aH * (rpt_m / rpm) * ik2;
 
   // ---- perturb_einstein (synchronous gauge, K = 0)
-  double h_prime = (k2 * eta_y + 1.5 * a2 * delta_rho) * e.inv_half_aH;
-  double eta = eta_y;
-  if (flags & LR_GIVEN_METRIC) { h_prime = ms_in[MS_HP]; eta = ms_in[MS_ETA]; }
+  const double h_prime = (k2 * eta + 1.5 * a2 * delta_rho) * e.inv_half_aH;
   double rsa_delta_g = 0., rsa_theta_g = 0.;
   if (ap.rsa_on) {
     double rsa_delta_ur = 0., rsa_theta_ur = 0.;
@@ -448,15 +450,13 @@ LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, double* __restrict__ mem, in
       rpt += 4. / 3. * rho_ur * rsa_theta_ur;
     }
   }
-  double eta_prime = (1.5 * a2 * rpt) * ik2;
-  if (flags & LR_GIVEN_METRIC) eta_prime = ms_in[MS_EP];
+  const double eta_prime = (1.5 * a2 * rpt) * ik2;
   const double alpha = (h_prime + 6. * eta_prime) * 0.5 * ik2;
   if (!ap.tca_off) {
     const double sg = 16. / 45. * e.tau_c * (theta_g + k2 * alpha);
     rps += 4. / 3. * rho_g * sg;
   }
-  double alpha_prime = -2. * aH * alpha + eta - 4.5 * (a2 * ik2) * rps;
-  if (flags & LR_GIVEN_METRIC) alpha_prime = ms_in[MS_AP];
+  const double alpha_prime = -2. * aH * alpha + eta - 4.5 * (a2 * ik2) * rps;
   m.h_prime = h_prime; m.eta_prime = eta_prime; m.alpha = alpha; m.alpha_prime = alpha_prime;
   m.rsa_delta_g = rsa_delta_g; m.rsa_theta_g = rsa_theta_g;
   if (!(flags & (LR_HUB | LR_CHAINS))) return;
@@ -475,10 +475,10 @@ LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, double* __restrict__ mem, in
       if (full_g) {
         const double P0 = (p0 + p2 + 2. * shear_g) * 0.125;
         dtheta_g = k2 * (delta_g * 0.25 - shear_g) + dkappa * (theta_b - theta_g);
-        DY(L.shear_g) = 0.5 * (8. / 15. * (theta_g + metric_shear) - 3. / 5. * k * g3 - dkappa * (2. * shear_g - 4. / 5. * P0));
-        DY(L.pol0_g) = -k * p1 - dkappa * (p0 - 4. * P0);
-        DY(L.pol0_g + 1) = k * (1. / 3.) * (p0 - 2. * p2) - dkappa * p1;
-        DY(L.pol0_g + 2) = k * (1. / 5.) * (2. * p1 - 3. * p3) - dkappa * (p2 - 4. / 5. * P0);
+        dy[L.shear_g] = 0.5 * (8. / 15. * (theta_g + metric_shear) - 3. / 5. * k * g3 - dkappa * (2. * shear_g - 4. / 5. * P0));
+        dy[L.pol0_g] = -k * p1 - dkappa * (p0 - 4. * P0);
+        dy[L.pol0_g + 1] = k * (1. / 3.) * (p0 - 2. * p2) - dkappa * p1;
+        dy[L.pol0_g + 2] = k * (1. / 5.) * (2. * p1 - 3. * p3) - dkappa * (p2 - 4. / 5. * P0);
       }
     } else {
       // ---- perturb_tca_slip_and_shear
@@ -509,17 +509,17 @@ LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, double* __restrict__ mem, in
       dtheta_g = -(dtheta_b + aH * theta_b - k2 * delta_p_b_over_rho_b) * e.inv_R + k2 * (0.25 * delta_g - sg);
     }
     if (has_g) {
-      DY(L.delta_g) = -4. / 3. * (theta_g + metric_continuity);
-      DY(L.theta_g) = dtheta_g;
+      dy[L.delta_g] = -4. / 3. * (theta_g + metric_continuity);
+      dy[L.theta_g] = dtheta_g;
     }
-    DY(L.delta_b) = -(theta_b + metric_continuity);
-    DY(L.theta_b) = dtheta_b;
-    DY(L.delta_cdm) = -metric_continuity;
-    DY(L.eta) = eta_prime;
+    dy[L.delta_b] = -(theta_b + metric_continuity);
+    dy[L.theta_b] = dtheta_b;
+    dy[L.delta_cdm] = -metric_continuity;
+    dy[L.eta] = eta_prime;
     if (has_ur) {
-      DY(L.delta_ur) = -4. / 3. * (theta_ur + metric_continuity) +
+      dy[L.delta_ur] = -4. / 3. * (theta_ur + metric_continuity) +
                        (1. - P.three_ceff2_ur) * aH * (delta_ur + 4. * aH * theta_ur * ik2);
-      DY(L.theta_ur) = k2 * (P.three_ceff2_ur * delta_ur * 0.25 - shear_ur) - (1. - P.three_ceff2_ur) * aH * theta_ur;
+      dy[L.theta_ur] = k2 * (P.three_ceff2_ur * delta_ur * 0.25 - shear_ur) - (1. - P.three_ceff2_ur) * aH * theta_ur;
       double dshear_ur;
       if (!ap.ufa_on) {
         dshear_ur = 0.5 * (8. / 15. * (theta_ur + metric_shear) - 3. / 5. * k * u3 -
@@ -529,108 +529,87 @@ LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, double* __restrict__ mem, in
         else if (P.ufa_method == CLPP_UFA_HU) dshear_ur = -3. * aH * shear_ur + 2. / 3. * (theta_ur + metric_shear);
         else dshear_ur = -3. * e.inv_tau * shear_ur + 2. / 3. * (theta_ur + metric_ufa_class);
       }
-      DY(L.shear_ur) = dshear_ur;
+      dy[L.shear_ur] = dshear_ur;
     }
     if (P.has_ncdm) {
       if (ap.ncdmfa_on) {
         for (int s = 0; s < P.N_ncdm; s++) {
           const double* nf = e.nf[s];
           const int idx = L.psi0_ncdm1 + 3 * s;
-          const double y0 = Y(idx), y1 = Y(idx + 1), y2 = Y(idx + 2);
+          const double y0 = y[idx], y1 = y[idx + 1], y2 = y[idx + 2];
           const double w_n = nf[2], ca2 = nf[4];
-          DY(idx) = -(1.0 + w_n) * (y1 + metric_continuity) - 3.0 * aH * (ca2 - w_n) * y0;
-          DY(idx + 1) = -aH * (1.0 - 3.0 * ca2) * y1 + nf[5] * k2 * y0 - k2 * y2;
+          dy[idx] = -(1.0 + w_n) * (y1 + metric_continuity) - 3.0 * aH * (ca2 - w_n) * y0;
+          dy[idx + 1] = -aH * (1.0 - 3.0 * ca2) * y1 + nf[5] * k2 * y0 - k2 * y2;
           const double msn = (P.ncdmfa_method == CLPP_NCDMFA_CLASS) ? metric_ufa_class : metric_shear;
-          DY(idx + 2) = -nf[7] * y2 + nf[6] * (y1 + msn);
+          dy[idx + 2] = -nf[7] * y2 + nf[6] * (y1 + msn);
         }
       } else {
-        for (int j = 0; j < P.nq_tot; j++) {
+        const double* __restrict__ dlnf0_tab = M.C->ncdm_dlnf0;
+        LN_UNROLL
+        for (int j = 0; j < nqt; j++) {
           const int idx = L.psi0_ncdm1 + 3 * j;
-          const double qk = k * LM(P.lo_nw + j);
-          const double dlnf0 = LN_LDG(M.C->ncdm_dlnf0 + j);
-          const double y0 = Y(idx), y1 = Y(idx + 1), y2 = Y(idx + 2), y3 = Y(L.c_ncdm + j * L.len_ncdm);
-          DY(idx) = -qk * y1 + metric_continuity * dlnf0 * (1. / 3.);
-          DY(idx + 1) = qk * (1. / 3.0) * (y0 - 2 * y2);
-          DY(idx + 2) = qk * (1. / 5.0) * (2 * y1 - 3. * y3) - metric_shear * 2. / 15. * dlnf0;
+          const double qk = k * nw[j];
+          const double dlnf0 = LN_LDG(dlnf0_tab + j);
+          const double y0 = y[idx], y1 = y[idx + 1], y2 = y[idx + 2], y3 = y[L.c_ncdm + j * L.len_ncdm];
+          dy[idx] = -qk * y1 + metric_continuity * dlnf0 * (1. / 3.);
+          dy[idx + 1] = qk * (1. / 3.0) * (y0 - 2 * y2);
+          dy[idx + 2] = qk * (1. / 5.0) * (2 * y1 - 3. * y3) - metric_shear * 2. / 15. * dlnf0;
         }
       }
     }
   }
-  // ---- multipole chains (l >= 3)
+  // ---- multipole chains (l >= 3): row l couples to l-1 (the hub root for l = 3), l, l+1
   if (flags & LR_CHAINS) {
     const double* __restrict__ i2l1 = P.i2l1;
-    if (full_g) {
-      {
-        const int c0 = L.c_g, len = L.len_g;
-        double ym = 2. * shear_g, yl = Y(c0);
-        for (int p = 0; p < len; p++) {
-          const int l = 3 + p;
-          if (p < len - 1) {
-            const double yp = Y(c0 + p + 1);
-            DY(c0 + p) = k * LN_LDG(i2l1 + l) * (l * ym - (l + 1) * yp) - dkappa * yl;
-            ym = yl; yl = yp;
-          } else {
-            DY(c0 + p) = k * (ym - (1. + l) * cotKgen * yl) - dkappa * yl;
-          }
-        }
-      }
-      {
-        const int c0 = L.c_pol, len = L.len_pol;
-        double ym = p2, yl = Y(c0);
-        for (int p = 0; p < len; p++) {
-          const int l = 3 + p;
-          if (p < len - 1) {
-            const double yp = Y(c0 + p + 1);
-            DY(c0 + p) = k * LN_LDG(i2l1 + l) * (l * ym - (l + 1.) * yp) - dkappa * yl;
-            ym = yl; yl = yp;
-          } else {
-            DY(c0 + p) = k * (ym - (l + 1) * cotKgen * yl) - dkappa * yl;
-          }
-        }
-      }
-    }
-    if (has_ur && !ap.ufa_on) {
-      const int c0 = L.c_ur, len = L.len_ur;
-      double ym = 2. * shear_ur, yl = Y(c0);
-      for (int p = 0; p < len; p++) {
+    for (int fam = 0; fam < 3; fam++) {
+      int c0, len;
+      double ym, damp;
+      if (fam == 0) { if (!full_g) continue; c0 = L.c_g; len = L.len_g; ym = 2. * shear_g; damp = dkappa; }
+      else if (fam == 1) { if (!full_g) continue; c0 = L.c_pol; len = L.len_pol; ym = p2; damp = dkappa; }
+      else { if (!(has_ur && !ap.ufa_on)) continue; c0 = L.c_ur; len = L.len_ur; ym = 2. * shear_ur; damp = 0.; }
+      const double* __restrict__ yc = y + c0;
+      double* __restrict__ dc = dy + c0;
+      LN_UNROLL
+      for (int p = 0; p < len - 1; p++) {
         const int l = 3 + p;
-        if (p < len - 1) {
-          const double yp = Y(c0 + p + 1);
-          DY(c0 + p) = k * LN_LDG(i2l1 + l) * (l * ym - (l + 1.) * yp);
-          ym = yl; yl = yp;
-        } else {
-          DY(c0 + p) = k * (ym - (1. + l) * cotKgen * yl);
-        }
+        const double ylm = (p == 0) ? ym : yc[p - 1];
+        dc[p] = k * LN_LDG(i2l1 + l) * (l * ylm - (l + 1) * yc[p + 1]) - damp * yc[p];
+      }
+      {
+        const int p = len - 1, l = 3 + p;
+        const double ylm = (p == 0) ? ym : yc[p - 1];
+        dc[p] = k * (ylm - (1. + l) * cotKgen * yc[p]) - damp * yc[p];
       }
     }
     if (P.has_ncdm && !ap.ncdmfa_on) {
       const int len = L.len_ncdm;
-      for (int j = 0; j < P.nq_tot; j++) {
-        const int c0 = L.c_ncdm + j * len;
-        const double qk = k * LM(P.lo_nw + j);
-        double ym = Y(L.psi0_ncdm1 + 3 * j + 2), yl = Y(c0);
-        for (int p = 0; p < len; p++) {
+      for (int j = 0; j < nqt; j++) {
+        const double* __restrict__ yc = y + L.c_ncdm + j * len;
+        double* __restrict__ dc = dy + L.c_ncdm + j * len;
+        const double qk = k * nw[j];
+        const double ym = y[L.psi0_ncdm1 + 3 * j + 2];
+        LN_UNROLL
+        for (int p = 0; p < len - 1; p++) {
           const int l = 3 + p;
-          if (p < len - 1) {
-            const double yp = Y(c0 + p + 1);
-            DY(c0 + p) = qk * LN_LDG(i2l1 + l) * (l * ym - (l + 1.) * yp);
-            ym = yl; yl = yp;
-          } else {
-            DY(c0 + p) = qk * ym - (1. + l) * k * cotKgen * yl;
-          }
+          const double ylm = (p == 0) ? ym : yc[p - 1];
+          dc[p] = qk * LN_LDG(i2l1 + l) * (l * ylm - (l + 1.) * yc[p + 1]);
+        }
+        {
+          const int p = len - 1, l = 3 + p;
+          const double ylm = (p == 0) ? ym : yc[p - 1];
+          dc[p] = qk * ylm - (1. + l) * k * cotKgen * yc[p];
         }
       }
     }
   }
-#undef Y
-#undef DY
 }
 
 // -------------------------------------------------------------------------------------------------
 // perturb_sources_member: source functions at sample index_tau from (y, dy)
-LN_NOINLINE void ln_write_sources(const PtParams& P, Lane& M, double* __restrict__ mem, double tau, int sy, int sdy, int index_tau) {
+LN_NOINLINE void ln_write_sources(const PtParams& P, Lane& M, double* __restrict__ mem, double tau, const double* __restrict__ y,
+                                  const double* __restrict__ dy, int index_tau) {
   ln_env(P, M, mem, tau, 1);
-  ln_rhs(P, M, mem, sy, -1, LR_MATTER, nullptr);
+  ln_rhs(P, M, y, nullptr, mem + P.lo_nw, LR_MATTER);
   const LnLayout& L = M.L;
   const Approx& ap = M.ap;
   const LnEnv& e = M.e;
@@ -642,18 +621,18 @@ LN_NOINLINE void ln_write_sources(const PtParams& P, Lane& M, double* __restrict
   double delta_g, Pi;
   if (ap.rsa_on) { delta_g = m.rsa_delta_g; Pi = 0.; }
   else {
-    delta_g = LVEC(sy, L.delta_g);
+    delta_g = y[L.delta_g];
     if (!ap.tca_off) Pi = 5. * M.tca_shear_last / 8.;
-    else Pi = (LVEC(sy, L.pol0_g) + LVEC(sy, L.pol0_g + 2) + 2. * LVEC(sy, L.shear_g)) / 8.;
+    else Pi = (y[L.pol0_g] + y[L.pol0_g + 2] + 2. * y[L.shear_g]) / 8.;
   }
   const size_t stride_tp = (size_t)M.C->k_size * M.C->tau_size;
   double* out = M.C->sources + (size_t)M.ik_index * M.C->tau_size + index_tau;
-  const double eta = LVEC(sy, L.eta);
+  const double eta = y[L.eta];
   if (P.tp_t0 >= 0) {
     int switch_isw = 1;
     if ((P.switch_eisw == 0) && (z >= P.eisw_lisw_split_z)) switch_isw = 0;
     if ((P.switch_lisw == 0) && (z < P.eisw_lisw_split_z)) switch_isw = 0;
-    const double theta_b = LVEC(sy, L.theta_b), dtheta_b = LVEC(sdy, L.theta_b);
+    const double theta_b = y[L.theta_b], dtheta_b = dy[L.theta_b];
     out[P.tp_t0 * stride_tp] =
         P.switch_sw * e.g * (delta_g / 4. + m.alpha_prime) +
         switch_isw * (e.g * (eta - m.alpha_prime - 2 * aH * m.alpha) +
@@ -672,6 +651,22 @@ LN_NOINLINE void ln_write_sources(const PtParams& P, Lane& M, double* __restrict
 // Jacobian J = A(tau) at the environment in M.e.
 //  chains: closed form (each l >= 3 row couples to l-1, l, l+1 only);
 //  hub block (nh x nh, row-major at lo_jhh): column j = hub rows of f(tau, e_j) (the system is linear and homogeneous).
+LN_FN void ln_chain_rows(double* __restrict__ jd, double* __restrict__ jl, double* __restrict__ ju, const double* __restrict__ i2l1,
+                         int len, double kk, double first, double damp, double last_diag) {
+  LN_UNROLL
+  for (int p = 0; p < len - 1; p++) {
+    const int l = 3 + p;
+    const double c = kk * LN_LDG(i2l1 + l);
+    jl[p] = (p == 0 ? first : 1.) * c * l;
+    ju[p] = -c * (l + 1);
+    jd[p] = -damp;
+  }
+  const int p = len - 1;
+  jl[p] = (p == 0 ? first : 1.) * kk;
+  ju[p] = 0.;
+  jd[p] = last_diag - damp;
+}
+
 LN_NOINLINE void ln_jacobian(const PtParams& P, Lane& M, double* __restrict__ mem) {
   const LnLayout& L = M.L;
   const LnEnv& e = M.e;
@@ -679,74 +674,41 @@ LN_NOINLINE void ln_jacobian(const PtParams& P, Lane& M, double* __restrict__ me
   const double k = M.k;
   const double cotKgen = e.inv_tau * M.ik;
   const double* __restrict__ i2l1 = P.i2l1;
+  double *jd = LVP(LV_JD), *jl = LVP(LV_JL), *ju = LVP(LV_JU);
+  const double* nw = mem + P.lo_nw;
   // ---- chains
   int c = 0;
   if (L.c_g >= 0) {
-    for (int fam = 0; fam < 2; fam++) {
-      const int c0 = fam == 0 ? L.c_g : L.c_pol, len = fam == 0 ? L.len_g : L.len_pol;
-      for (int p = 0; p < len; p++) {
-        const int l = 3 + p;
-        const double first = (p == 0 && fam == 0) ? 2. : 1.;  // F_2 = 2 shear_g
-        if (p < len - 1) {
-          LVEC(LV_JL, c0 + p) = first * k * LN_LDG(i2l1 + l) * l;
-          LVEC(LV_JU, c0 + p) = -k * LN_LDG(i2l1 + l) * (l + 1);
-          LVEC(LV_JD, c0 + p) = -e.dkappa;
-        } else {
-          LVEC(LV_JL, c0 + p) = first * k;
-          LVEC(LV_JU, c0 + p) = 0.;
-          LVEC(LV_JD, c0 + p) = -k * (1. + l) * cotKgen - e.dkappa;
-        }
-      }
-      LCH_JUR(c) = fam == 0 ? -0.3 * k : -0.6 * k;
-      c++;
-    }
+    ln_chain_rows(jd + L.c_g, jl + L.c_g, ju + L.c_g, i2l1, L.len_g, k, 2., e.dkappa, -k * (1. + (2 + L.len_g)) * cotKgen);
+    LCH_JUR(c) = -0.3 * k; c++;
+    ln_chain_rows(jd + L.c_pol, jl + L.c_pol, ju + L.c_pol, i2l1, L.len_pol, k, 1., e.dkappa, -k * (1. + (2 + L.len_pol)) * cotKgen);
+    LCH_JUR(c) = -0.6 * k; c++;
   }
   if (L.c_ur >= 0) {
-    const int c0 = L.c_ur, len = L.len_ur;
-    for (int p = 0; p < len; p++) {
-      const int l = 3 + p;
-      const double first = (p == 0) ? 2. : 1.;
-      if (p < len - 1) {
-        LVEC(LV_JL, c0 + p) = first * k * LN_LDG(i2l1 + l) * l;
-        LVEC(LV_JU, c0 + p) = -k * LN_LDG(i2l1 + l) * (l + 1);
-        LVEC(LV_JD, c0 + p) = 0.;
-      } else {
-        LVEC(LV_JL, c0 + p) = first * k;
-        LVEC(LV_JU, c0 + p) = 0.;
-        LVEC(LV_JD, c0 + p) = -k * (1. + l) * cotKgen;
-      }
-    }
-    LCH_JUR(c) = -0.3 * k;
-    c++;
+    ln_chain_rows(jd + L.c_ur, jl + L.c_ur, ju + L.c_ur, i2l1, L.len_ur, k, 2., 0., -k * (1. + (2 + L.len_ur)) * cotKgen);
+    LCH_JUR(c) = -0.3 * k; c++;
   }
   if (L.c_ncdm >= 0) {
     const int len = L.len_ncdm;
     for (int j = 0; j < P.nq_tot; j++) {
       const int c0 = L.c_ncdm + j * len;
-      const double qk = k * LM(P.lo_nw + j);
-      for (int p = 0; p < len; p++) {
-        const int l = 3 + p;
-        if (p < len - 1) {
-          LVEC(LV_JL, c0 + p) = qk * LN_LDG(i2l1 + l) * l;
-          LVEC(LV_JU, c0 + p) = -qk * LN_LDG(i2l1 + l) * (l + 1);
-          LVEC(LV_JD, c0 + p) = 0.;
-        } else {
-          LVEC(LV_JL, c0 + p) = qk;
-          LVEC(LV_JU, c0 + p) = 0.;
-          LVEC(LV_JD, c0 + p) = -(1. + l) * k * cotKgen;
-        }
-      }
-      LCH_JUR(c) = -0.6 * qk;
-      c++;
+      const double qk = k * nw[j];
+      ln_chain_rows(jd + c0, jl + c0, ju + c0, i2l1, len, qk, 1., 0., -(1. + (2 + len)) * k * cotKgen);
+      LCH_JUR(c) = -0.6 * qk; c++;
     }
   }
   // ---- hub block by probing (hub rows only; the chain parts of the probe vector stay zero)
-  for (int i = 0; i < n; i++) LVEC(LV_TMP, i) = 0.;
+  double* __restrict__ ej = LVP(LV_TMP);
+  double* __restrict__ col = LVP(LV_DEL);
+  double* __restrict__ jhh = mem + P.lo_jhh;
+  LN_UNROLL
+  for (int i = 0; i < n; i++) ej[i] = 0.;
   for (int j = 0; j < nh; j++) {
-    LVEC(LV_TMP, j) = 1.;
-    ln_rhs(P, M, mem, LV_TMP, LV_DEL, LR_HUB, nullptr);
-    for (int i = 0; i < nh; i++) LM(P.lo_jhh + i * nh + j) = LVEC(LV_DEL, i);
-    LVEC(LV_TMP, j) = 0.;
+    ej[j] = 1.;
+    ln_rhs(P, M, ej, col, nw, LR_HUB);
+    LN_UNROLL
+    for (int i = 0; i < nh; i++) jhh[i * nh + j] = col[i];
+    ej[j] = 0.;
   }
   M.st.jacobians++;
   M.st.fevals += nh;
@@ -754,103 +716,132 @@ LN_NOINLINE void ln_jacobian(const PtParams& P, Lane& M, double* __restrict__ me
 
 // Factorisation of A = I - c J: chains (backward elimination towards their root), Schur complement on the root
 // diagonals, LU with partial pivoting of the hub block (row-major at lo_lu, 1/pivot on the diagonal).
+LN_FN double ln_chain_factor(const double* __restrict__ jd, const double* __restrict__ jl, const double* __restrict__ ju,
+                             double* __restrict__ ip, double* __restrict__ mu, int len, double c, double jur, double& mur_out) {
+  const int last = len - 1;
+  double ipn = 1.0 / (1.0 - c * jd[last]);
+  ip[last] = ipn;
+  double lon = -c * jl[last];
+  for (int i = last - 1; i >= 0; i--) {
+    const double mui = -c * ju[i] * ipn;
+    const double p = (1.0 - c * jd[i]) - mui * lon;
+    ipn = 1.0 / p;
+    lon = -c * jl[i];
+    ip[i] = ipn; mu[i] = mui;
+  }
+  const double mur = -c * jur * ipn;
+  mur_out = mur;
+  return -mur * lon;  // Schur term on the root diagonal
+}
+
 LN_NOINLINE void ln_factor(const PtParams& P, Lane& M, double* __restrict__ mem, double c) {
   const LnLayout& L = M.L;
   const int nh = L.nh, nch = L.nch;
   M.fac_c = c;
-  for (int i = 0; i < nh; i++)
-    for (int j = 0; j < nh; j++) LM(P.lo_lu + i * nh + j) = (i == j ? 1.0 : 0.0) - c * LM(P.lo_jhh + i * nh + j);
+  const double* __restrict__ jhh = mem + P.lo_jhh;
+  double* __restrict__ lu = mem + P.lo_lu;
+  double* __restrict__ piv = mem + P.lo_piv;
+  for (int i = 0; i < nh; i++) {
+    LN_UNROLL
+    for (int j = 0; j < nh; j++) lu[i * nh + j] = (i == j ? 1.0 : 0.0) - c * jhh[i * nh + j];
+  }
   for (int ch = 0; ch < nch; ch++) {
     int s, len, root;
     ln_chain(L, ch, s, len, root);
-    const int last = s + len - 1;
-    double ipn = 1.0 / (1.0 - c * LVEC(LV_JD, last));
-    LVEC(LV_IP, last) = ipn;
-    double lon = -c * LVEC(LV_JL, last);
-    for (int i = last - 1; i >= s; i--) {
-      const double mui = -c * LVEC(LV_JU, i) * ipn;
-      const double p = (1.0 - c * LVEC(LV_JD, i)) - mui * lon;
-      ipn = 1.0 / p;
-      lon = -c * LVEC(LV_JL, i);
-      LVEC(LV_IP, i) = ipn; LVEC(LV_MU, i) = mui;
-    }
-    const double mur = -c * LCH_JUR(ch) * ipn;
+    double mur;
+    const double schur = ln_chain_factor(LVP(LV_JD) + s, LVP(LV_JL) + s, LVP(LV_JU) + s, LVP(LV_IP) + s, LVP(LV_MU) + s, len, c,
+                                         LCH_JUR(ch), mur);
     LCH_MUR(ch) = mur;
-    LM(P.lo_lu + root * nh + root) += -mur * lon;
+    lu[root * nh + root] += schur;
   }
   // LU, partial pivoting
   for (int j = 0; j < nh; j++) {
-    double best = fabs(LM(P.lo_lu + j * nh + j));
+    double best = fabs(lu[j * nh + j]);
     int bi = j;
     for (int i = j + 1; i < nh; i++) {
-      const double v = fabs(LM(P.lo_lu + i * nh + j));
+      const double v = fabs(lu[i * nh + j]);
       if (v > best) { best = v; bi = i; }
     }
-    LM(P.lo_piv + j) = (double)bi;
+    piv[j] = (double)bi;
     if (bi != j) {
       for (int cc = 0; cc < nh; cc++) {
-        const double t = LM(P.lo_lu + j * nh + cc);
-        LM(P.lo_lu + j * nh + cc) = LM(P.lo_lu + bi * nh + cc);
-        LM(P.lo_lu + bi * nh + cc) = t;
+        const double t = lu[j * nh + cc];
+        lu[j * nh + cc] = lu[bi * nh + cc];
+        lu[bi * nh + cc] = t;
       }
     }
-    double pv = LM(P.lo_lu + j * nh + j);
+    double pv = lu[j * nh + j];
     if (pv == 0.) pv = 1e-50;  // TINY, as ludcmp does for a singular pivot
     const double pinv = 1.0 / pv;
-    LM(P.lo_lu + j * nh + j) = pinv;
+    lu[j * nh + j] = pinv;
+    const double* __restrict__ rj = lu + j * nh;
     for (int i = j + 1; i < nh; i++) {
-      const double f = LM(P.lo_lu + i * nh + j) * pinv;
-      LM(P.lo_lu + i * nh + j) = f;
-      if (f != 0.)
-        for (int cc = j + 1; cc < nh; cc++) LM(P.lo_lu + i * nh + cc) -= f * LM(P.lo_lu + j * nh + cc);
+      double* ri = lu + i * nh;
+      const double f = ri[j] * pinv;
+      ri[j] = f;
+      if (f != 0.) {
+        LN_UNROLL
+        for (int cc = j + 1; cc < nh; cc++) ri[cc] -= f * rj[cc];
+      }
     }
   }
   M.st.factorizations++;
 }
 
-// solve A x = b in place (vector slot sb) with the factors of ln_factor
-LN_NOINLINE void ln_solve(const PtParams& P, Lane& M, double* __restrict__ mem, int sb) {
+// solve A x = b in place with the factors of ln_factor
+LN_NOINLINE void ln_solve(const PtParams& P, Lane& M, double* __restrict__ mem, double* __restrict__ b) {
   const LnLayout& L = M.L;
   const int nh = L.nh, nch = L.nch;
   const double c = M.fac_c;
-#define B(i) LVEC(sb, i)
+  const double* __restrict__ lu = mem + P.lo_lu;
+  const double* __restrict__ piv = mem + P.lo_piv;
+  const double* __restrict__ mu = LVP(LV_MU);
+  const double* __restrict__ ip = LVP(LV_IP);
+  const double* __restrict__ jl = LVP(LV_JL);
   for (int ch = 0; ch < nch; ch++) {
     int s, len, root;
     ln_chain(L, ch, s, len, root);
     const int last = s + len - 1;
-    double r = B(last);
+    double r = b[last];
+    LN_UNROLL
     for (int i = last - 1; i >= s; i--) {
-      r = B(i) - LVEC(LV_MU, i) * r;
-      B(i) = r;
+      r = b[i] - mu[i] * r;
+      b[i] = r;
     }
-    B(root) -= LCH_MUR(ch) * r;
+    b[root] -= LCH_MUR(ch) * r;
   }
   for (int j = 0; j < nh; j++) {
-    const int p = (int)LM(P.lo_piv + j);
-    if (p != j) { const double t = B(j); B(j) = B(p); B(p) = t; }
+    const int p = (int)piv[j];
+    if (p != j) { const double t = b[j]; b[j] = b[p]; b[p] = t; }
   }
   for (int i = 1; i < nh; i++) {
-    double s = B(i);
-    for (int j = 0; j < i; j++) s -= LM(P.lo_lu + i * nh + j) * B(j);
-    B(i) = s;
+    double s0 = b[i], s1 = 0.;
+    const double* __restrict__ ri = lu + i * nh;
+    int j = 0;
+    for (; j + 1 < i; j += 2) { s0 -= ri[j] * b[j]; s1 -= ri[j + 1] * b[j + 1]; }
+    if (j < i) s0 -= ri[j] * b[j];
+    b[i] = s0 + s1;
   }
   for (int i = nh - 1; i >= 0; i--) {
-    double s = B(i);
-    for (int j = i + 1; j < nh; j++) s -= LM(P.lo_lu + i * nh + j) * B(j);
-    B(i) = s * LM(P.lo_lu + i * nh + i);
+    double s0 = b[i], s1 = 0.;
+    const double* __restrict__ ri = lu + i * nh;
+    int j = i + 1;
+    for (; j + 1 < nh; j += 2) { s0 -= ri[j] * b[j]; s1 -= ri[j + 1] * b[j + 1]; }
+    if (j < nh) s0 -= ri[j] * b[j];
+    b[i] = (s0 + s1) * ri[i];
   }
   for (int ch = 0; ch < nch; ch++) {
     int s, len, root;
     ln_chain(L, ch, s, len, root);
     const int last = s + len - 1;
-    double xp = B(root);
+    double xp = b[root];
+    LN_UNROLL
     for (int i = s; i <= last; i++) {
-      const double lo = -c * LVEC(LV_JL, i);
-      xp = (B(i) - lo * xp) * LVEC(LV_IP, i);
-      B(i) = xp;
+      const double lo = -c * jl[i];
+      xp = (b[i] - lo * xp) * ip[i];
+      b[i] = xp;
     }
   }
-#undef B
   M.st.solves++;
 }
 
@@ -879,19 +870,139 @@ LN_NOINLINE void ln_adjust_stepsize(const PtParams& P, Lane& M, double* __restri
       }
   }
   const int n = M.L.neq;
+  double* __restrict__ d0 = LVP(LV_DIF0);
+  double* __restrict__ d1 = LVP(LV_DIF0 + 1);
+  double* __restrict__ d2 = LVP(LV_DIF0 + 2);
+  double* __restrict__ d3 = LVP(LV_DIF0 + 3);
+  double* __restrict__ d4 = LVP(LV_DIF0 + 4);
+  LN_UNROLL
   for (int i = 0; i < n; i++) {
     double row[5];
-#pragma unroll
-    for (int kk = 0; kk < 5; kk++) row[kk] = (kk < kord) ? LVEC(LV_DIF0 + kk, i) : 0.;
+    row[0] = d0[i];
+    row[1] = (1 < kord) ? d1[i] : 0.;
+    row[2] = (2 < kord) ? d2[i] : 0.;
+    row[3] = (3 < kord) ? d3[i] : 0.;
+    row[4] = (4 < kord) ? d4[i] : 0.;
+    double o[5];
 #pragma unroll
     for (int jj = 0; jj < 5; jj++) {
-      if (jj < kord) {
-        double s = 0.0;
+      double s = 0.0;
 #pragma unroll
-        for (int kk = 0; kk < 5; kk++) s += row[kk] * RU[kk][jj];
-        LVEC(LV_DIF0 + jj, i) = s;
+      for (int kk = 0; kk < 5; kk++) s += row[kk] * RU[kk][jj];
+      o[jj] = s;
+    }
+    d0[i] = o[0];
+    if (1 < kord) d1[i] = o[1];
+    if (2 < kord) d2[i] = o[2];
+    if (3 < kord) d3[i] = o[3];
+    if (4 < kord) d4[i] = o[4];
+  }
+}
+
+// ---- vector loops of the NDF step (restrict pointers: see LN_UNROLL above)
+LN_FN double ln_predict(const double* __restrict__ y, const double* __restrict__ dif, int np, int k, int n, double* __restrict__ psi,
+                        double* __restrict__ pred, double* __restrict__ ynew, double* __restrict__ difkp1,
+                        double* __restrict__ invwt, double threshold, double eps) {
+  const double invGak = c_invGa[k - 1];
+  double g[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) g[j] = c_G[j] * invGak;
+  double minnrm = 0.0;
+  LN_UNROLL
+  for (int i = 0; i < n; i++) {
+    const double yi = y[i];
+    double ps = 0.0, pr = yi;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      if (j < k) {
+        const double d = dif[j * np + i];
+        ps += d * g[j];
+        pr += d;
       }
     }
+    psi[i] = ps;
+    pred[i] = pr;
+    ynew[i] = pr;
+    difkp1[i] = 0.0;
+    const double iw = 1.0 / fmax(fmax(fabs(pr), fabs(yi)), threshold);
+    invwt[i] = iw;
+    minnrm = fmax(minnrm, 100 * eps * fabs(pr * iw));
+  }
+  return minnrm;
+}
+
+LN_FN void ln_residual(double* __restrict__ del, const double* __restrict__ f, const double* __restrict__ psi,
+                       const double* __restrict__ difkp1, double hinvGak, int n) {
+  LN_UNROLL
+  for (int i = 0; i < n; i++) del[i] = hinvGak * f[i] - (psi[i] + difkp1[i]);
+}
+
+LN_FN double ln_newton_update(const double* __restrict__ del, const double* __restrict__ invwt, const double* __restrict__ pred,
+                              double* __restrict__ difkp1, double* __restrict__ ynew, int n) {
+  double newnrm = 0.0;
+  LN_UNROLL
+  for (int i = 0; i < n; i++) {
+    const double d = del[i];
+    newnrm = fmax(newnrm, fabs(d * invwt[i]));
+    const double dk = difkp1[i] + d;
+    difkp1[i] = dk;
+    ynew[i] = pred[i] + dk;
+  }
+  return newnrm;
+}
+
+LN_FN double ln_wnorm(const double* __restrict__ v, const double* __restrict__ invwt, int n) {
+  double e = 0.0;
+  LN_UNROLL
+  for (int i = 0; i < n; i++) e = fmax(e, fabs(v[i] * invwt[i]));
+  return e;
+}
+
+LN_FN double ln_wnorm2(const double* __restrict__ v, const double* __restrict__ w, const double* __restrict__ invwt, int n) {
+  double e = 0.0;
+  LN_UNROLL
+  for (int i = 0; i < n; i++) e = fmax(e, fabs((v[i] + w[i]) * invwt[i]));
+  return e;
+}
+
+// dif[k+1] = dk - dif[k]; dif[k] = dk; dif[j] += dif[j+1] (j < k); also the norms of the new dif[k-1] and dif[k+1]
+LN_FN void ln_dif_update(double* __restrict__ dif, int np, int k, int n, const double* __restrict__ difkp1,
+                         const double* __restrict__ invwt, double& e_km1, double& e_kp1) {
+  double a = 0., b = 0.;
+  LN_UNROLL
+  for (int i = 0; i < n; i++) {
+    const double dk = difkp1[i], iw = invwt[i];
+    const double dkp1 = dk - dif[k * np + i];
+    dif[(k + 1) * np + i] = dkp1;
+    double acc = dk;
+    dif[k * np + i] = acc;
+    for (int j = k - 1; j >= 0; j--) {
+      acc += dif[j * np + i];
+      dif[j * np + i] = acc;
+      if (j == k - 1) a = fmax(a, fabs(acc * iw));
+    }
+    b = fmax(b, fabs(dkp1 * iw));
+  }
+  e_km1 = a; e_kp1 = b;
+}
+
+LN_FN void ln_copy(double* __restrict__ dst, const double* __restrict__ src, int n) {
+  LN_UNROLL
+  for (int i = 0; i < n; i++) dst[i] = src[i];
+}
+
+LN_FN void ln_interp(const double* __restrict__ dif, int np, int k, int n, const double* __restrict__ ynew, const double* c1,
+                     const double* c2, double* __restrict__ yi, double* __restrict__ ypi) {
+  LN_UNROLL
+  for (int i = 0; i < n; i++) {
+    double a1 = 0, a2 = 0;
+    for (int j = 0; j < k; j++) {
+      const double d = dif[j * np + i];
+      a1 += c1[j] * d;
+      a2 += c2[j] * d;
+    }
+    yi[i] = ynew[i] + a1;
+    ypi[i] = a2;
   }
 }
 
@@ -902,18 +1013,24 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
   const double eps = 1e-16, threshold = 1e-15;
   const int maxit = 4, maxk = 5;
   const double rtol = P.rtol;
-  const int n = M.L.neq;
+  const int n = M.L.neq, np = P.np;
+  double *Y = LVP(LV_Y), *YNEW = LVP(LV_YNEW), *F = LVP(LV_F), *PRED = LVP(LV_PRED), *PSI = LVP(LV_PSI),
+         *DIFKP1 = LVP(LV_DIFKP1), *DEL = LVP(LV_DEL), *INVWT = LVP(LV_INVWT), *DIF = LVP(LV_DIF0);
+  const double* NW = mem + P.lo_nw;
   const double* t_vec = M.C->tau;
   const int tres = M.C->tau_size;
   int next = M.next;
   while (next < tres && LN_LDG(t_vec + next) < t0) next++;
   double tnext = (next < tres) ? LN_LDG(t_vec + next) : 1e300;
-  for (int j = 0; j < 7; j++)
-    for (int i = 0; i < n; i++) LVEC(LV_DIF0 + j, i) = 0.;
+  for (int j = 0; j < 7; j++) {
+    double* __restrict__ dj = DIF + j * np;
+    LN_UNROLL
+    for (int i = 0; i < n; i++) dj[i] = 0.;
+  }
   const double htspan = fabs(tfinal - t0);
   double t = t0, tnew = t0;
   ln_env(P, M, mem, t0, 0);
-  ln_rhs(P, M, mem, LV_Y, LV_F, LR_HUB | LR_CHAINS, nullptr);
+  ln_rhs(P, M, Y, F, NW, LR_HUB | LR_CHAINS);
   M.st.fevals++;
   const double hmax = (tfinal - t0) / 10.0;
   ln_jacobian(P, M, mem);
@@ -921,24 +1038,24 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
   double hmin = 16.0 * eps * fabs(t);
   double rh = 0.0;
   for (int i = 0; i < n; i++) {
-    const double wt = fmax(fabs(LVEC(LV_Y, i)), threshold);
-    rh = fmax(rh, 1.25 / sqrt(rtol) * fabs(LVEC(LV_F, i) / wt));
+    const double wt = fmax(fabs(Y[i]), threshold);
+    rh = fmax(rh, 1.25 / sqrt(rtol) * fabs(F[i] / wt));
   }
   double absh = fmin(hmax, htspan);
   if (absh * rh > 1.0) absh = 1.0 / rh;
   absh = fmax(absh, hmin);
   double h = absh;
   {
-    ln_rhs(P, M, mem, LV_F, LV_PSI, LR_HUB | LR_CHAINS, nullptr);  // J*f0 = f(t0, f0): linear, homogeneous
+    ln_rhs(P, M, F, PSI, NW, LR_HUB | LR_CHAINS);  // J*f0 = f(t0, f0): linear, homogeneous
     M.st.fevals++;
     const double tdel = (t + fmin(sqrt(eps) * fmax(fabs(t), fabs(t + h)), absh)) - t;
     ln_env(P, M, mem, t + tdel, 0);
-    ln_rhs(P, M, mem, LV_Y, LV_DEL, LR_HUB | LR_CHAINS, nullptr);
+    ln_rhs(P, M, Y, DEL, NW, LR_HUB | LR_CHAINS);
     M.st.fevals++;
     rh = 0.0;
     for (int i = 0; i < n; i++) {
-      const double wt = fmax(fabs(LVEC(LV_Y, i)), threshold);
-      const double s = LVEC(LV_PSI, i) + (LVEC(LV_DEL, i) - LVEC(LV_F, i)) / tdel;
+      const double wt = fmax(fabs(Y[i]), threshold);
+      const double s = PSI[i] + (DEL[i] - F[i]) / tdel;
       rh = fmax(rh, 1.25 * sqrt(0.5 * fabs(s / wt) / rtol));
     }
     absh = fmin(hmax, htspan);
@@ -948,7 +1065,7 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
   }
   int k = 1, klast = k;
   double abshlast = absh;
-  for (int i = 0; i < n; i++) LVEC(LV_DIF0, i) = h * LVEC(LV_F, i);
+  for (int i = 0; i < n; i++) DIF[i] = h * F[i];
   double hinvGak = h * c_invGa[k - 1];
   int nconhk = 0;
   ln_factor(P, M, mem, hinvGak);
@@ -985,43 +1102,16 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
     tnew = t + h;
     if (done) tnew = tfinal;
     h = tnew - t;
-    double minnrm = 0.0;
-    {
-      const double invGak = c_invGa[k - 1];
-      for (int i = 0; i < n; i++) {
-        double ps = 0.0;
-        const double yi = LVEC(LV_Y, i);
-        double pr = yi;
-        for (int j = 0; j < k; j++) {
-          const double d = LVEC(LV_DIF0 + j, i);
-          ps += d * c_G[j] * invGak;
-          pr += d;
-        }
-        LVEC(LV_PSI, i) = ps;
-        LVEC(LV_PRED, i) = pr;
-        LVEC(LV_YNEW, i) = pr;
-        LVEC(LV_DIFKP1, i) = 0.0;
-        const double iw = 1.0 / fmax(fmax(fabs(pr), fabs(yi)), threshold);
-        LVEC(LV_INVWT, i) = iw;
-        minnrm = fmax(minnrm, 100 * eps * fabs(pr * iw));
-      }
-    }
+    const double minnrm = ln_predict(Y, DIF, np, k, n, PSI, PRED, YNEW, DIFKP1, INVWT, threshold, eps);
     ln_env(P, M, mem, tnew, 0);
-    bool tooslow = false, gotynew = false;
+    bool gotynew = false;
     for (int iter = 1; iter <= maxit; iter++) {
-      ln_rhs(P, M, mem, LV_YNEW, LV_F, LR_HUB | LR_CHAINS, nullptr);
+      ln_rhs(P, M, YNEW, F, NW, LR_HUB | LR_CHAINS);
       if (!M.ap.tca_off) M.tca_shear_last = M.m.tca_shear_g;
       M.st.fevals++;
-      for (int i = 0; i < n; i++) LVEC(LV_DEL, i) = hinvGak * LVEC(LV_F, i) - (LVEC(LV_PSI, i) + LVEC(LV_DIFKP1, i));
-      ln_solve(P, M, mem, LV_DEL);
-      double newnrm = 0.0;
-      for (int i = 0; i < n; i++) {
-        const double d = LVEC(LV_DEL, i);
-        newnrm = fmax(newnrm, fabs(d * LVEC(LV_INVWT, i)));
-        const double dk = LVEC(LV_DIFKP1, i) + d;
-        LVEC(LV_DIFKP1, i) = dk;
-        LVEC(LV_YNEW, i) = LVEC(LV_PRED, i) + dk;
-      }
+      ln_residual(DEL, F, PSI, DIFKP1, hinvGak, n);
+      ln_solve(P, M, mem, DEL);
+      const double newnrm = ln_newton_update(DEL, INVWT, PRED, DIFKP1, YNEW, n);
       if (newnrm <= minnrm) { gotynew = true; break; }
       else if (iter == 1) {
         if (havrate) {
@@ -1031,24 +1121,22 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
           rate = 0.0;
         }
       } else if (newnrm > 0.9 * oldnrm) {
-        tooslow = true;
-        break;
+        break;  // too slow
       } else {
         rate = fmax(0.9 * rate, newnrm / oldnrm);
         havrate = true;
         const double errit = newnrm * rate / (1.0 - rate);
         if (errit <= 0.5 * rtol) { gotynew = true; break; }
-        else if (iter == maxit) { tooslow = true; break; }
+        else if (iter == maxit) break;
         else {
           double rp = rate;  // rate^(maxit-iter)
           for (int q = 1; q < maxit - iter; q++) rp *= rate;
-          if (0.5 * rtol < errit * rp) { tooslow = true; break; }
+          if (0.5 * rtol < errit * rp) break;
         }
       }
       oldnrm = newnrm;
     }
-    if (!gotynew) {  // Newton iteration too slow (tooslow is implied)
-      (void)tooslow;
+    if (!gotynew) {  // Newton iteration too slow
       M.st.failed++;
       if (!Jcurrent) {
         ln_env(P, M, mem, t, 0);
@@ -1072,9 +1160,7 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
       continue;
     }
     // ---- error estimate
-    err = 0.0;
-    for (int i = 0; i < n; i++) err = fmax(err, fabs(LVEC(LV_DIFKP1, i) * LVEC(LV_INVWT, i)));
-    err *= c_erconst[k - 1];
+    err = ln_wnorm(DIFKP1, INVWT, n) * c_erconst[k - 1];
     if (err > rtol) {
       M.st.failed++;
       if (absh <= hmin) {
@@ -1086,10 +1172,7 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
         nofailed = false;
         double hopt = absh * fmax(0.1, 0.833 * ln_root_n(rtol / err, k + 1.0));
         if (k > 1) {
-          double errkm1 = 0.0;
-          for (int i = 0; i < n; i++)
-            errkm1 = fmax(errkm1, fabs((LVEC(LV_DIF0 + (k - 1), i) + LVEC(LV_DIFKP1, i)) * LVEC(LV_INVWT, i)));
-          errkm1 *= c_erconst[k - 2];
+          const double errkm1 = ln_wnorm2(DIF + (k - 1) * np, DIFKP1, INVWT, n) * c_erconst[k - 2];
           const double hkm1 = absh * fmax(0.1, 0.769 * ln_root_n(rtol / errkm1, (double)k));
           if (hkm1 > hopt) {
             hopt = fmin(absh, hkm1);
@@ -1111,93 +1194,67 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
     }
     // ---- step accepted
     M.st.steps++;
-    {
-      double e_km1 = 0., e_kp1 = 0.;
-      const bool want_order = !done && (nconhk + 1 >= k + 2 || nconhk + 1 >= maxk + 2);
-      for (int i = 0; i < n; i++) {
-        const double dk = LVEC(LV_DIFKP1, i);
-        const double dkp1 = dk - LVEC(LV_DIF0 + k, i);
-        LVEC(LV_DIF0 + k + 1, i) = dkp1;
-        double acc = dk;
-        LVEC(LV_DIF0 + k, i) = acc;
-        for (int j = k - 1; j >= 0; j--) {
-          acc += LVEC(LV_DIF0 + j, i);
-          LVEC(LV_DIF0 + j, i) = acc;
-          if (j == k - 1 && want_order) e_km1 = fmax(e_km1, fabs(acc * LVEC(LV_INVWT, i)));
+    double e_km1 = 0., e_kp1 = 0.;
+    ln_dif_update(DIF, np, k, n, DIFKP1, INVWT, e_km1, e_kp1);
+    // ---- output at the sample times passed by this step
+    while ((next < tres) && ((tnew - tnext) >= 0.0)) {
+      if (tnew == tnext) {
+        ln_write_sources(P, M, mem, tnext, YNEW, F, next);
+      } else {
+        const double s = (tnext - tnew) / h;
+        double c1[5], c2[5];
+        double prod = 1.0, sumfrac = 0., fact = 1.0;
+        for (int j = 0; j < k; j++) {
+          prod *= (s + j);
+          fact *= (j + 1);
+          sumfrac += 1.0 / (s + j);
+          c1[j] = prod / fact;
+          c2[j] = prod * sumfrac / (h * fact);
         }
-        if (want_order) e_kp1 = fmax(e_kp1, fabs(dkp1 * LVEC(LV_INVWT, i)));
+        ln_interp(DIF, np, k, n, YNEW, c1, c2, LVP(LV_TMP), LVP(LV_YPI));
+        ln_write_sources(P, M, mem, tnext, LVP(LV_TMP), LVP(LV_YPI), next);
       }
-      // ---- output at the sample times passed by this step
-      while ((next < tres) && ((tnew - tnext) >= 0.0)) {
-        if (tnew == tnext) {
-          ln_write_sources(P, M, mem, tnext, LV_YNEW, LV_F, next);
-        } else {
-          const double s = (tnext - tnew) / h;
-          double c1[5], c2[5];
-          {
-            double prod = 1.0, sumfrac = 0., fact = 1.0;
-            for (int j = 0; j < k; j++) {
-              prod *= (s + j);
-              fact *= (j + 1);
-              sumfrac += 1.0 / (s + j);
-              c1[j] = prod / fact;
-              c2[j] = prod * sumfrac / (h * fact);
-            }
-          }
-          for (int i = 0; i < n; i++) {
-            double a1 = 0, a2 = 0;
-            for (int j = 0; j < k; j++) {
-              const double d = LVEC(LV_DIF0 + j, i);
-              a1 += c1[j] * d;
-              a2 += c2[j] * d;
-            }
-            LVEC(LV_TMP, i) = LVEC(LV_YNEW, i) + a1;
-            LVEC(LV_YPI, i) = a2;
-          }
-          ln_write_sources(P, M, mem, tnext, LV_TMP, LV_YPI, next);
-        }
-        next++;
-        tnext = (next < tres) ? LN_LDG(t_vec + next) : 1e300;
+      next++;
+      tnext = (next < tres) ? LN_LDG(t_vec + next) : 1e300;
+    }
+    if (done) break;
+    klast = k;
+    abshlast = absh;
+    nconhk = nconhk + 1 < maxk + 2 ? nconhk + 1 : maxk + 2;
+    if (nconhk >= k + 2) {
+      double temp = 0.;
+      if (err > 0.) temp = 1.2 * ln_root_n(err / rtol, k + 1.0);
+      double hopt = (temp > 0.1) ? absh / temp : 10 * absh;
+      int kopt = k;
+      if (k > 1) {
+        e_km1 *= c_erconst[k - 2];
+        temp = 0.;
+        if (e_km1 > 0.) temp = 1.3 * ln_root_n(e_km1 / rtol, (double)k);
+        const double hkm1 = (temp > 0.1) ? absh / temp : 10 * absh;
+        if (hkm1 > hopt) { hopt = hkm1; kopt = k - 1; }
       }
-      if (done) break;
-      klast = k;
-      abshlast = absh;
-      nconhk = nconhk + 1 < maxk + 2 ? nconhk + 1 : maxk + 2;
-      if (nconhk >= k + 2) {
-        double temp = 0.;
-        if (err > 0.) temp = 1.2 * ln_root_n(err / rtol, k + 1.0);
-        double hopt = (temp > 0.1) ? absh / temp : 10 * absh;
-        int kopt = k;
-        if (k > 1) {
-          e_km1 *= c_erconst[k - 2];
-          temp = 0.;
-          if (e_km1 > 0.) temp = 1.3 * ln_root_n(e_km1 / rtol, (double)k);
-          const double hkm1 = (temp > 0.1) ? absh / temp : 10 * absh;
-          if (hkm1 > hopt) { hopt = hkm1; kopt = k - 1; }
-        }
-        if (k < maxk) {
-          e_kp1 *= c_erconst[k];
-          temp = 0.;
-          if (e_kp1 > 0.) temp = 1.4 * ln_root_n(e_kp1 / rtol, k + 2.0);
-          const double hkp1 = (temp > 0.1) ? absh / temp : 10 * absh;
-          if (hkp1 > hopt) { hopt = hkp1; kopt = k + 1; }
-        }
-        if (hopt > absh) {
-          absh = hopt;
-          if (k != kopt) k = kopt;
-        }
+      if (k < maxk) {
+        e_kp1 *= c_erconst[k];
+        temp = 0.;
+        if (e_kp1 > 0.) temp = 1.4 * ln_root_n(e_kp1 / rtol, k + 2.0);
+        const double hkp1 = (temp > 0.1) ? absh / temp : 10 * absh;
+        if (hkp1 > hopt) { hopt = hkp1; kopt = k + 1; }
+      }
+      if (hopt > absh) {
+        absh = hopt;
+        if (k != kopt) k = kopt;
       }
     }
     t = tnew;
-    for (int i = 0; i < n; i++) LVEC(LV_Y, i) = LVEC(LV_YNEW, i);
+    ln_copy(Y, YNEW, n);
     Jcurrent = false;
     new_step = true;
   }
   // final state, and a last RHS call so that the environment and the TCA/RSA by-products are current at the end of
   // the interval (evolver_ndf15.cpp:653-662)
-  for (int i = 0; i < n; i++) LVEC(LV_Y, i) = LVEC(LV_YNEW, i);
+  ln_copy(Y, YNEW, n);
   ln_env(P, M, mem, tnew, 0);
-  ln_rhs(P, M, mem, LV_Y, LV_F, LR_HUB | LR_CHAINS, nullptr);
+  ln_rhs(P, M, Y, F, NW, LR_HUB | LR_CHAINS);
   if (!M.ap.tca_off) M.tca_shear_last = M.m.tca_shear_g;
   M.st.fevals++;
   M.next = next;
@@ -1229,18 +1286,18 @@ LN_NOINLINE void ln_initial_conditions(const PtParams& P, Lane& M, double* __res
   const double l3_ur = ktau_three * 2. / 7. / (12. * fracnu + 45.) * ci;
   const double eta = ci * (1. - ktau_two / 12. / (15. + 4. * fracnu) *
                                     (5. + 4. * fracnu - (16. * fracnu * fracnu + 280. * fracnu + 325) / 10. / (2. * fracnu + 15.) * tau * om));
-  for (int i = 0; i < L.neq; i++) LVEC(LV_Y, i) = 0.;
-  LVEC(LV_Y, L.delta_g) = delta_g;
-  LVEC(LV_Y, L.theta_g) = theta_g;
-  LVEC(LV_Y, L.delta_b) = 3. / 4. * delta_g;
-  LVEC(LV_Y, L.theta_b) = theta_g;
-  LVEC(LV_Y, L.delta_cdm) = 3. / 4. * delta_g;
-  LVEC(LV_Y, L.eta) = eta;
+  for (int i = 0; i < L.neq; i++) LVP(LV_Y)[i] = 0.;
+  LVP(LV_Y)[L.delta_g] = delta_g;
+  LVP(LV_Y)[L.theta_g] = theta_g;
+  LVP(LV_Y)[L.delta_b] = 3. / 4. * delta_g;
+  LVP(LV_Y)[L.theta_b] = theta_g;
+  LVP(LV_Y)[L.delta_cdm] = 3. / 4. * delta_g;
+  LVP(LV_Y)[L.eta] = eta;
   if (P.has_ur) {
-    LVEC(LV_Y, L.delta_ur) = delta_ur;
-    LVEC(LV_Y, L.theta_ur) = theta_ur;
-    LVEC(LV_Y, L.shear_ur) = shear_ur;
-    LVEC(LV_Y, L.c_ur) = l3_ur;
+    LVP(LV_Y)[L.delta_ur] = delta_ur;
+    LVP(LV_Y)[L.theta_ur] = theta_ur;
+    LVP(LV_Y)[L.shear_ur] = shear_ur;
+    LVP(LV_Y)[L.c_ur] = l3_ur;
   }
   if (P.has_ncdm) {
     for (int s = 0; s < P.N_ncdm; s++) {
@@ -1250,10 +1307,10 @@ LN_NOINLINE void ln_initial_conditions(const PtParams& P, Lane& M, double* __res
         const double q = M.C->ncdm_q[j];
         const double dlnf0 = M.C->ncdm_dlnf0[j];
         const double epsq = sqrt(q * q + a * a * Ms * Ms);
-        LVEC(LV_Y, idx + 0) = -0.25 * delta_ur * dlnf0;
-        LVEC(LV_Y, idx + 1) = -epsq / 3. / q / k * theta_ur * dlnf0;
-        LVEC(LV_Y, idx + 2) = -0.5 * shear_ur * dlnf0;
-        LVEC(LV_Y, L.c_ncdm + j * L.len_ncdm) = -0.25 * l3_ur * dlnf0;
+        LVP(LV_Y)[idx + 0] = -0.25 * delta_ur * dlnf0;
+        LVP(LV_Y)[idx + 1] = -epsq / 3. / q / k * theta_ur * dlnf0;
+        LVP(LV_Y)[idx + 2] = -0.5 * shear_ur * dlnf0;
+        LVP(LV_Y)[L.c_ncdm + j * L.len_ncdm] = -0.25 * l3_ur * dlnf0;
       }
     }
   }
@@ -1266,8 +1323,8 @@ LN_NOINLINE void ln_remap_state(const PtParams& P, Lane& M, double* __restrict__
   const Approx& apo = M.apprev;
   const Approx& apn = M.ap;
   const double k = M.k;
-#define YO(i) LVEC(LV_Y, i)
-#define YN(i) LVEC(LV_YNEW, i)
+#define YO(i) LVP(LV_Y)[i]
+#define YN(i) LVP(LV_YNEW)[i]
   for (int i = 0; i < Ln.neq; i++) YN(i) = 0.;
   YN(Ln.delta_b) = YO(Lo.delta_b);
   YN(Ln.theta_b) = YO(Lo.theta_b);

@@ -2931,12 +2931,19 @@ __global__ void __launch_bounds__(32 * PT_TAIL_MAX_WPC, PT_TAIL_MIN_BLOCKS / PT_
 // =============================================================================================
 #include "lane.cuh"
 
+// W = doubles of per-thread state (compile-time size of the local-memory slab); W = 0: slab in global memory
+// (fallback for state vectors larger than the largest instantiation; correct but slow)
+template <int W>
 __global__ void __launch_bounds__(LN_CTA) perturb_lane_kernel(const __grid_constant__ PtParams P) {
   const int slot = blockIdx.x * LN_CTA + threadIdx.x;
   if (slot >= P.n_modes) return;
   const int2 md = P.modes[slot];
-  double* mem = P.lane_scratch + (size_t)blockIdx.x * P.ln_words * LN_CTA + threadIdx.x;
-  ln_mode(P, mem, P.cosmo + md.x, md.y);
+  if constexpr (W > 0) {
+    double slab[W];
+    ln_mode(P, slab, P.cosmo + md.x, md.y);
+  } else {
+    ln_mode(P, P.lane_scratch + (size_t)slot * P.ln_words, P.cosmo + md.x, md.y);
+  }
 }
 
 // =============================================================================================
@@ -3144,18 +3151,29 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     if (clpp_dev_reserve(d0, &d0->i2l1, (size_t)P.n_i2l1, err)) return CLPP_FAILURE;
     CLPP_CUDA(cudaMemcpyAsync(d0->i2l1, i2l1.data(), P.n_i2l1 * sizeof(double), cudaMemcpyHostToDevice, st), err);
     const int n_cta = (n_modes + LN_CTA - 1) / LN_CTA;
-    if (clpp_dev_reserve(d0, &d0->lane_scratch, (size_t)std::max(n_cta, 1) * P.ln_words * LN_CTA, err)) return CLPP_FAILURE;
+    static const int slab_sizes[] = {1536, 2816, 4608, 9216, 14336};
+    int slab = 0;
+    for (int w : slab_sizes)
+      if (slab == 0 && P.ln_words <= w) slab = w;
+    if (slab == 0 && clpp_dev_reserve(d0, &d0->lane_scratch, (size_t)std::max(n_modes, 1) * P.ln_words, err)) return CLPP_FAILURE;
     P.cosmo = (const PtCosmo*)d0->pt_cosmo;
     P.modes = (const int2*)d0->pt_modes;
     P.n_modes = n_modes;
     P.lane_scratch = d0->lane_scratch;
     P.i2l1 = d0->i2l1;
     if (getenv("CLPP_VERBOSE"))
-      fprintf(stderr, "[clpp] perturb (lane kernel): %d modes, %d CTAs of %d threads, %d doubles of scratch per mode, neq_max %d, hub %d\n",
-              n_modes, n_cta, LN_CTA, P.ln_words, P.neq_max, P.nh_max);
+      fprintf(stderr, "[clpp] perturb (lane kernel): %d modes, %d CTAs of %d threads, %d doubles of state per mode (slab %d), neq_max %d, hub %d\n",
+              n_modes, n_cta, LN_CTA, P.ln_words, slab, P.neq_max, P.nh_max);
     cudaEventRecord(d0->ev[0], st);
     if (n_modes > 0) {
-      perturb_lane_kernel<<<n_cta, LN_CTA, 0, st>>>(P);
+      switch (slab) {
+        case 1536: perturb_lane_kernel<1536><<<n_cta, LN_CTA, 0, st>>>(P); break;
+        case 2816: perturb_lane_kernel<2816><<<n_cta, LN_CTA, 0, st>>>(P); break;
+        case 4608: perturb_lane_kernel<4608><<<n_cta, LN_CTA, 0, st>>>(P); break;
+        case 9216: perturb_lane_kernel<9216><<<n_cta, LN_CTA, 0, st>>>(P); break;
+        case 14336: perturb_lane_kernel<14336><<<n_cta, LN_CTA, 0, st>>>(P); break;
+        default: perturb_lane_kernel<0><<<n_cta, LN_CTA, 0, st>>>(P); break;
+      }
       c0->launches++;
     }
   } else {

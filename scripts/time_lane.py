@@ -43,5 +43,5 @@ for B in batches:
         if ref is None:
             ref = src
         else:
-            sc = np.max(np.abs(ref), axis=2, keepdims=True)
-            print("   max |S - S_first| / max_tau |S| per type:", ["%.1e" % v for v in np.max(np.abs(src - ref) / np.where(sc > 0, sc, 1), axis=(1, 2))], flush=True)
+            sc = np.max(np.abs(ref), axis=1, keepdims=True)
+            print("   max |S - S_first| / max_tau |S| per type:", ["%.1e" % v for v in np.max(np.abs(src - ref) / np.where(sc > 0, sc, 1), axis=1)], flush=True)
