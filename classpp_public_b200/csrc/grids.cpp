@@ -145,9 +145,24 @@ static int tau_sampling(clpp_ctx* c, char* err) {
   c->pinfo.tau_size = (int)T.size();
 
   CLPP_CHECK(p.z_max_pk >= 0, err, "asked for negative redshift z=%e", p.z_max_pk);
-  CLPP_CHECK(p.z_max_pk == 0., err,
-             "z_max_pk > 0 (late-time source interpolation table) is not supported by the B200 path yet");
+  // z_max_pk > 0: the last samples (from the one before tau(z_max_pk), plus four more) form the late-time table that
+  // perturb_sources_at_tau splines in ln(tau) (:1541-1592); the sampling itself does not change
   c->pinfo.ln_tau_size = 1;
+  if (p.z_max_pk > 0.) {
+    const double a_target = bg.a_today / (1. + p.z_max_pk);
+    const HostTable& B = c->bgt;
+    int i = 0;
+    while (i < B.n_lines - 2 && B.y[(size_t)(i + 1) * B.n_cols + bg.index_bg_a] < a_target) i++;
+    const double a0 = B.y[(size_t)i * B.n_cols + bg.index_bg_a], a1 = B.y[(size_t)(i + 1) * B.n_cols + bg.index_bg_a];
+    const double tau_lower = B.x[i] + (B.x[i + 1] - B.x[i]) * (a_target - a0) / (a1 - a0);
+    CLPP_CHECK(tau_lower > T[0], err,
+               "you asked for zmax=%e, i.e. taumin=%e, smaller than or equal to the first possible value =%e; it should be "
+               "strictly bigger for a successfull interpolation", p.z_max_pk, tau_lower, T[0]);
+    int first = 0;
+    while (T[first] < tau_lower) first++;
+    first = std::max(first - 5, 0);
+    c->pinfo.ln_tau_size = (int)T.size() - first;
+  }
   return CLPP_SUCCESS;
 }
 

@@ -1261,6 +1261,586 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
   return true;
 }
 
+// =================================================================================================
+// TAIL: the radiation-streaming interval (RSA on, ncdm fluid on if any): N = 4 + 3 N_ncdm equations, no chains.  It is
+// the last interval of every mode with k tau_0 > 45 and holds 70 % of all steps (10^4 .. 3x10^5 per high-k mode): the
+// serial critical path of a launch.  Everything of the integrator lives in REGISTERS (fully unrolled static arrays:
+// state, backward differences, step-control vectors); only the LU factors of the N x N Newton matrix sit in local
+// memory (partial pivoting needs dynamic row indices).  The environment is evaluated straight into registers.
+// State order (ln_make_layout with rsa_on): delta_b, theta_b, delta_cdm, [delta, theta, shear](ncdm s), eta.
+// =================================================================================================
+template <int NN>
+struct LnTailEnv {
+  double a2x15, aH, inv_half_aH, rho_b, rho_cdm, rho_g43, rho_ur43, dkappa, ddkappa, cb2, Rdk;
+  double nf[NN > 0 ? NN : 1][8];
+};
+
+template <int NN>
+LN_FN void ln_env_tail(const PtParams& P, Lane& M, double tau, LnTailEnv<NN>& E) {
+  double av, Hv, rho_g, rho_b;
+  double rho_n[NN > 0 ? NN : 1], p_n[NN > 0 ? NN : 1], pp_n[NN > 0 ? NN : 1];
+  {
+    const int inf = ln_locate(M.bg_tau, M.bt_size, tau, M.bg_cur);
+    M.bg_cur = inf;
+    const double x0 = LN_LDG(M.bg_tau + inf), x1 = LN_LDG(M.bg_tau + inf + 1);
+    const double h = x1 - x0, ih = 1.0 / h, h26 = h * h / 6.;
+    const double b = (tau - x0) * ih, a = 1 - b;
+    const double ca = (a * a * a - a), cb = (b * b * b - b);
+    const double* __restrict__ y0 = M.bg_y + (size_t)inf * P.bg_size;
+    const double* __restrict__ y1 = y0 + P.bg_size;
+    const double* __restrict__ d0 = M.bg_dd + (size_t)inf * P.bg_size;
+    const double* __restrict__ d1 = d0 + P.bg_size;
+#define LN_BG(col) (a * LN_LDG(y0 + (col)) + b * LN_LDG(y1 + (col)) + (ca * LN_LDG(d0 + (col)) + cb * LN_LDG(d1 + (col))) * h26)
+    av = LN_BG(P.ia); Hv = LN_BG(P.iH);
+    rho_g = LN_BG(P.irho_g); rho_b = LN_BG(P.irho_b); E.rho_cdm = LN_BG(P.irho_cdm);
+    E.rho_ur43 = P.has_ur ? 4. / 3. * LN_BG(P.irho_ur) : 0.;
+#pragma unroll
+    for (int s = 0; s < NN; s++) {
+      rho_n[s] = LN_BG(P.irho_ncdm1 + s); p_n[s] = LN_BG(P.ip_ncdm1 + s); pp_n[s] = LN_BG(P.ipseudo_p_ncdm1 + s);
+    }
+#undef LN_BG
+  }
+  const double inv_a = 1. / av;
+  const double z = inv_a - 1.;
+  if (z >= M.z_last) {
+    const PtCosmo* C = M.C;
+    const double* row = M.th_y + (size_t)(M.tt_size - 1) * P.th_size;
+    const double xe0 = LN_LDG(row + P.ixe);
+    E.dkappa = (1. + z) * (1. + z) * C->n_e * xe0 * CLPP_sigma * CLPP_Mpc_over_m;
+    E.ddkappa = -Hv * 2. / (1. + z) * E.dkappa;
+    const double wb = CLPP_k_B / (CLPP_c * CLPP_c * CLPP_m_H) * (1. + (1. / CLPP_not4 - 1.) * C->YHe + xe0 * (1. - C->YHe)) *
+                      C->T_cmb * (1. + z);
+    E.cb2 = wb * 4. / 3.;
+  } else {
+    const bool linear = (z < M.th_lin);
+    const int inf = ln_locate(M.th_z, M.tt_size, z, M.th_cur);
+    M.th_cur = inf;
+    const double x0 = LN_LDG(M.th_z + inf), x1 = LN_LDG(M.th_z + inf + 1);
+    const double h = x1 - x0, ih = 1.0 / h, h26 = linear ? 0. : h * h / 6.;
+    const double b = (z - x0) * ih, a = 1 - b;
+    const double ca = (a * a * a - a), cb = (b * b * b - b);
+    const double* __restrict__ y0 = M.th_y + (size_t)inf * P.th_size;
+    const double* __restrict__ y1 = y0 + P.th_size;
+    const double* __restrict__ d0 = M.th_dd + (size_t)inf * P.th_size;
+    const double* __restrict__ d1 = d0 + P.th_size;
+#define LN_TH(col) (a * LN_LDG(y0 + (col)) + b * LN_LDG(y1 + (col)) + (ca * LN_LDG(d0 + (col)) + cb * LN_LDG(d1 + (col))) * h26)
+    E.dkappa = LN_TH(P.idkappa); E.ddkappa = LN_TH(P.iddkappa); E.cb2 = LN_TH(P.icb2);
+#undef LN_TH
+  }
+  const double aH = Hv * av;
+  E.a2x15 = 1.5 * av * av;
+  E.aH = aH;
+  E.inv_half_aH = 2. / aH;
+  E.rho_b = rho_b;
+  E.rho_g43 = 4. / 3. * rho_g;
+  E.Rdk = 4. / 3. * rho_g / rho_b * E.dkappa;
+#pragma unroll
+  for (int s = 0; s < NN; s++) {
+    const double rho = rho_n[s], p = p_n[s], pseudo = pp_n[s];
+    const double w_n = p / rho, pseudo_p_over_p = pseudo / p, i1w = rho / (rho + p);
+    const double cg2 = w_n * (1.0 - i1w * (1. / 3.) * (3.0 * w_n - 2.0 + pseudo_p_over_p));
+    const double ca2 = w_n * (1. / 3.) * i1w * (5.0 - pseudo_p_over_p);
+    const double cvis2 = (P.ncdmfa_method == CLPP_NCDMFA_HU) ? w_n : 3. * w_n * ca2;
+    const double damp = (P.ncdmfa_method == CLPP_NCDMFA_HU) ? 3.0 * aH * ca2 * (rho / p)
+                                                            : 3.0 * (aH * (2. / 3. - ca2 - pseudo_p_over_p * (1. / 3.)) + 1.0 / tau);
+    E.nf[s][0] = rho; E.nf[s][1] = rho + p; E.nf[s][2] = w_n; E.nf[s][3] = cg2 * rho; E.nf[s][4] = ca2; E.nf[s][5] = ca2 * i1w;
+    E.nf[s][6] = 8.0 / 3.0 * cvis2 * i1w; E.nf[s][7] = damp;
+  }
+}
+
+// f(tau, y) of the radiation-streaming interval (perturb_total_stress_energy / perturb_einstein /
+// perturb_rsa_delta_and_theta / perturb_derivs_member restricted to this approximation set)
+template <int NN>
+LN_FN void ln_rhs_tail(const PtParams& P, const LnTailEnv<NN>& E, double k2, double ik2, const double (&y)[4 + 3 * NN],
+                       double (&dy)[4 + 3 * NN]) {
+  constexpr int N = 4 + 3 * NN;
+  const double delta_b = y[0], theta_b = y[1], delta_cdm = y[2], eta = y[N - 1];
+  double delta_rho = E.rho_b * delta_b + E.rho_cdm * delta_cdm;
+  double rpt = E.rho_b * theta_b;
+#pragma unroll
+  for (int s = 0; s < NN; s++) {
+    delta_rho += E.nf[s][0] * y[3 + 3 * s];
+    rpt += E.nf[s][1] * y[4 + 3 * s];
+  }
+  const double aH = E.aH;
+  const double h_prime = (k2 * eta + E.a2x15 * delta_rho) * E.inv_half_aH;
+  double rsa_theta_g = 0.;
+  if (P.rsa_method != CLPP_RSA_NULL) rsa_theta_g = -0.5 * h_prime;
+  const double rsa_theta_ur = rsa_theta_g;  // before the reionisation correction
+  if (P.rsa_method == CLPP_RSA_MD_WITH_REIO)
+    rsa_theta_g += 3. * ik2 * (E.ddkappa * (theta_b + 0.5 * h_prime) +
+                               E.dkappa * (-aH * theta_b + E.cb2 * k2 * delta_b - aH * h_prime + k2 * eta));
+  rpt += E.rho_g43 * rsa_theta_g + E.rho_ur43 * rsa_theta_ur;
+  const double eta_prime = (E.a2x15 * rpt) * ik2;
+  const double alpha = (h_prime + 6. * eta_prime) * 0.5 * ik2;
+  const double metric_continuity = 0.5 * h_prime;
+  const double metric_shear = k2 * alpha;
+  dy[0] = -(theta_b + metric_continuity);
+  dy[1] = -aH * theta_b + k2 * E.cb2 * delta_b + E.Rdk * (rsa_theta_g - theta_b);
+  dy[2] = -metric_continuity;
+  dy[N - 1] = eta_prime;
+#pragma unroll
+  for (int s = 0; s < NN; s++) {
+    const double* nf = E.nf[s];
+    const double y0 = y[3 + 3 * s], y1 = y[4 + 3 * s], y2 = y[5 + 3 * s];
+    const double w_n = nf[2], ca2 = nf[4];
+    const double msn = (P.ncdmfa_method == CLPP_NCDMFA_CLASS) ? metric_continuity : metric_shear;
+    dy[3 + 3 * s] = -(1.0 + w_n) * (y1 + metric_continuity) - 3.0 * aH * (ca2 - w_n) * y0;
+    dy[4 + 3 * s] = -aH * (1.0 - 3.0 * ca2) * y1 + nf[5] * k2 * y0 - k2 * y2;
+    dy[5 + 3 * s] = -nf[7] * y2 + nf[6] * (y1 + msn);
+  }
+}
+
+template <int NN>
+LN_NOINLINE bool ln_ndf15_tail(const PtParams& P, Lane& M, double* __restrict__ mem, double t0, double tfinal) {
+  constexpr int N = 4 + 3 * NN;
+  const double eps = 1e-16, threshold = 1e-15;
+  const int maxit = 4, maxk = 5;
+  const double rtol = P.rtol;
+  const double k2 = M.k2, ik2 = M.ik2;
+  const double* t_vec = M.C->tau;
+  const int tres = M.C->tau_size;
+  int next = M.next;
+  while (next < tres && LN_LDG(t_vec + next) < t0) next++;
+  double tnext = (next < tres) ? LN_LDG(t_vec + next) : 1e300;
+  double y[N], dif[7][N], psi[N], pred[N], dk1[N], iw[N], f[N], tmp[N];
+  double J[N * N], A[N * N];  // Jacobian and LU factors of I - c J (row-major; local memory: dynamic pivot rows)
+  int piv[N];
+  LnTailEnv<NN> E;
+  {
+    const double* Ys = LVP(LV_Y);
+#pragma unroll
+    for (int i = 0; i < N; i++) y[i] = Ys[i];
+  }
+#pragma unroll
+  for (int j = 0; j < 7; j++)
+#pragma unroll
+    for (int i = 0; i < N; i++) dif[j][i] = 0.;
+
+  auto jacobian = [&]() {  // columns f(e_j): the system is linear and homogeneous; the environment must be current
+#pragma unroll 1
+    for (int j = 0; j < N; j++) {
+      double ej[N], col[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) ej[i] = (i == j) ? 1. : 0.;
+      ln_rhs_tail<NN>(P, E, k2, ik2, ej, col);
+#pragma unroll
+      for (int i = 0; i < N; i++) J[i * N + j] = col[i];
+    }
+    M.st.jacobians++;
+    M.st.fevals += N;
+  };
+  auto factor = [&](double c) {
+#pragma unroll 1
+    for (int i = 0; i < N * N; i++) A[i] = -c * J[i];
+#pragma unroll 1
+    for (int i = 0; i < N; i++) A[i * N + i] += 1.0;
+#pragma unroll 1
+    for (int j = 0; j < N; j++) {
+      double best = fabs(A[j * N + j]);
+      int bi = j;
+      for (int i = j + 1; i < N; i++) {
+        const double v = fabs(A[i * N + j]);
+        if (v > best) { best = v; bi = i; }
+      }
+      piv[j] = bi;
+      if (bi != j) {
+        for (int cc = 0; cc < N; cc++) {
+          const double t_ = A[j * N + cc];
+          A[j * N + cc] = A[bi * N + cc];
+          A[bi * N + cc] = t_;
+        }
+      }
+      double pv = A[j * N + j];
+      if (pv == 0.) pv = 1e-50;
+      const double pinv = 1.0 / pv;
+      A[j * N + j] = pinv;
+      for (int i = j + 1; i < N; i++) {
+        const double fm = A[i * N + j] * pinv;
+        A[i * N + j] = fm;
+        for (int cc = j + 1; cc < N; cc++) A[i * N + cc] -= fm * A[j * N + cc];
+      }
+    }
+    M.st.factorizations++;
+  };
+  auto solve = [&](double (&b)[N]) {  // in place
+#pragma unroll
+    for (int i = 0; i < N; i++) tmp[i] = b[i];
+#pragma unroll 1
+    for (int j = 0; j < N; j++) {
+      const int p = piv[j];
+      if (p != j) { const double t_ = tmp[j]; tmp[j] = tmp[p]; tmp[p] = t_; }
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) b[i] = tmp[i];
+#pragma unroll
+    for (int i = 1; i < N; i++) {
+      double s = b[i];
+#pragma unroll
+      for (int j = 0; j < i; j++) s -= A[i * N + j] * b[j];
+      b[i] = s;
+    }
+#pragma unroll
+    for (int i = N - 1; i >= 0; i--) {
+      double s = b[i];
+#pragma unroll
+      for (int j = i + 1; j < N; j++) s -= A[i * N + j] * b[j];
+      b[i] = s * A[i * N + i];
+    }
+    M.st.solves++;
+  };
+  auto rescale = [&](double r, int kord) {  // adjust_stepsize
+    double RU[5][5];
+    {
+      double Rm[5][5];
+#pragma unroll
+      for (int kk = 0; kk < 5; kk++) {
+        double Rv = 1.;
+#pragma unroll
+        for (int ii = 0; ii < 5; ii++) {
+          Rv *= (ii - (kk + 1) * r) * c_invint[ii + 1];
+          Rm[ii][kk] = Rv;
+        }
+      }
+#pragma unroll
+      for (int ii = 0; ii < 5; ii++)
+#pragma unroll
+        for (int jj = 0; jj < 5; jj++) {
+          double s = 0.;
+#pragma unroll
+          for (int kk = 0; kk < 5; kk++) s += Rm[ii][kk] * c_U[kk][jj];
+          RU[ii][jj] = s;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      double row[5], o[5];
+#pragma unroll
+      for (int kk = 0; kk < 5; kk++) row[kk] = (kk < kord) ? dif[kk][i] : 0.;
+#pragma unroll
+      for (int jj = 0; jj < 5; jj++) {
+        double s = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 5; kk++) s += row[kk] * RU[kk][jj];
+        o[jj] = s;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 5; jj++)
+        if (jj < kord) dif[jj][i] = o[jj];
+    }
+  };
+
+  const double htspan = fabs(tfinal - t0);
+  double t = t0, tnew = t0;
+  ln_env_tail<NN>(P, M, t0, E);
+  ln_rhs_tail<NN>(P, E, k2, ik2, y, f);
+  M.st.fevals++;
+  const double hmax = (tfinal - t0) / 10.0;
+  jacobian();
+  bool Jcurrent = true;
+  double hmin = 16.0 * eps * fabs(t);
+  double rh = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const double wt = fmax(fabs(y[i]), threshold);
+    rh = fmax(rh, 1.25 / sqrt(rtol) * fabs(f[i] / wt));
+  }
+  double absh = fmin(hmax, htspan);
+  if (absh * rh > 1.0) absh = 1.0 / rh;
+  absh = fmax(absh, hmin);
+  double h = absh;
+  {
+    double jf[N], fdel[N];
+    ln_rhs_tail<NN>(P, E, k2, ik2, f, jf);  // J*f0 = f(t0, f0)
+    const double tdel = (t + fmin(sqrt(eps) * fmax(fabs(t), fabs(t + h)), absh)) - t;
+    ln_env_tail<NN>(P, M, t + tdel, E);
+    ln_rhs_tail<NN>(P, E, k2, ik2, y, fdel);
+    M.st.fevals += 2;
+    rh = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const double wt = fmax(fabs(y[i]), threshold);
+      const double s = jf[i] + (fdel[i] - f[i]) / tdel;
+      rh = fmax(rh, 1.25 * sqrt(0.5 * fabs(s / wt) / rtol));
+    }
+    absh = fmin(hmax, htspan);
+    if (absh * rh > 1.0) absh = 1.0 / rh;
+    absh = fmax(absh, hmin);
+    h = absh;
+  }
+  int k = 1, klast = k;
+  double abshlast = absh;
+#pragma unroll
+  for (int i = 0; i < N; i++) dif[0][i] = h * f[i];
+  double hinvGak = h * c_invGa[k - 1];
+  int nconhk = 0;
+  factor(hinvGak);
+  bool havrate = false, done = false, at_hmin = false, new_step = true, nofailed = true;
+  double rate = 0., oldnrm = 0., err = 0.;
+
+  for (;;) {
+    if (new_step) {
+      hmin = P.hmin_allowed;
+      absh = fmin(hmax, fmax(hmin, absh));
+      if (fabs(absh - hmin) < 100 * eps) {
+        if (at_hmin) absh = abshlast;
+        at_hmin = true;
+      } else {
+        at_hmin = false;
+      }
+      h = absh;
+      if (1.1 * absh >= fabs(tfinal - t)) {
+        h = tfinal - t;
+        absh = fabs(h);
+        done = true;
+      }
+      if (((fabs(absh - abshlast) / absh) > 1e-6) || (k != klast)) {
+        rescale(absh / abshlast, k);
+        hinvGak = h * c_invGa[k - 1];
+        nconhk = 0;
+        factor(hinvGak);
+        havrate = false;
+      }
+      nofailed = true;
+      new_step = false;
+    }
+    // ---- one attempt
+    tnew = t + h;
+    if (done) tnew = tfinal;
+    h = tnew - t;
+    double minnrm = 0.0;
+    {
+      const double invGak = c_invGa[k - 1];
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        double ps = 0., pr = y[i];
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+          if (j < k) {
+            ps += dif[j][i] * (c_G[j] * invGak);
+            pr += dif[j][i];
+          }
+        }
+        psi[i] = ps; pred[i] = pr; dk1[i] = 0.;
+        iw[i] = 1.0 / fmax(fmax(fabs(pr), fabs(y[i])), threshold);
+        minnrm = fmax(minnrm, 100 * eps * fabs(pr * iw[i]));
+      }
+    }
+    ln_env_tail<NN>(P, M, tnew, E);
+    bool gotynew = false;
+#pragma unroll 1
+    for (int iter = 1; iter <= maxit; iter++) {
+      double yn[N], r[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) yn[i] = pred[i] + dk1[i];
+      ln_rhs_tail<NN>(P, E, k2, ik2, yn, f);
+      M.st.fevals++;
+#pragma unroll
+      for (int i = 0; i < N; i++) r[i] = hinvGak * f[i] - (psi[i] + dk1[i]);
+      solve(r);
+      double newnrm = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        newnrm = fmax(newnrm, fabs(r[i] * iw[i]));
+        dk1[i] += r[i];
+      }
+      if (newnrm <= minnrm) { gotynew = true; break; }
+      else if (iter == 1) {
+        if (havrate) {
+          const double errit = newnrm * rate / (1.0 - rate);
+          if (errit <= 0.05 * rtol) { gotynew = true; break; }
+        } else {
+          rate = 0.0;
+        }
+      } else if (newnrm > 0.9 * oldnrm) {
+        break;
+      } else {
+        rate = fmax(0.9 * rate, newnrm / oldnrm);
+        havrate = true;
+        const double errit = newnrm * rate / (1.0 - rate);
+        if (errit <= 0.5 * rtol) { gotynew = true; break; }
+        else if (iter == maxit) break;
+        else {
+          double rp = rate;
+          for (int q = 1; q < maxit - iter; q++) rp *= rate;
+          if (0.5 * rtol < errit * rp) break;
+        }
+      }
+      oldnrm = newnrm;
+    }
+    if (!gotynew) {
+      M.st.failed++;
+      if (!Jcurrent) {
+        ln_env_tail<NN>(P, M, t, E);
+        M.st.fevals++;
+        jacobian();
+        Jcurrent = true;
+      } else if (absh <= hmin) {
+        M.status = 2;
+        return false;
+      } else {
+        abshlast = absh;
+        absh = fmax(0.3 * absh, hmin);
+        h = absh;
+        done = false;
+        rescale(absh / abshlast, k);
+        hinvGak = h * c_invGa[k - 1];
+        nconhk = 0;
+      }
+      factor(hinvGak);
+      havrate = false;
+      continue;
+    }
+    err = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i++) err = fmax(err, fabs(dk1[i] * iw[i]));
+    err *= c_erconst[k - 1];
+    if (err > rtol) {
+      M.st.failed++;
+      if (absh <= hmin) {
+        M.status = 2;
+        return false;
+      }
+      abshlast = absh;
+      if (nofailed) {
+        nofailed = false;
+        double hopt = absh * fmax(0.1, 0.833 * ln_root_n(rtol / err, k + 1.0));
+        if (k > 1) {
+          double errkm1 = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; i++) {
+            double dkm = dif[0][i];
+#pragma unroll
+            for (int j = 1; j < 5; j++) dkm = (j == k - 1) ? dif[j][i] : dkm;
+            errkm1 = fmax(errkm1, fabs((dkm + dk1[i]) * iw[i]));
+          }
+          errkm1 *= c_erconst[k - 2];
+          const double hkm1 = absh * fmax(0.1, 0.769 * ln_root_n(rtol / errkm1, (double)k));
+          if (hkm1 > hopt) {
+            hopt = fmin(absh, hkm1);
+            k = k - 1;
+          }
+        }
+        absh = fmax(hmin, hopt);
+      } else {
+        absh = fmax(hmin, 0.5 * absh);
+      }
+      h = absh;
+      if (absh < abshlast) done = false;
+      rescale(absh / abshlast, k);
+      hinvGak = h * c_invGa[k - 1];
+      nconhk = 0;
+      factor(hinvGak);
+      havrate = false;
+      continue;
+    }
+    // ---- step accepted: dif[k+1] = dk1 - dif[k]; dif[k] = dk1; dif[j] += dif[j+1] (j < k)
+    M.st.steps++;
+    double e_km1 = 0., e_kp1 = 0.;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      double difk_old = dif[0][i];
+#pragma unroll
+      for (int j = 1; j < 7; j++) difk_old = (j == k) ? dif[j][i] : difk_old;
+      const double dkp1 = dk1[i] - difk_old;
+#pragma unroll
+      for (int j = 6; j >= 0; j--) {
+        if (j == k + 1) dif[j][i] = dkp1;
+        else if (j == k) dif[j][i] = dk1[i];
+        else if (j < k) dif[j][i] += dif[j + 1][i];
+        if (j == k - 1) e_km1 = fmax(e_km1, fabs(dif[j][i] * iw[i]));
+      }
+      e_kp1 = fmax(e_kp1, fabs(dkp1 * iw[i]));
+    }
+    // ---- output at the sample times passed by this step (through the generic source routine)
+    while ((next < tres) && ((tnew - tnext) >= 0.0)) {
+      double* yo = LVP(LV_TMP);
+      double* dyo = LVP(LV_YPI);
+      if (tnew == tnext) {
+#pragma unroll
+        for (int i = 0; i < N; i++) { yo[i] = pred[i] + dk1[i]; dyo[i] = f[i]; }
+      } else {
+        const double s = (tnext - tnew) / h;
+        double c1[5], c2[5];
+        double prod = 1.0, sumfrac = 0., fact = 1.0;
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+          prod *= (s + j);
+          fact *= (j + 1);
+          sumfrac += 1.0 / (s + j);
+          c1[j] = (j < k) ? prod / fact : 0.;
+          c2[j] = (j < k) ? prod * sumfrac / (h * fact) : 0.;
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          double a1 = 0, a2 = 0;
+#pragma unroll
+          for (int j = 0; j < 5; j++) { a1 += c1[j] * dif[j][i]; a2 += c2[j] * dif[j][i]; }
+          yo[i] = (pred[i] + dk1[i]) + a1;
+          dyo[i] = a2;
+        }
+      }
+      ln_write_sources(P, M, mem, tnext, yo, dyo, next);
+      next++;
+      tnext = (next < tres) ? LN_LDG(t_vec + next) : 1e300;
+    }
+    if (done) break;
+    klast = k;
+    abshlast = absh;
+    nconhk = nconhk + 1 < maxk + 2 ? nconhk + 1 : maxk + 2;
+    if (nconhk >= k + 2) {
+      double temp = 0.;
+      if (err > 0.) temp = 1.2 * ln_root_n(err / rtol, k + 1.0);
+      double hopt = (temp > 0.1) ? absh / temp : 10 * absh;
+      int kopt = k;
+      if (k > 1) {
+        e_km1 *= c_erconst[k - 2];
+        temp = 0.;
+        if (e_km1 > 0.) temp = 1.3 * ln_root_n(e_km1 / rtol, (double)k);
+        const double hkm1 = (temp > 0.1) ? absh / temp : 10 * absh;
+        if (hkm1 > hopt) { hopt = hkm1; kopt = k - 1; }
+      }
+      if (k < maxk) {
+        e_kp1 *= c_erconst[k];
+        temp = 0.;
+        if (e_kp1 > 0.) temp = 1.4 * ln_root_n(e_kp1 / rtol, k + 2.0);
+        const double hkp1 = (temp > 0.1) ? absh / temp : 10 * absh;
+        if (hkp1 > hopt) { hopt = hkp1; kopt = k + 1; }
+      }
+      if (hopt > absh) {
+        absh = hopt;
+        if (k != kopt) k = kopt;
+      }
+    }
+    t = tnew;
+#pragma unroll
+    for (int i = 0; i < N; i++) y[i] = pred[i] + dk1[i];
+    Jcurrent = false;
+    new_step = true;
+  }
+  {
+    double* Ys = LVP(LV_Y);
+#pragma unroll
+    for (int i = 0; i < N; i++) Ys[i] = pred[i] + dk1[i];
+  }
+  M.st.fevals++;  // the reference's final RHS call (nothing follows the last interval)
+  M.next = next;
+  return true;
+}
+
+// dispatch on the number of ncdm species; false: not a tail interval (generic integrator)
+LN_FN bool ln_is_tail(const PtParams& P, const Approx& ap) {
+  return ap.rsa_on && (!P.has_ncdm || ap.ncdmfa_on) && P.N_ncdm <= PT_MAX_NCDM && P.rsa_method != CLPP_RSA_NONE;
+}
+LN_FN bool ln_run_tail(const PtParams& P, Lane& M, double* __restrict__ mem, double t0, double tfinal) {
+  switch (P.has_ncdm ? P.N_ncdm : 0) {
+    case 0: return ln_ndf15_tail<0>(P, M, mem, t0, tfinal);
+    case 1: return ln_ndf15_tail<1>(P, M, mem, t0, tfinal);
+    case 2: return ln_ndf15_tail<2>(P, M, mem, t0, tfinal);
+    default: return ln_ndf15_tail<3>(P, M, mem, t0, tfinal);
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // perturb_initial_conditions: adiabatic mode, synchronous gauge, flat space
 LN_NOINLINE void ln_initial_conditions(const PtParams& P, Lane& M, double* __restrict__ mem, double tau) {
@@ -1500,7 +2080,8 @@ LN_FN void ln_mode(const PtParams& P, double* __restrict__ mem, const PtCosmo* C
     M.need_nw = P.has_ncdm && !apn.ncdmfa_on;
     const long long c0 = LN_CLOCK();
     const int s0 = M.st.steps;
-    const bool ok = ln_ndf15(P, M, mem, limit[iv], limit[iv + 1]);
+    const bool ok = (!P.force_generic && ln_is_tail(P, apn)) ? ln_run_tail(P, M, mem, limit[iv], limit[iv + 1])
+                                                             : ln_ndf15(P, M, mem, limit[iv], limit[iv + 1]);
     ks->iv_neq[iv] = M.L.neq;
     ks->iv_steps[iv] = M.st.steps - s0;
     ks->iv_cycles[iv] = LN_CLOCK() - c0;

@@ -3151,7 +3151,7 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     if (clpp_dev_reserve(d0, &d0->i2l1, (size_t)P.n_i2l1, err)) return CLPP_FAILURE;
     CLPP_CUDA(cudaMemcpyAsync(d0->i2l1, i2l1.data(), P.n_i2l1 * sizeof(double), cudaMemcpyHostToDevice, st), err);
     const int n_cta = (n_modes + LN_CTA - 1) / LN_CTA;
-    static const int slab_sizes[] = {1536, 2816, 4608, 9216, 14336};
+    static const int slab_sizes[] = {1536, 4608, 14336};
     int slab = 0;
     for (int w : slab_sizes)
       if (slab == 0 && P.ln_words <= w) slab = w;
@@ -3168,9 +3168,7 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     if (n_modes > 0) {
       switch (slab) {
         case 1536: perturb_lane_kernel<1536><<<n_cta, LN_CTA, 0, st>>>(P); break;
-        case 2816: perturb_lane_kernel<2816><<<n_cta, LN_CTA, 0, st>>>(P); break;
         case 4608: perturb_lane_kernel<4608><<<n_cta, LN_CTA, 0, st>>>(P); break;
-        case 9216: perturb_lane_kernel<9216><<<n_cta, LN_CTA, 0, st>>>(P); break;
         case 14336: perturb_lane_kernel<14336><<<n_cta, LN_CTA, 0, st>>>(P); break;
         default: perturb_lane_kernel<0><<<n_cta, LN_CTA, 0, st>>>(P); break;
       }
