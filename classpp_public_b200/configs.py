@@ -51,6 +51,9 @@ LCDM_COARSE = dict(LCDM, **{
 # fallbacks of the device path (generic NDF, shared-memory Gauss-Jordan, 18 chains)
 NCDM3_COARSE = dict(LCDM_COARSE, **{"N_ur": 0.00641, "N_ncdm": 3, "m_ncdm": "0.02,0.02,0.02"})
 
+# config 4 as written in BASELINE.json: three separate species on the default grids (neq up to 316)
+NCDM3 = dict(LCDM, **{"N_ur": 0.00641, "N_ncdm": 3, "m_ncdm": "0.02,0.02,0.02"})
+
 # config 3 stand-in (cl_permille.pre is not in the reference tree): denser k sampling, larger photon / ur
 # hierarchies, tighter integration tolerance, finer time sampling and l grid
 LCDM_DENSE = dict(LCDM, **{
@@ -74,4 +77,5 @@ CONFIGS = {
     "lcdm_coarse": LCDM_COARSE,
     "lcdm_dense": LCDM_DENSE,
     "ncdm3_coarse": NCDM3_COARSE,
+    "ncdm3": NCDM3,
 }

@@ -345,8 +345,11 @@ LN_FN void ln_chain(const LnLayout& L, int c, int& start, int& len, int& root) {
 // -------------------------------------------------------------------------------------------------
 // Right-hand side f(tau, y) for the environment in M.e.  Fills M.m (metric and by-products).
 //  LR_MATTER: also delta_m, delta_cb.  LR_HUB / LR_CHAINS: which rows of dy to write (none: metric only).
+//  LR_GIVEN_METRIC: the metric scalars (h', eta', alpha', eta) are imposed through ms_in[] instead of being computed
+//  from y: the hub block of the Jacobian is D + U V with V = d(metric)/dy, U = d(rows)/d(metric) and D = d(rows)/dy at
+//  fixed metric, which is block diagonal (ln_jacobian_s).
 LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, const double* __restrict__ y, double* __restrict__ dy,
-                        const double* __restrict__ nw, int flags) {
+                        const double* __restrict__ nw, int flags, const double* ms_in = nullptr) {
   const LnLayout& L = M.L;
   const Approx ap = M.ap;
   const LnEnv& e = M.e;
@@ -372,7 +375,9 @@ LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, const double* __restrict__ y
     delta_ur = y[L.delta_ur]; theta_ur = y[L.theta_ur]; shear_ur = y[L.shear_ur];
     if (!ap.ufa_on) u3 = y[L.c_ur];
   }
-  const double delta_b = y[L.delta_b], theta_b = y[L.theta_b], delta_cdm = y[L.delta_cdm], eta = y[L.eta];
+  const double delta_b = y[L.delta_b], theta_b = y[L.theta_b], delta_cdm = y[L.delta_cdm];
+  const bool given = (flags & LR_GIVEN_METRIC) != 0;
+  const double eta = given ? ms_in[MS_ETA] : y[L.eta];
   const double delta_p_b_over_rho_b = cb2 * delta_b;
 
   // ---- perturb_total_stress_energy
@@ -426,7 +431,7 @@ LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, const double* __restrict__ y
   if (flags & LR_MATTER) m.delta_m = delta_rho_m / rho_m + 3. * aH * (rpt_m / rpm) * ik2;
 
   // ---- perturb_einstein (synchronous gauge, K = 0)
-  const double h_prime = (k2 * eta + 1.5 * a2 * delta_rho) * e.inv_half_aH;
+  const double h_prime = given ? ms_in[MS_HP] : (k2 * eta + 1.5 * a2 * delta_rho) * e.inv_half_aH;
   double rsa_delta_g = 0., rsa_theta_g = 0.;
   if (ap.rsa_on) {
     double rsa_delta_ur = 0., rsa_theta_ur = 0.;
@@ -450,13 +455,13 @@ LN_NOINLINE void ln_rhs(const PtParams& P, Lane& M, const double* __restrict__ y
       rpt += 4. / 3. * rho_ur * rsa_theta_ur;
     }
   }
-  const double eta_prime = (1.5 * a2 * rpt) * ik2;
+  const double eta_prime = given ? ms_in[MS_EP] : (1.5 * a2 * rpt) * ik2;
   const double alpha = (h_prime + 6. * eta_prime) * 0.5 * ik2;
   if (!ap.tca_off) {
     const double sg = 16. / 45. * e.tau_c * (theta_g + k2 * alpha);
     rps += 4. / 3. * rho_g * sg;
   }
-  const double alpha_prime = -2. * aH * alpha + eta - 4.5 * (a2 * ik2) * rps;
+  const double alpha_prime = given ? ms_in[MS_AP] : -2. * aH * alpha + eta - 4.5 * (a2 * ik2) * rps;
   m.h_prime = h_prime; m.eta_prime = eta_prime; m.alpha = alpha; m.alpha_prime = alpha_prime;
   m.rsa_delta_g = rsa_delta_g; m.rsa_theta_g = rsa_theta_g;
   if (!(flags & (LR_HUB | LR_CHAINS))) return;
@@ -667,10 +672,9 @@ LN_FN void ln_chain_rows(double* __restrict__ jd, double* __restrict__ jl, doubl
   jd[p] = last_diag - damp;
 }
 
-LN_NOINLINE void ln_jacobian(const PtParams& P, Lane& M, double* __restrict__ mem) {
+LN_FN void ln_jacobian_chains(const PtParams& P, Lane& M, double* __restrict__ mem) {
   const LnLayout& L = M.L;
   const LnEnv& e = M.e;
-  const int n = L.neq, nh = L.nh;
   const double k = M.k;
   const double cotKgen = e.inv_tau * M.ik;
   const double* __restrict__ i2l1 = P.i2l1;
@@ -697,6 +701,13 @@ LN_NOINLINE void ln_jacobian(const PtParams& P, Lane& M, double* __restrict__ me
       LCH_JUR(c) = -0.6 * qk; c++;
     }
   }
+}
+
+LN_NOINLINE void ln_jacobian(const PtParams& P, Lane& M, double* __restrict__ mem) {
+  const LnLayout& L = M.L;
+  const int n = L.neq, nh = L.nh;
+  const double* nw = mem + P.lo_nw;
+  ln_jacobian_chains(P, M, mem);
   // ---- hub block by probing (hub rows only; the chain parts of the probe vector stay zero)
   double* __restrict__ ej = LVP(LV_TMP);
   double* __restrict__ col = LVP(LV_DEL);
@@ -843,6 +854,329 @@ LN_NOINLINE void ln_solve(const PtParams& P, Lane& M, double* __restrict__ mem, 
     }
   }
   M.st.solves++;
+}
+
+// -------------------------------------------------------------------------------------------------
+// STRUCTURED hub solve.  With the metric scalars s = (h', eta', alpha', eta) held fixed, a hub row only depends on the
+// variables of its own physical block (photon-baryon plasma; cdm; ur; each ncdm momentum bin / fluid; eta), so the hub
+// block of the Jacobian is  J_hh = D + U V,  D block diagonal (blocks of <= 8), U = d(rows)/ds (nh x 4), V = ds/dy (4 x nh).
+// The Newton matrix  A = (I - cD + Schur terms of the chains) - c U V  is solved by block LU + a 4x4 capacitance matrix
+// (Sherman-Morrison-Woodbury):  x = w + Z t,  w = B^-1 b,  Z = B^-1 U,  (I - c V Z) t = c V w.
+// A refactorisation costs O(nh) instead of O(nh^3/3), a solve O(nh) instead of O(nh^2) -- what keeps one refactorisation
+// per step attempt (some lane of a warp changes its step size at almost every attempt) affordable.
+// Slab layout (doubles from lo_jhh): DB[nh][8] | Uc[4][nh] | V[4][nh] | Zc[4][nh] | BL[nh][8] | bpiv[nh] | Minv[16] | active[4]
+#define LN_SB 8
+LN_FN void ln_block(const LnLayout& L, int i, int& b0, int& bs) {
+  if (i < L.delta_cdm) { b0 = 0; bs = L.delta_cdm; }
+  else if (i == L.delta_cdm) { b0 = i; bs = 1; }
+  else if (L.delta_ur >= 0 && i <= L.shear_ur) { b0 = L.delta_ur; bs = 3; }
+  else if (i < L.eta) { b0 = L.psi0_ncdm1 + 3 * ((i - L.psi0_ncdm1) / 3); bs = 3; }
+  else { b0 = i; bs = 1; }
+}
+#define LS_DB(P) (mem + (P).lo_jhh)
+#define LS_UC(P, nh) (LS_DB(P) + LN_SB * (nh))
+#define LS_V(P, nh) (LS_UC(P, nh) + 4 * (nh))
+#define LS_ZC(P, nh) (LS_V(P, nh) + 4 * (nh))
+#define LS_BL(P, nh) (LS_ZC(P, nh) + 4 * (nh))
+#define LS_BP(P, nh) (LS_BL(P, nh) + LN_SB * (nh))
+#define LS_MI(P, nh) (LS_BP(P, nh) + (nh))
+#define LS_ACT(P, nh) (LS_MI(P, nh) + 16)
+
+LN_NOINLINE void ln_jacobian_s(const PtParams& P, Lane& M, double* __restrict__ mem) {
+  const LnLayout& L = M.L;
+  const int n = L.neq, nh = L.nh;
+  const double* nw = mem + P.lo_nw;
+  ln_jacobian_chains(P, M, mem);
+  double* __restrict__ ej = LVP(LV_TMP);
+  double* __restrict__ col = LVP(LV_DEL);
+  double* __restrict__ DB = LS_DB(P);
+  double* __restrict__ Uc = LS_UC(P, nh);
+  double* __restrict__ V = LS_V(P, nh);
+  double* __restrict__ act = LS_ACT(P, nh);
+  double ms[MS_COUNT] = {0., 0., 0., 0.};
+  LN_UNROLL
+  for (int i = 0; i < n; i++) ej[i] = 0.;
+  // D: one probe per position inside the blocks (all blocks at once: they do not see each other at fixed metric)
+  const int bs_max = L.delta_cdm > 3 ? L.delta_cdm : 3;
+  for (int g = 0; g < LN_SB; g++) {
+    if (g < bs_max) {
+      for (int i = 0; i < nh; i++) {
+        int b0, bs;
+        ln_block(L, i, b0, bs);
+        ej[i] = (i - b0 == g) ? 1. : 0.;
+      }
+      ln_rhs(P, M, ej, col, nw, LR_HUB | LR_GIVEN_METRIC, ms);
+      for (int i = 0; i < nh; i++) {
+        int b0, bs;
+        ln_block(L, i, b0, bs);
+        DB[i * LN_SB + g] = (g < bs) ? col[i] : 0.;
+      }
+    } else {
+      for (int i = 0; i < nh; i++) DB[i * LN_SB + g] = 0.;
+    }
+  }
+  for (int i = 0; i < nh; i++) ej[i] = 0.;
+  // U: response of the rows to each metric scalar
+  for (int mm = 0; mm < MS_COUNT; mm++) {
+    ms[mm] = 1.;
+    ln_rhs(P, M, ej, col, nw, LR_HUB | LR_GIVEN_METRIC, ms);
+    ms[mm] = 0.;
+    double any = 0.;
+    for (int i = 0; i < nh; i++) { Uc[mm * nh + i] = col[i]; any = fmax(any, fabs(col[i])); }
+    act[mm] = any > 0. ? 1. : 0.;
+  }
+  // V: the metric scalars as functionals of the hub variables
+  for (int j = 0; j < nh; j++) {
+    ej[j] = 1.;
+    ln_rhs(P, M, ej, nullptr, nw, 0);
+    ej[j] = 0.;
+    V[0 * nh + j] = M.m.h_prime; V[1 * nh + j] = M.m.eta_prime; V[2 * nh + j] = M.m.alpha_prime;
+    V[3 * nh + j] = (j == L.eta) ? 1. : 0.;
+  }
+  M.st.jacobians++;
+  M.st.fevals += bs_max + MS_COUNT;  // (the nh metric probes are ~1/10 of an RHS each)
+}
+
+// in-place LU with partial pivoting of one diagonal block (rows r0..r0+bs-1 of BL, LN_SB columns each)
+LN_FN void ln_block_lu(double* __restrict__ BL, double* __restrict__ bpiv, int r0, int bs) {
+  for (int j = 0; j < bs; j++) {
+    double best = fabs(BL[(r0 + j) * LN_SB + j]);
+    int bi = j;
+    for (int i = j + 1; i < bs; i++) {
+      const double v = fabs(BL[(r0 + i) * LN_SB + j]);
+      if (v > best) { best = v; bi = i; }
+    }
+    bpiv[r0 + j] = (double)bi;
+    if (bi != j) {
+      for (int cc = 0; cc < bs; cc++) {
+        const double t = BL[(r0 + j) * LN_SB + cc];
+        BL[(r0 + j) * LN_SB + cc] = BL[(r0 + bi) * LN_SB + cc];
+        BL[(r0 + bi) * LN_SB + cc] = t;
+      }
+    }
+    double pv = BL[(r0 + j) * LN_SB + j];
+    if (pv == 0.) pv = 1e-50;
+    const double pinv = 1.0 / pv;
+    BL[(r0 + j) * LN_SB + j] = pinv;
+    for (int i = j + 1; i < bs; i++) {
+      const double f = BL[(r0 + i) * LN_SB + j] * pinv;
+      BL[(r0 + i) * LN_SB + j] = f;
+      for (int cc = j + 1; cc < bs; cc++) BL[(r0 + i) * LN_SB + cc] -= f * BL[(r0 + j) * LN_SB + cc];
+    }
+  }
+}
+// x <- B^-1 x for the block-diagonal B factorised by ln_block_lu
+LN_FN void ln_blocks_solve(const LnLayout& L, const double* __restrict__ BL, const double* __restrict__ bpiv, double* __restrict__ x) {
+  const int nh = L.nh;
+  int r0 = 0;
+  while (r0 < nh) {
+    int b0, bs;
+    ln_block(L, r0, b0, bs);
+    if (bs == 1) {
+      x[r0] *= BL[r0 * LN_SB];
+    } else {
+      for (int j = 0; j < bs; j++) {
+        const int p = (int)bpiv[r0 + j];
+        if (p != j) { const double t = x[r0 + j]; x[r0 + j] = x[r0 + p]; x[r0 + p] = t; }
+      }
+      for (int i = 1; i < bs; i++) {
+        double s = x[r0 + i];
+        for (int j = 0; j < i; j++) s -= BL[(r0 + i) * LN_SB + j] * x[r0 + j];
+        x[r0 + i] = s;
+      }
+      for (int i = bs - 1; i >= 0; i--) {
+        double s = x[r0 + i];
+        for (int j = i + 1; j < bs; j++) s -= BL[(r0 + i) * LN_SB + j] * x[r0 + j];
+        x[r0 + i] = s * BL[(r0 + i) * LN_SB + i];
+      }
+    }
+    r0 += bs;
+  }
+}
+
+LN_NOINLINE void ln_factor_s(const PtParams& P, Lane& M, double* __restrict__ mem, double c) {
+  const LnLayout& L = M.L;
+  const int nh = L.nh, nch = L.nch;
+  M.fac_c = c;
+  const double* __restrict__ DB = LS_DB(P);
+  const double* __restrict__ Uc = LS_UC(P, nh);
+  const double* __restrict__ V = LS_V(P, nh);
+  double* __restrict__ Zc = LS_ZC(P, nh);
+  double* __restrict__ BL = LS_BL(P, nh);
+  double* __restrict__ bpiv = LS_BP(P, nh);
+  double* __restrict__ Mi = LS_MI(P, nh);
+  const double* __restrict__ act = LS_ACT(P, nh);
+  for (int i = 0; i < nh; i++) {
+    int b0, bs;
+    ln_block(L, i, b0, bs);
+#pragma unroll
+    for (int cc = 0; cc < LN_SB; cc++) BL[i * LN_SB + cc] = ((b0 + cc == i) ? 1.0 : 0.0) - c * DB[i * LN_SB + cc];
+  }
+  for (int ch = 0; ch < nch; ch++) {
+    int s, len, root;
+    ln_chain(L, ch, s, len, root);
+    double mur;
+    const double schur = ln_chain_factor(LVP(LV_JD) + s, LVP(LV_JL) + s, LVP(LV_JU) + s, LVP(LV_IP) + s, LVP(LV_MU) + s, len, c,
+                                         LCH_JUR(ch), mur);
+    LCH_MUR(ch) = mur;
+    int b0, bs;
+    ln_block(L, root, b0, bs);
+    BL[root * LN_SB + (root - b0)] += schur;
+  }
+  {
+    int r0 = 0;
+    while (r0 < nh) {
+      int b0, bs;
+      ln_block(L, r0, b0, bs);
+      if (bs == 1) BL[r0 * LN_SB] = 1.0 / BL[r0 * LN_SB];
+      else ln_block_lu(BL, bpiv, r0, bs);
+      r0 += bs;
+    }
+  }
+  // Z = B^-1 U and the capacitance matrix G = I - c V Z (inactive metric scalars: identity rows/columns)
+  double G[MS_COUNT][MS_COUNT];
+  for (int mm = 0; mm < MS_COUNT; mm++) {
+    if (act[mm] != 0.) {
+      double* __restrict__ z = Zc + mm * nh;
+      const double* __restrict__ u = Uc + mm * nh;
+      for (int i = 0; i < nh; i++) z[i] = u[i];
+      ln_blocks_solve(L, BL, bpiv, z);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < MS_COUNT; a++)
+#pragma unroll
+    for (int b = 0; b < MS_COUNT; b++) {
+      double sum = 0.;
+      if (act[a] != 0. && act[b] != 0.) {
+        const double* __restrict__ v = V + a * nh;
+        const double* __restrict__ z = Zc + b * nh;
+        LN_UNROLL
+        for (int j = 0; j < nh; j++) sum += v[j] * z[j];
+      }
+      G[a][b] = (a == b ? 1.0 : 0.0) - c * sum;
+    }
+  // invert G (Gauss-Jordan, partial pivoting; 4 x 4 in registers)
+  double Inv[MS_COUNT][MS_COUNT];
+#pragma unroll
+  for (int a = 0; a < MS_COUNT; a++)
+#pragma unroll
+    for (int b = 0; b < MS_COUNT; b++) Inv[a][b] = (a == b) ? 1. : 0.;
+#pragma unroll
+  for (int j = 0; j < MS_COUNT; j++) {
+    int p = j;
+    double best = fabs(G[j][j]);
+#pragma unroll
+    for (int i = 0; i < MS_COUNT; i++)
+      if (i > j && fabs(G[i][j]) > best) { best = fabs(G[i][j]); p = i; }
+#pragma unroll
+    for (int i = 0; i < MS_COUNT; i++) {
+      if (i > j && i == p) {
+#pragma unroll
+        for (int b = 0; b < MS_COUNT; b++) {
+          double t = G[j][b]; G[j][b] = G[i][b]; G[i][b] = t;
+          t = Inv[j][b]; Inv[j][b] = Inv[i][b]; Inv[i][b] = t;
+        }
+      }
+    }
+    double pv = G[j][j];
+    if (pv == 0.) pv = 1e-50;
+    const double pinv = 1.0 / pv;
+#pragma unroll
+    for (int b = 0; b < MS_COUNT; b++) { G[j][b] *= pinv; Inv[j][b] *= pinv; }
+#pragma unroll
+    for (int i = 0; i < MS_COUNT; i++) {
+      if (i != j) {
+        const double f = G[i][j];
+#pragma unroll
+        for (int b = 0; b < MS_COUNT; b++) { G[i][b] -= f * G[j][b]; Inv[i][b] -= f * Inv[j][b]; }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < MS_COUNT; a++)
+#pragma unroll
+    for (int b = 0; b < MS_COUNT; b++) Mi[a * MS_COUNT + b] = Inv[a][b];
+  M.st.factorizations++;
+}
+
+LN_NOINLINE void ln_solve_s(const PtParams& P, Lane& M, double* __restrict__ mem, double* __restrict__ b) {
+  const LnLayout& L = M.L;
+  const int nh = L.nh, nch = L.nch;
+  const double c = M.fac_c;
+  const double* __restrict__ V = LS_V(P, nh);
+  const double* __restrict__ Zc = LS_ZC(P, nh);
+  const double* __restrict__ BL = LS_BL(P, nh);
+  const double* __restrict__ bpiv = LS_BP(P, nh);
+  const double* __restrict__ Mi = LS_MI(P, nh);
+  const double* __restrict__ act = LS_ACT(P, nh);
+  const double* __restrict__ mu = LVP(LV_MU);
+  const double* __restrict__ ip = LVP(LV_IP);
+  const double* __restrict__ jl = LVP(LV_JL);
+  for (int ch = 0; ch < nch; ch++) {
+    int s, len, root;
+    ln_chain(L, ch, s, len, root);
+    const int last = s + len - 1;
+    double r = b[last];
+    LN_UNROLL
+    for (int i = last - 1; i >= s; i--) {
+      r = b[i] - mu[i] * r;
+      b[i] = r;
+    }
+    b[root] -= LCH_MUR(ch) * r;
+  }
+  ln_blocks_solve(L, BL, bpiv, b);
+  double g[MS_COUNT], t[MS_COUNT];
+#pragma unroll
+  for (int mm = 0; mm < MS_COUNT; mm++) {
+    double sum = 0.;
+    if (act[mm] != 0.) {
+      const double* __restrict__ v = V + mm * nh;
+      LN_UNROLL
+      for (int j = 0; j < nh; j++) sum += v[j] * b[j];
+    }
+    g[mm] = c * sum;
+  }
+#pragma unroll
+  for (int a = 0; a < MS_COUNT; a++) {
+    double sum = 0.;
+#pragma unroll
+    for (int bb = 0; bb < MS_COUNT; bb++) sum += Mi[a * MS_COUNT + bb] * g[bb];
+    t[a] = sum;
+  }
+#pragma unroll
+  for (int mm = 0; mm < MS_COUNT; mm++) {
+    if (act[mm] != 0.) {
+      const double* __restrict__ z = Zc + mm * nh;
+      const double tm = t[mm];
+      LN_UNROLL
+      for (int j = 0; j < nh; j++) b[j] += z[j] * tm;
+    }
+  }
+  for (int ch = 0; ch < nch; ch++) {
+    int s, len, root;
+    ln_chain(L, ch, s, len, root);
+    const int last = s + len - 1;
+    double xp = b[root];
+    LN_UNROLL
+    for (int i = s; i <= last; i++) {
+      const double lo = -c * jl[i];
+      xp = (b[i] - lo * xp) * ip[i];
+      b[i] = xp;
+    }
+  }
+  M.st.solves++;
+}
+
+// dense or structured hub algebra (P.ln_structured; the dense path remains as the cross-check)
+LN_FN void ln_do_jacobian(const PtParams& P, Lane& M, double* __restrict__ mem) {
+  if (P.ln_structured) ln_jacobian_s(P, M, mem); else ln_jacobian(P, M, mem);
+}
+LN_FN void ln_do_factor(const PtParams& P, Lane& M, double* __restrict__ mem, double c) {
+  if (P.ln_structured) ln_factor_s(P, M, mem, c); else ln_factor(P, M, mem, c);
+}
+LN_FN void ln_do_solve(const PtParams& P, Lane& M, double* __restrict__ mem, double* __restrict__ b) {
+  if (P.ln_structured) ln_solve_s(P, M, mem, b); else ln_solve(P, M, mem, b);
 }
 
 // rescale the backward differences when the step changes by the factor r (kord = current order)
@@ -1033,7 +1367,7 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
   ln_rhs(P, M, Y, F, NW, LR_HUB | LR_CHAINS);
   M.st.fevals++;
   const double hmax = (tfinal - t0) / 10.0;
-  ln_jacobian(P, M, mem);
+  ln_do_jacobian(P, M, mem);
   bool Jcurrent = true;
   double hmin = 16.0 * eps * fabs(t);
   double rh = 0.0;
@@ -1068,7 +1402,7 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
   for (int i = 0; i < n; i++) DIF[i] = h * F[i];
   double hinvGak = h * c_invGa[k - 1];
   int nconhk = 0;
-  ln_factor(P, M, mem, hinvGak);
+  ln_do_factor(P, M, mem, hinvGak);
   bool havrate = false, done = false, at_hmin = false, new_step = true, nofailed = true;
   double rate = 0., oldnrm = 0., err = 0.;
 
@@ -1092,7 +1426,7 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
         ln_adjust_stepsize(P, M, mem, absh / abshlast, k);
         hinvGak = h * c_invGa[k - 1];
         nconhk = 0;
-        ln_factor(P, M, mem, hinvGak);
+        ln_do_factor(P, M, mem, hinvGak);
         havrate = false;
       }
       nofailed = true;
@@ -1110,7 +1444,7 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
       if (!M.ap.tca_off) M.tca_shear_last = M.m.tca_shear_g;
       M.st.fevals++;
       ln_residual(DEL, F, PSI, DIFKP1, hinvGak, n);
-      ln_solve(P, M, mem, DEL);
+      ln_do_solve(P, M, mem, DEL);
       const double newnrm = ln_newton_update(DEL, INVWT, PRED, DIFKP1, YNEW, n);
       if (newnrm <= minnrm) { gotynew = true; break; }
       else if (iter == 1) {
@@ -1141,7 +1475,7 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
       if (!Jcurrent) {
         ln_env(P, M, mem, t, 0);
         M.st.fevals++;  // the reference re-evaluates f(t, y) for numjac; the probes below need the environment only
-        ln_jacobian(P, M, mem);
+        ln_do_jacobian(P, M, mem);
         Jcurrent = true;
       } else if (absh <= hmin) {
         M.status = 2;  // step size too small
@@ -1155,7 +1489,7 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
         hinvGak = h * c_invGa[k - 1];
         nconhk = 0;
       }
-      ln_factor(P, M, mem, hinvGak);
+      ln_do_factor(P, M, mem, hinvGak);
       havrate = false;
       continue;
     }
@@ -1188,7 +1522,7 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
       ln_adjust_stepsize(P, M, mem, absh / abshlast, k);
       hinvGak = h * c_invGa[k - 1];
       nconhk = 0;
-      ln_factor(P, M, mem, hinvGak);
+      ln_do_factor(P, M, mem, hinvGak);
       havrate = false;
       continue;
     }

@@ -3045,7 +3045,9 @@ static void set_geometry(PtParams& P, int neq_max, int nh_max, const clpp_pertur
   P.lo_jhh = P.lo_nw + 4 * P.nq_tot;
   P.lo_lu = P.lo_jhh + P.nh_max * P.nh_max;
   P.lo_piv = P.lo_lu + P.nh_max * P.nh_max;
-  P.lo_ch = P.lo_piv + P.nh_max;
+  // hub region: dense (J, LU, pivots) or structured (ln_jacobian_s: 29 nh + 20 doubles), whichever is larger
+  P.lo_ch = P.lo_jhh + std::max(2 * P.nh_max * P.nh_max + P.nh_max, 29 * P.nh_max + 20);
+  P.ln_structured = getenv("CLPP_LANE_DENSE") ? 0 : 1;
   P.ln_words = P.lo_ch + 2 * PT_MAX_CHAINS;
 }
 

@@ -289,6 +289,20 @@ long rp_get(void* h, const char* cname, double* out, long cap) {
     }
     return put(pk.data(), m.k_size_[md], out, cap);
   }
+  if (name == "nl.pk_nl_m_at_pt_k") {  // non-linear P_m(k, z=0) on the perturbation k grid (nonlinear_pk_at_z, pk_nonlinear)
+    const NonlinearModule& n = *c.GetNonlinearModule();
+    const PerturbationsModule& m = *c.GetPerturbationsModule();
+    const int nk = m.k_size_[m.index_md_scalars_];
+    if (!n.has_pk_m_ || nl.method == nl_none) return 0;
+    std::vector<double> pk(n.k_size_);
+    if (n.nonlinear_pk_at_z(linear, pk_nonlinear, 0., n.index_pk_m_, pk.data(), nullptr) != 0) return -1;
+    return put(pk.data(), nk, out, cap);
+  }
+  if (name == "nl.sigma8_m") {
+    const NonlinearModule& n = *c.GetNonlinearModule();
+    if (!n.has_pk_m_) return 0;
+    return put1(n.sigma8_[n.index_pk_m_], out, cap);
+  }
   if (name == "nl.pk_lin_m_at_pt_k" || name == "nl.pk_lin_cb_at_pt_k") {
     const NonlinearModule& n = *c.GetNonlinearModule();
     const PerturbationsModule& m = *c.GetPerturbationsModule();

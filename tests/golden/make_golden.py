@@ -55,6 +55,27 @@ def make(name, n_k_cols=9, n_l_rows=8):
     print(name, "->", out, "%.2f MB" % (os.path.getsize(out) / 1e6))
 
 
+def make_pk(names):
+    """Matter power spectra of the reference on the perturbation k grid at z = 0 (small, one file for all configs):
+    primordial P_R(k_i), linear P_m / P_cb, non-linear (halofit) P_m, sigma8."""
+    out = {}
+    for name in names:
+        ref = RefCosmology(CONFIGS[name], threads=os.cpu_count()).compute("nonlinear")
+        out[name + "__pm.pk_at_pt_k"] = ref.get("pm.pk_at_pt_k")
+        for key in ("nl.pk_lin_m_at_pt_k", "nl.pk_lin_cb_at_pt_k", "nl.pk_nl_m_at_pt_k", "nl.sigma8_m"):
+            v = ref.get(key)
+            if v is not None and len(v):
+                out[name + "__" + key] = v
+        ref.close()
+    path = os.path.join(HERE, "pk_z0.npz")
+    np.savez_compressed(path, **out)
+    print("pk ->", path, "%.2f MB" % (os.path.getsize(path) / 1e6))
+
+
 if __name__ == "__main__":
-    for name in (sys.argv[1:] or ["lcdm_coarse", "lcdm", "planck18"]):
-        make(name)
+    args = sys.argv[1:]
+    if args and args[0] == "pk":
+        make_pk(args[1:] or ["lcdm_coarse", "lcdm", "planck18", "ncdm3_deg", "lcdm_dense"])
+    else:
+        for name in (args or ["lcdm_coarse", "lcdm", "planck18"]):
+            make(name)

@@ -32,7 +32,8 @@ extern "C" int hostsim_solve(void* ctx, const int* k_list, int n, double* source
   Q.n_e = c->th.n_e; Q.YHe = c->th.YHe; Q.T_cmb = c->bg.T_cmb; Q.tau_free_streaming = c->th.tau_free_streaming;
   Q.a_today = c->bg.a_today;
   for (int s = 0; s < P.N_ncdm; s++) { Q.ncdm_M[s] = c->ncdm_M[s]; Q.ncdm_factor[s] = c->ncdm_factor[s]; }
-  std::vector<double> mem((size_t)P.ln_words);
+  if (getenv("HOSTSIM_DENSE")) P.ln_structured = 0; else if (getenv("HOSTSIM_STRUCTURED")) P.ln_structured = 1;
+  std::vector<double> mem((size_t)P.ln_words + 4096);
   if (getenv("HOSTSIM_VERBOSE"))
     fprintf(stderr, "[hostsim] neq_max %d nh_max %d words %d\n", P.neq_max, P.nh_max, P.ln_words);
   for (int i = 0; i < n; i++) {
