@@ -1299,22 +1299,33 @@ LN_FN double ln_wnorm2(const double* __restrict__ v, const double* __restrict__ 
   return e;
 }
 
-// dif[k+1] = dk - dif[k]; dif[k] = dk; dif[j] += dif[j+1] (j < k); also the norms of the new dif[k-1] and dif[k+1]
+// dif[k+1] = dk - dif[k]; dif[k] = dk; dif[j] += dif[j+1] (j < k); also the norms of the new dif[k-1] and dif[k+1].
+// The column of differences of element i is loaded into registers first: a load-add-store recurrence through memory
+// (stores to dif[] may alias the next load as far as the compiler knows) costs one memory round trip per order.
 LN_FN void ln_dif_update(double* __restrict__ dif, int np, int k, int n, const double* __restrict__ difkp1,
                          const double* __restrict__ invwt, double& e_km1, double& e_kp1) {
   double a = 0., b = 0.;
-  LN_UNROLL
+#pragma unroll 2
   for (int i = 0; i < n; i++) {
     const double dk = difkp1[i], iw = invwt[i];
-    const double dkp1 = dk - dif[k * np + i];
-    dif[(k + 1) * np + i] = dkp1;
+    double d[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) d[j] = (j <= k) ? dif[j * np + i] : 0.;
+    double dkold = d[0];
+#pragma unroll
+    for (int j = 1; j < 6; j++) dkold = (j == k) ? d[j] : dkold;
+    const double dkp1 = dk - dkold;
     double acc = dk;
-    dif[k * np + i] = acc;
-    for (int j = k - 1; j >= 0; j--) {
-      acc += dif[j * np + i];
-      dif[j * np + i] = acc;
-      if (j == k - 1) a = fmax(a, fabs(acc * iw));
+#pragma unroll
+    for (int j = 5; j >= 0; j--) {
+      if (j == k) d[j] = dk;
+      else if (j < k) { acc += d[j]; d[j] = acc; }
+      if (j == k - 1) a = fmax(a, fabs(d[j] * iw));
     }
+    dif[(k + 1) * np + i] = dkp1;
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+      if (j <= k) dif[j * np + i] = d[j];
     b = fmax(b, fabs(dkp1 * iw));
   }
   e_km1 = a; e_kp1 = b;
@@ -1580,13 +1591,14 @@ LN_NOINLINE bool ln_ndf15(const PtParams& P, Lane& M, double* __restrict__ mem, 
       }
     }
     t = tnew;
-    ln_copy(Y, YNEW, n);
+    { double* sw = Y; Y = YNEW; YNEW = sw; }  // y <- ynew without a pass over memory
     Jcurrent = false;
     new_step = true;
   }
-  // final state, and a last RHS call so that the environment and the TCA/RSA by-products are current at the end of
-  // the interval (evolver_ndf15.cpp:653-662)
-  ln_copy(Y, YNEW, n);
+  // final state (into the LV_Y slot, where the next interval expects it), and a last RHS call so that the environment
+  // and the TCA/RSA by-products are current at the end of the interval (evolver_ndf15.cpp:653-662)
+  if (YNEW != LVP(LV_Y)) ln_copy(LVP(LV_Y), YNEW, n);
+  Y = LVP(LV_Y);
   ln_env(P, M, mem, tnew, 0);
   ln_rhs(P, M, Y, F, NW, LR_HUB | LR_CHAINS);
   if (!M.ap.tca_off) M.tca_shear_last = M.m.tca_shear_g;
@@ -1724,6 +1736,52 @@ LN_FN void ln_rhs_tail(const PtParams& P, const LnTailEnv<NN>& E, double k2, dou
     dy[5 + 3 * s] = -nf[7] * y2 + nf[6] * (y1 + msn);
   }
 }
+
+// order-specialised pieces of the tail integrator (static register indices instead of select chains)
+template <int N, int K>
+LN_FN void ln_tail_predict(const double (&y)[N], const double (&dif)[7][N], double (&psi)[N], double (&pred)[N]) {
+  const double invGak = c_invGa[K - 1];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    double ps = 0., pr = y[i];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      ps += dif[j][i] * (c_G[j] * invGak);
+      pr += dif[j][i];
+    }
+    psi[i] = ps; pred[i] = pr;
+  }
+}
+template <int N, int K>
+LN_FN void ln_tail_accept(double (&dif)[7][N], const double (&dk1)[N], const double (&iw)[N], double& e_km1, double& e_kp1) {
+  double a = 0., b = 0.;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const double dkp1 = dk1[i] - dif[K][i];
+    dif[K + 1][i] = dkp1;
+    dif[K][i] = dk1[i];
+#pragma unroll
+    for (int j = K - 1; j >= 0; j--) dif[j][i] += dif[j + 1][i];
+    a = fmax(a, fabs(dif[K - 1][i] * iw[i]));
+    b = fmax(b, fabs(dkp1 * iw[i]));
+  }
+  e_km1 = a; e_kp1 = b;
+}
+template <int N, int K>
+LN_FN double ln_tail_errkm1(const double (&dif)[7][N], const double (&dk1)[N], const double (&iw)[N]) {
+  double e = 0.;
+#pragma unroll
+  for (int i = 0; i < N; i++) e = fmax(e, fabs((dif[K - 1][i] + dk1[i]) * iw[i]));
+  return e;
+}
+#define LN_TAIL_BY_ORDER(k, CALL)                      \
+  switch (k) {                                         \
+    case 1: { constexpr int K_ = 1; CALL; } break;     \
+    case 2: { constexpr int K_ = 2; CALL; } break;     \
+    case 3: { constexpr int K_ = 3; CALL; } break;     \
+    case 4: { constexpr int K_ = 4; CALL; } break;     \
+    default: { constexpr int K_ = 5; CALL; } break;    \
+  }
 
 template <int NN>
 LN_NOINLINE bool ln_ndf15_tail(const PtParams& P, Lane& M, double* __restrict__ mem, double t0, double tfinal) {
@@ -1943,22 +2001,12 @@ LN_NOINLINE bool ln_ndf15_tail(const PtParams& P, Lane& M, double* __restrict__ 
     if (done) tnew = tfinal;
     h = tnew - t;
     double minnrm = 0.0;
-    {
-      const double invGak = c_invGa[k - 1];
+    LN_TAIL_BY_ORDER(k, (ln_tail_predict<N, K_>(y, dif, psi, pred)));
 #pragma unroll
-      for (int i = 0; i < N; i++) {
-        double ps = 0., pr = y[i];
-#pragma unroll
-        for (int j = 0; j < 5; j++) {
-          if (j < k) {
-            ps += dif[j][i] * (c_G[j] * invGak);
-            pr += dif[j][i];
-          }
-        }
-        psi[i] = ps; pred[i] = pr; dk1[i] = 0.;
-        iw[i] = 1.0 / fmax(fmax(fabs(pr), fabs(y[i])), threshold);
-        minnrm = fmax(minnrm, 100 * eps * fabs(pr * iw[i]));
-      }
+    for (int i = 0; i < N; i++) {
+      dk1[i] = 0.;
+      iw[i] = 1.0 / fmax(fmax(fabs(pred[i]), fabs(y[i])), threshold);
+      minnrm = fmax(minnrm, 100 * eps * fabs(pred[i] * iw[i]));
     }
     ln_env_tail<NN>(P, M, tnew, E);
     bool gotynew = false;
@@ -2041,13 +2089,7 @@ LN_NOINLINE bool ln_ndf15_tail(const PtParams& P, Lane& M, double* __restrict__ 
         double hopt = absh * fmax(0.1, 0.833 * ln_root_n(rtol / err, k + 1.0));
         if (k > 1) {
           double errkm1 = 0.0;
-#pragma unroll
-          for (int i = 0; i < N; i++) {
-            double dkm = dif[0][i];
-#pragma unroll
-            for (int j = 1; j < 5; j++) dkm = (j == k - 1) ? dif[j][i] : dkm;
-            errkm1 = fmax(errkm1, fabs((dkm + dk1[i]) * iw[i]));
-          }
+          LN_TAIL_BY_ORDER(k, (errkm1 = ln_tail_errkm1<N, (K_ > 1 ? K_ : 2)>(dif, dk1, iw)));
           errkm1 *= c_erconst[k - 2];
           const double hkm1 = absh * fmax(0.1, 0.769 * ln_root_n(rtol / errkm1, (double)k));
           if (hkm1 > hopt) {
@@ -2071,21 +2113,7 @@ LN_NOINLINE bool ln_ndf15_tail(const PtParams& P, Lane& M, double* __restrict__ 
     // ---- step accepted: dif[k+1] = dk1 - dif[k]; dif[k] = dk1; dif[j] += dif[j+1] (j < k)
     M.st.steps++;
     double e_km1 = 0., e_kp1 = 0.;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-      double difk_old = dif[0][i];
-#pragma unroll
-      for (int j = 1; j < 7; j++) difk_old = (j == k) ? dif[j][i] : difk_old;
-      const double dkp1 = dk1[i] - difk_old;
-#pragma unroll
-      for (int j = 6; j >= 0; j--) {
-        if (j == k + 1) dif[j][i] = dkp1;
-        else if (j == k) dif[j][i] = dk1[i];
-        else if (j < k) dif[j][i] += dif[j + 1][i];
-        if (j == k - 1) e_km1 = fmax(e_km1, fabs(dif[j][i] * iw[i]));
-      }
-      e_kp1 = fmax(e_kp1, fabs(dkp1 * iw[i]));
-    }
+    LN_TAIL_BY_ORDER(k, (ln_tail_accept<N, K_>(dif, dk1, iw, e_km1, e_kp1)));
     // ---- output at the sample times passed by this step (through the generic source routine)
     while ((next < tres) && ((tnew - tnext) >= 0.0)) {
       double* yo = LVP(LV_TMP);

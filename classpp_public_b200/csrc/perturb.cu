@@ -2933,8 +2933,11 @@ __global__ void __launch_bounds__(32 * PT_TAIL_MAX_WPC, PT_TAIL_MIN_BLOCKS / PT_
 
 // W = doubles of per-thread state (compile-time size of the local-memory slab); W = 0: slab in global memory
 // (fallback for state vectors larger than the largest instantiation; correct but slow)
+#ifndef LN_MIN_CTAS
+#define LN_MIN_CTAS 1  // register budget of the lane kernel: 1 -> 255 registers per thread, 8 -> 128 (16 warps per SM)
+#endif
 template <int W>
-__global__ void __launch_bounds__(LN_CTA) perturb_lane_kernel(const __grid_constant__ PtParams P) {
+__global__ void __launch_bounds__(LN_CTA, LN_MIN_CTAS) perturb_lane_kernel(const __grid_constant__ PtParams P) {
   const int slot = blockIdx.x * LN_CTA + threadIdx.x;
   if (slot >= P.n_modes) return;
   const int2 md = P.modes[slot];
