@@ -8,13 +8,15 @@ PerturbationsModule -> (halofit) -> TransferModule -> SpectraModule -> LensingMo
 (SURVEY.md section 8 with its two "next" rows).
 
 A "step" = one pass of the hot path over one batch of `--batch` cosmologies per GPU: ONE batched
-perturbation launch, then the per-cosmology stages.  Steps are scheduled by sweep.SweepPipeline on two
-sets of contexts (per-cosmology stages of step i under the launch of step i+1; --no-pipeline: strictly
-one step after the other); everything is drained before the clock stops.  Upstream inputs
-(background/thermodynamics tables, ncdm grids, primordial spectrum) are synthetic-by-construction: they
-were generated once from the reference for the named configuration and are stored in
-tests/golden/planck18.npz.  The reference arm times the same five module constructors of the unmodified
-reference (oracle/_ref) on all host cores.
+perturbation launch, then the per-cosmology stages.  The batch is `--batch` DIFFERENT cosmologies: the
+seed-0 Latin hypercube of BASELINE configs[4] with the Planck-18 settings (`--identical`: copies of the
+best fit); their upstream tables (background, thermodynamics, ncdm grids) are produced once, outside the
+timed region, by the reference's own upstream modules inside the compiled drop-in library
+(shim/_build/libclass_b200.so).  Steps are scheduled by sweep.SweepPipeline on `--sets` sets of contexts:
+the batched launches of consecutive steps overlap and the per-cosmology stages run under them;
+everything is drained before the clock stops.  The reference arm runs the unmodified reference
+(oracle/_ref) in its throughput-optimal arrangement (one single-threaded process per core) on the same
+workload and the same five module constructors.
 
   python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU)
   python bench.py --impl reference --steps K --warmup W    the reference's CPU implementation
@@ -91,25 +93,42 @@ class _NL:
         self.nl_corr_density_m = arr
 
 
-def hot_path(M, inp, ctx, bg, th, pk, nl, fetch_tables=False):
-    """One cosmology through the three stages on an existing context."""
-    pt = M.PerturbationsModule(inp, bg, th)
-    tr = M.TransferModule(inp, bg, th, pt, nl)
-    sp = M.SpectraModule(inp, pt, M.TabulatedPrimordial(pk), nl, tr)
-    out_bytes = sp.cl_[0].nbytes
-    if fetch_tables:  # what the reference-facing drop-in hands back as public members
-        out_bytes += sum(s.nbytes for s in pt.sources_[0]) + tr.transfer_[0].nbytes
-    return pt, tr, sp, out_bytes
+# DRAM bytes one batched perturbation launch moves per cosmology: measured with ncu (profiles/, see roofline.traffic_source)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic.json")
 
 
-# DRAM bytes one batched perturbation launch moves per cosmology (ncu, see roofline.traffic_source)
-TRAFFIC_BYTES_PER_COSMOLOGY = {"planck18": 36.44e6}
+def sweep_inputs(args, M):
+    """The B cosmologies of a step.  Default: B DIFFERENT cosmologies -- the seed-0 Latin hypercube of BASELINE config 5
+     with the Planck-2018 settings of configs[1] -- whose upstream tables come from the compiled drop-in library
+    (shim/_build/libclass_b200.so: the reference's own input/background/thermodynamics modules, out of scope and unchanged).
+    --identical (or no drop-in library on this box): B copies of the Planck-18 best fit from tests/golden/planck18.npz."""
+    from classpp_public_b200.configs import CONFIGS
+    base = CONFIGS[args.config]
+    fixture = M.Inputs.load(os.path.join(ROOT, "tests", "golden", args.config + ".npz"))
+    if not args.identical:
+        try:
+            from classpp_public_b200 import upstream
+            if not upstream.available():
+                raise ImportError("shim/_build/libclass_b200.so not found")
+            from concurrent.futures import ThreadPoolExecutor
+            pars = upstream.latin_hypercube_sweep(args.batch, base, seed=0)
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+                inps = list(ex.map(upstream.inputs_for, pars))
+            prims = [M.AnalyticPrimordial(p["A_s"], p["n_s"]) for p in pars]
+            return inps, prims, {"kind": "lhs", "upstream_host_s_per_cosmology": (time.perf_counter() - t0) / args.batch,
+                                 "upstream_threads": os.cpu_count()}
+        except Exception as e:  # noqa: BLE001
+            print("bench.py: falling back to identical cosmologies (%s)" % e, file=sys.stderr)
+    prim = M.AnalyticPrimordial(base.get("A_s", 2.215e-9), base.get("n_s", 0.9619))
+    return [fixture] * args.batch, [prim] * args.batch, {"kind": "identical"}
 
 
 def run_gpu(args):
     import torch
     import torch.distributed as dist
     from classpp_public_b200 import modules as M
+    from classpp_public_b200.sweep import SweepPipeline
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -122,42 +141,35 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    inp = M.Inputs.load(os.path.join(ROOT, "tests", "golden", args.config + ".npz"))
-    a = inp.arrays
-    pk = a["pm.pk_at_transfer_k"]
-    nl = _NL(a["nl.nl_corr_density_m"]) if "nl.nl_corr_density_m" in a else None
-    # `non linear = halofit` (config 2): by default the halofit step runs on the device between stages 1 and 2
-    #  instead of taking the reference's correction table as an input
-    from classpp_public_b200.configs import CONFIGS
-    halofit_on_device = nl is not None and args.halofit == "device"
-    prim_k = M.AnalyticPrimordial(CONFIGS[args.config].get("A_s", 2.215e-9), CONFIGS[args.config].get("n_s", 0.9619))
-    B = args.batch
-    prim_pt = np.ascontiguousarray(prim_k.pk_at_k(a["ref.k"]))
+    B, NSET = args.batch, (1 if args.no_pipeline else args.sets)
+    inps, prims, wl = sweep_inputs(args, M)
+    use_halofit = int(inps[0].meta["nl.method"]) != 0
 
-    # ---- device-resident inputs: one context (own stream) per cosmology of the batch. Two sets of contexts, used by
-    # alternate steps: the per-cosmology stages of step i (halofit .. P(k), short kernels and host work) run while the
-    # batched perturbation launch of step i+1 already occupies the GPU; everything is drained before the clock stops.
-    NSET = 1 if args.no_pipeline else 2
+    # ---- one context (own stream) per cosmology, NSET sets of B contexts used by consecutive steps: the batched
+    # perturbation launches of consecutive steps OVERLAP (the lane kernel's duration is set by its longest k chain, not
+    # by the batch: the GPU is mostly idle while the last chains finish), and the per-cosmology stages of a step run
+    # under the launches of the next ones.  Everything is drained before the clock stops.
     sets = []
     for s_ in range(NSET):
         cs_, ms_ = [], []
         for b in range(B):
             ctx = M.Context(local)
-            bg = M.BackgroundModule(inp, ctx)
-            th = M.ThermodynamicsModule(inp, bg)
+            ctx.set_option("lean_scratch", 1)
+            if args.path != "auto":
+                ctx.set_option("lane_path", 1 if args.path == "lane" else 0)
+            bg = M.BackgroundModule(inps[b], ctx)
+            th = M.ThermodynamicsModule(inps[b], bg)
             cs_.append(ctx)
             ms_.append((bg, th))
         sets.append((cs_, ms_))
     ctxs = [c for cs_, _ in sets for c in cs_]
 
     results = [None] * B
-    import threading
-    from classpp_public_b200.sweep import SweepPipeline
-    kms = {}
-    kms_lock = threading.Lock()
+    kms, kms_lock = {}, threading.Lock()
+    KEYS = ("perturb", "k_spline", "bessel", "los", "spectra", "perturb_tail", "halofit", "lensing")
 
     def kms_reset():
-        for k_ in ("perturb", "k_spline", "bessel", "los", "spectra", "perturb_tail", "halofit", "lensing"):
+        for k_ in KEYS:
             kms[k_] = 0.0
 
     kms_reset()
@@ -168,61 +180,55 @@ def run_gpu(args):
             for k_ in keys:
                 kms[k_] += t[k_]
 
-    # One pass of the hot path over a batch ("step"): every k mode of the B cosmologies in ONE perturbation launch
-    # (longest modes first across the batch), then halofit, transfer, spectra, lensing and P(k) per cosmology on its own
-    # stream. With `inputs` (pinned host arrays) the upstream tables are uploaded first and the public result members
-    # (sources_, cl_, cl_lens_, P(k)) are read back: the end-to-end variant.
-    def front(s_, b, inputs, p_, n_, fetch):
+    def front(s_, b, host_inputs):
         cs, ms = sets[s_]
-        if inputs is not None:  # host -> device copy of this step's inputs
-            bg = M.BackgroundModule(inputs, cs[b])
-            ms[b] = (bg, M.ThermodynamicsModule(inputs, bg))
-        return M.PerturbationsModule(inputs or inp, ms[b][0], ms[b][1], solve=False)
+        if host_inputs is not None:  # end to end: host -> device copy of this step's inputs (pinned host tables)
+            bg = M.BackgroundModule(host_inputs[b], cs[b])
+            ms[b] = (bg, M.ThermodynamicsModule(host_inputs[b], bg))
+        return M.PerturbationsModule((host_inputs or inps)[b], ms[b][0], ms[b][1], solve=False)
 
     def on_solved(s_):
-        for c in sets[s_][0]:
-            kms_add(c, ("perturb", "perturb_tail"))
+        kms_add(sets[s_][0][0], ("perturb", "perturb_tail"))
 
-    def back(s_, b, pt, inputs, p_, n_, fetch):
+    def back(s_, b, pt, host_inputs):
         cs, ms = sets[s_]
-        x = inputs or inp
-        nlb = n_
-        if halofit_on_device:  # NonlinearModule (halofit) on the device, from the resident delta_m sources
-            nlb = M.NonlinearModule(x, ms[b][0], pt, prim_k)
+        x = (host_inputs or inps)[b]
+        nlb = M.NonlinearModule(x, ms[b][0], pt, prims[b]) if use_halofit else None  # halofit on the device
         tr = M.TransferModule(x, ms[b][0], ms[b][1], pt, nlb)
-        sp = M.SpectraModule(x, pt, M.TabulatedPrimordial(p_), nlb, tr)
-        le = M.LensingModule(x, sp)  # lensed TT/TE/EE/BB on the device (SURVEY 8f row 2): the metric's "lensed C_l"
-        pk_lin = pt.pk_linear(prim_pt)  # linear P(k, z=0) on the perturbation k grid
-        out_bytes = sp.cl_[0].nbytes + le.cl_lens_.nbytes + pk_lin.nbytes
-        if fetch:  # device -> host: the public members downstream modules read (Nonlinear/Lensing/Output)
-            out_bytes += sum(s__.nbytes for s__ in pt.sources_[0])
+        sp = M.SpectraModule(x, pt, prims[b], nlb, tr)
+        le = M.LensingModule(x, sp)  # lensed TT/TE/EE/BB on the device: the metric's "lensed C_l"
+        pk_lin = pt.pk_linear(prims[b].pk_at_k(pt.k_[0]))  # linear P(k, z=0) on the perturbation k grid
+        out_bytes = sp.cl_[0].nbytes + le.cl_lens_.nbytes + pk_lin.nbytes  # device -> host: the results a user reads
         kms_add(cs[b], ("k_spline", "bessel", "los", "spectra", "halofit", "lensing"))
-        results[b] = (pt, tr, sp, out_bytes)
+        results[b] = (pt.info, tr.info, out_bytes, float(le.cl_lens_[le.lt_size_ * 10]))
         return out_bytes
 
     pipe = SweepPipeline(B, front, back, n_sets=NSET, on_solved=on_solved)
 
-    def step(inputs=None, pk_=None, nl_=None, fetch=False):
-        pipe.submit(inputs, pk if pk_ is None else pk_, nl if nl_ is None else nl_, fetch)
+    def step(host_inputs=None):
+        pipe.submit(host_inputs)
         if NSET == 1:
             pipe.drain()
 
-    drain = pipe.drain
-
     def barrier():
-        drain()
+        pipe.drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for w_ in range(args.warmup):
+    # ---- warm-up: the first launch runs alone (its duration sets the stagger between overlapping launches)
+    t_w = time.perf_counter()
+    step()
+    pipe.drain()
+    solo_s = pipe.solve_seconds[-1]
+    if NSET > 1:
+        pipe.stagger = max(solo_s / NSET, 0.0) if args.stagger < 0 else args.stagger * solo_s
+    for _ in range(max(args.warmup - 1, 0)):
         step()
-        if w_ == 0:  # the first launch runs alone: its duration sets the stagger between overlapping launches
-            drain()
-            if NSET > 1 and args.stagger >= 0:
-                pipe.stagger = args.stagger * pipe.solve_seconds[-1]
-    drain()
+    pipe.drain()
+    warm_s = time.perf_counter() - t_w
+
     launches0 = sum(c.launch_count for c in ctxs)
     sampler = ClockSampler(local)
     sampler.start()
@@ -234,9 +240,7 @@ def run_gpu(args):
     for _ in range(args.steps):
         step()
     barrier()
-    if os.environ.get("CLPP_VERBOSE"):
-        print("launch log (set, start, end):", [(s_, round(a_ - t0, 2), round(b_ - t0, 2)) for s_, a_, b_ in pipe.launch_log[-args.steps:]], file=sys.stderr)
-    kms_timed = dict(kms)  # frozen: the end-to-end passes below keep accumulating into the live dict
+    kms_timed = dict(kms)
     ev1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -248,30 +252,31 @@ def run_gpu(args):
         t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
-    n_cosmo = B * args.steps * world
-    value = n_cosmo / elapsed
+    value = B * args.steps * world / elapsed
+    launch_log = [(s_, round(a_ - t0, 2), round(b_ - t0, 2)) for s_, a_, b_ in pipe.launch_log[-args.steps:]]
 
-    # ---- end to end through the public (reference-facing) API from pinned HOST buffers
+    # ---- end to end through the C ABI from pinned HOST buffers: every step uploads the upstream tables of its B
+    # cosmologies (clpp_set_background / clpp_set_thermo: host spline + H2D) and reads the results back (C_l, lensed C_l, P(k))
     def pinned(x):
         return torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()
-    inp_h = M.Inputs(inp.meta, {k: (pinned(v) if v.dtype == np.float64 and v.size > 64 else v) for k, v in a.items()})
-    pk_h = pinned(pk)
-    nl_h = _NL(pinned(nl.nl_corr_density_m)) if nl is not None else None
-    h2d = sum(inp_h.arrays[k].nbytes for k in ("bg.tau_table", "bg.background_table", "th.z_table",
-                                               "th.thermodynamics_table")) * 2  # tables + their spline tables
-    # the halofit table is an input only with --halofit input; on the device it is computed from the resident sources
-    h2d += (nl_h.nl_corr_density_m.nbytes if (nl_h is not None and not halofit_on_device) else 0) + pk_h.nbytes
-    e2e_steps = max(1, min(args.steps, 3))
-    h2d *= B
-    step(inp_h, pk_h, nl_h, fetch=True)  # one untimed pass: first-touch allocations of the result buffers
+    cache = {}
+
+    def pin_inputs(i):
+        if id(i) not in cache:
+            cache[id(i)] = M.Inputs(i.meta, {k: (pinned(v) if v.dtype == np.float64 and v.size > 64 else v) for k, v in i.arrays.items()})
+        return cache[id(i)]
+    host = [pin_inputs(i) for i in inps]
+    h2d = sum(sum(i.arrays[k].nbytes for k in ("bg.tau_table", "bg.background_table", "th.z_table", "th.thermodynamics_table")) * 2
+              for i in host)  # tables + their spline tables
+    e2e_steps = max(1, min(args.steps, NSET))
     barrier()
     te0 = time.perf_counter()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record()
     for _ in range(e2e_steps):
-        step(inp_h, pk_h, nl_h, fetch=True)
-    d2h = sum(r[3] for r in results)
+        step(host)
     barrier()
+    d2h = sum(r[2] for r in results)
     ee1.record()
     torch.cuda.synchronize()
     e2e_elapsed = max(ee0.elapsed_time(ee1) * 1e-3, time.perf_counter() - te0)
@@ -281,147 +286,232 @@ def run_gpu(args):
         e2e_elapsed = float(t.item())
     e2e_value = e2e_steps * B * world / e2e_elapsed
 
+    # ---- latency of ONE cosmology (the Class.compute() use case): perturbations alone and the whole hot path
+    lat = {}
+    if rank == 0 and not args.no_latency:
+        c1 = M.Context(local)
+        bg1 = M.BackgroundModule(inps[0], c1)
+        th1 = M.ThermodynamicsModule(inps[0], bg1)
+        for rep in range(2):
+            t1 = time.perf_counter()
+            pt1 = M.PerturbationsModule(inps[0], bg1, th1)
+            t2 = time.perf_counter()
+            nl1 = M.NonlinearModule(inps[0], bg1, pt1, prims[0]) if use_halofit else None
+            tr1 = M.TransferModule(inps[0], bg1, th1, pt1, nl1)
+            sp1 = M.SpectraModule(inps[0], pt1, prims[0], nl1, tr1)
+            M.LensingModule(inps[0], sp1)
+            t3 = time.perf_counter()
+        lat = {"latency_single_cosmology_s": t3 - t1, "latency_single_cosmology_perturb_s": t2 - t1,
+               "latency_note": "one cosmology alone on the GPU (warp-per-mode kernels: bounded by the k = 22.6/Mpc chain of 3.6e5 "
+                               "step attempts); second of two runs"}
+        c1.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (perturb_kernel): FP64 vector pipe
+    # ---- roofline of the dominant kernel (the batched perturbation launch): FP64 vector pipe
     peaks, peaks_kind = load_peaks()
     fp64_peak = ctxs[0].fp64_peak_tflops()
-    n_launch = B * args.steps
-    # one perturb_kernel launch integrates the whole batch: B cosmologies of algorithmic work each
-    # overlapping launches (pipeline): the device time the perturbation kernels occupy is at most the timed region itself
-    perturb_busy = min(kms_timed["perturb"] * 1e-3, elapsed)
-    t_perturb = max(perturb_busy / args.steps, 1e-12)
+    perturb_busy = min(kms_timed["perturb"] * 1e-3, elapsed)  # launches of consecutive steps overlap on purpose
     algo = ALGO_FLOP_STAGE1.get(args.config, 1.0e9) * B
-    achieved = algo / t_perturb / 1e12
-    tr_info = results[0][1].info
-    t_los = max(kms_timed["los"] * 1e-3 / n_launch, 1e-12)
-    sec_achieved = ALGO_FLOP_PER_LOS_POINT * 1.5e8 / t_los / 1e12
-    roofline = {"kernel": "perturb_kernel", "bound": "fp64-vector (latency-bound in practice; neither hbm nor tensor)",
+    achieved = algo * args.steps / max(perturb_busy, 1e-12) / 1e12
+    info_pt, info_tr = results[0][0], results[0][1]
+    n_back = B * args.steps
+    t_los = max(kms_timed["los"] * 1e-3 / n_back, 1e-12)
+    sec_achieved = ALGO_FLOP_PER_LOS_POINT * float(info_tr.n_points) / t_los / 1e12
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = json.load(open(TRAFFIC_FILE)) if os.path.exists(TRAFFIC_FILE) else {}
+    kern = "perturb_lane_kernel" if (args.path == "lane" or (args.path == "auto" and B >= 256)) else "perturb_kernel + perturb_tail_kernel"
+    roofline = {"kernel": kern, "bound": "fp64-vector (latency-bound in practice; neither hbm nor tensor)",
                 "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "peak_source": "DFMA microbenchmark run live in bench.py (MEASURED_PEAKS.json has no FP64 entry; "
                                "its hbm_gbs=%s bf16_tflops=%s are %s)" % (peaks.get("hbm_gbs"), peaks.get("bf16_tflops"), peaks_kind),
-                "traffic": TRAFFIC_BYTES_PER_COSMOLOGY.get(args.config, 0.0) * B or None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of perturb_kernel + perturb_tail_kernel from the ncu "
-                                  "launch list profiles/r01_launches_v3_bench_b16.csv (bench.py --batch 16: 36.4 MB per cosmology "
-                                  "per step, scaled to this batch); algorithmic: 24.3 MB of S(k,tau) written once + 6 MB of tables",
+                "traffic": (traffic.get(kern, {}).get("dram_bytes_per_cosmology", 0.0) * B) or None,
+                "traffic_source": traffic.get(kern, {}).get("source", "no ncu capture of this kernel at this batch size yet"),
                 "algorithmic_flop_per_launch": algo,
+                "algorithmic_bytes_per_launch": 30.3e6 * B,
                 "launch_duration_ms_avg": kms_timed["perturb"] / args.steps,
                 "launches_in_flight_avg": kms_timed["perturb"] * 1e-3 / elapsed,
-                "note": "achieved = algorithmic flop of the K launches / device time they occupy (= min(sum of launch "
-                        "durations, timed region): launches of consecutive steps overlap on purpose)",
+                "note": "achieved = algorithmic flop of the K launches (SURVEY 8d: oracle stepstat x fixed per-RHS / per-solve "
+                        "costs, 3.6 GFLOP per Planck-18 cosmology) / device time they occupy (= min(sum of launch durations, "
+                        "timed region): launches of consecutive steps overlap on purpose)",
                 "kernel_ms_per_step": {k_: v / args.steps for k_, v in kms_timed.items()},
                 "kernel_share_of_step": {k_: v * 1e-3 / elapsed for k_, v in kms_timed.items()},
-                "secondary": {"kernel": "los_kernel", "bound": "fp64-vector", "achieved": sec_achieved,
-                              "peak": fp64_peak, "unit": "TFLOP/s", "frac": sec_achieved / fp64_peak}}
+                "secondary": [
+                    {"kernel": "los_kernel", "bound": "fp64-vector", "achieved": sec_achieved, "peak": fp64_peak,
+                     "unit": "TFLOP/s", "frac": sec_achieved / fp64_peak,
+                     "algorithmic_flop_per_launch": ALGO_FLOP_PER_LOS_POINT * float(info_tr.n_points),
+                     "launch_duration_ms_avg": t_los * 1e3, "note": "integrand points counted by the kernel (tr_info.n_points) x 40 flop"},
+                    {"kernel": "k_spline_kernel", "bound": "hbm",
+                     "achieved": 3 * 8.0 * info_pt.tp_size * info_pt.k_size * info_pt.tau_size /
+                                 max(kms_timed["k_spline"] * 1e-3 / n_back, 1e-12) / 1e9,
+                     "peak": hbm, "unit": "GB/s", "note": "read S, write S'' and the sweep scratch: 3 x 8 B x tp x k x tau per launch"},
+                    {"kernel": "spectra_partial_kernel + spectra_final_kernel", "bound": "hbm",
+                     "achieved": 8.0 * info_tr.tt_size * info_tr.l_size * info_tr.q_size /
+                                 max(kms_timed["spectra"] * 1e-3 / n_back, 1e-12) / 1e9,
+                     "peak": hbm, "unit": "GB/s", "note": "reads Delta_l(q) once: 8 B x tt x l x q per launch"}]}
+    for s_ in roofline["secondary"][1:]:
+        s_["frac"] = s_["achieved"] / s_["peak"]
 
+    workload = ("BASELINE configs[1]: base_2018_plikHM_TTTEEE_lowl_lowE_lensing.ini settings (1 ncdm species, halofit, "
+                "l_max_scalars=2500, P_k_max_h/Mpc=1); batch = %d %s" %
+                (B, "DIFFERENT cosmologies: seed-0 Latin hypercube of BASELINE configs[4] (omega_b, omega_cdm, h, ln10^10A_s, n_s, "
+                    "tau_reio)" if wl["kind"] == "lhs" else "copies of the Planck-18 best fit (identical cosmologies)"))
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": ("BASELINE configs[1]: base_2018_plikHM_TTTEEE_lowl_lowE_lensing.ini (Planck-2018 best fit, "
-                                "1 ncdm species, halofit, l_max_scalars=2500, P_k_max_h/Mpc=1)") if args.config == "planck18"
-                               else args.config,
-                   "fixture": "tests/golden/%s.npz" % args.config, "batch_per_gpu": B,
-                   "halofit": ("on the device, inside the step (clpp_nonlinear_halofit)" if halofit_on_device else
-                               "correction table is an input" if nl is not None else "none"),
+        "config": {"workload": workload if args.config == "planck18" else args.config, "batch_per_gpu": B,
+                   "cosmologies": wl,
+                   "halofit": "on the device, inside the step (clpp_nonlinear_halofit)" if use_halofit else "none",
                    "scope": "per cosmology: perturbations -> halofit -> transfer -> spectra -> lensing (fast mode) -> linear P(k)",
-                   "k_modes": int(results[0][0].info.k_size), "tau_samples": int(results[0][0].info.tau_size),
-                   "q_values": int(tr_info.q_size), "l_values": int(tr_info.l_size),
-                   "pipeline": ("%d context sets: the per-cosmology stages of step i run under the batched launch of step "
-                                "i+1 (%s); all drained before the clock stops" %
-                                (NSET, "launches overlap, %.2f x solo duration apart" % args.stagger if args.stagger >= 0
-                                 else "one batched launch at a time")) if NSET > 1 else "off",
-                   "parallelism": "independent cosmologies per GPU (replicas, no data-path collective); per GPU all k modes "
-                                  "of the batch in one batched launch: long-tail modes on a high-priority stream, the bulk in "
-                                  "chunks on low-priority streams, generic kernel -> radiation-streaming tail kernel",
-                   "l2_policy": "working set per step = batch x (tables 6 MB + sources 24 MB + source spline 72 MB + Bessel 25 MB "
-                                "+ transfer 12 MB) >> 126 MB L2; every buffer is rewritten every step",
+                   "k_modes": int(info_pt.k_size), "tau_samples": int(info_pt.tau_size),
+                   "q_values": int(info_tr.q_size), "l_values": int(info_tr.l_size),
+                   "pipeline": ("%d context sets of %d cosmologies; batched perturbation launches of consecutive steps overlap, "
+                                "%.2f s apart (solo launch %.2f s); per-cosmology stages run under them; all drained before the "
+                                "clock stops" % (NSET, B, pipe.stagger or 0.0, solo_s)) if NSET > 1 else "off",
+                   "launch_log_set_start_end_s": launch_log,
+                   "parallelism": "independent cosmologies per GPU (replicas, no data-path collective); per GPU every k mode of a "
+                                  "batch in one launch, one THREAD per mode (lane kernel) from 256 cosmologies per launch, one "
+                                  "warp per mode below",
+                   "l2_policy": "working set per step = batch x (tables 6 MB + sources 24 MB + per-mode state 35 KB x 617 + transfer "
+                                "work buffers 90 MB) >> 126 MB L2; every buffer is rewritten every step",
                    "timing": "torch.cuda.Event around K steps after device-wide synchronize, max over ranks; per-kernel "
                              "times from cudaEvents on the launching stream inside libclpp.so"},
-        "k_modes_per_s": value * int(results[0][0].info.k_size),
-        "wall_s": wall,
+        "k_modes_per_s": value * int(info_pt.k_size),
+        "wall_s": wall, "warmup_s": warm_s,
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps,
                 "note": "per step and per cosmology of the batch: upstream tables from pinned host memory through "
                         "clpp_set_background/clpp_set_thermo (host spline + H2D), grids, batched perturbation launch, "
-                        "halofit, transfer, spectra, lensing, P(k), D2H of sources_, cl_, cl_lens_ and P(k) (contexts and "
-                        "device buffers are reused across steps)"},
+                        "halofit, transfer, spectra, lensing, P(k), D2H of cl_, cl_lens_ and P(k) (contexts and device "
+                        "buffers are reused across steps; the 24 MB source table of a cosmology stays on the device)"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
+    out.update(lat)
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args.config, budget_s=20.0)
+        out["cpu_baseline"] = cpu_baseline(args.config, budget_s=20.0, identical=(wl["kind"] != "lhs"))
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(config, budget_s=20.0, threads=None):
-    """The reference's own CPU implementation of the hot path (oracle/_ref = unmodified CLASS++ built
-    from /root/reference) on this box's host cores, timed per module constructor by the probe."""
+def _ref_hot_path_seconds(params, threads):
+    """Wall time of the five module constructors of the hot path in the unmodified reference (oracle/_ref)."""
     from oracle import refprobe
+    ref = refprobe.RefCosmology(params, threads=threads)
+    ref.compute("lensing")
+    t3 = ref.scalar("time.perturb") + ref.scalar("time.transfer") + ref.scalar("time.spectra")
+    t = t3 + ref.scalar("time.nonlinear") + ref.scalar("time.lensing")
+    up = ref.scalar("time.background") + ref.scalar("time.thermo")
+    ref.close()
+    return t, t3, up
+
+
+def _sweep_params(config, n, identical=False):
     from classpp_public_b200.configs import CONFIGS
+    from classpp_public_b200.upstream import latin_hypercube_sweep
+    return [dict(CONFIGS[config])] * n if identical else latin_hypercube_sweep(n, CONFIGS[config], seed=0)
+
+
+def ref_worker(args):
+    """One process of the throughput arrangement of the reference: one cosmology, thread pool of ONE thread."""
+    par = _sweep_params(args.config, args.ref_worker + 1, args.identical)[args.ref_worker]
+    t, t3, up = _ref_hot_path_seconds(par, 1)
+    print(json.dumps({"hot_path_s": t, "three_module_s": t3, "upstream_s": up}))
+
+
+def reference_throughput(config, n_proc, identical=False, rounds=1):
+    """the throughput-optimal CPU arrangement -- one process per cosmology with one thread each,
+    packed onto all host cores.  Returns (cosmologies per second over the hot-path constructors, details)."""
+    best = None
+    for _ in range(rounds):
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", config,
+                                   "--ref-worker", str(i)] + (["--identical"] if identical else []),
+                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL) for i in range(n_proc)]
+        outs = [json.loads(p.communicate()[0].decode().strip().splitlines()[-1]) for p in procs]
+        wall = time.perf_counter() - t0
+        # every process also pays interpreter start-up and the upstream modules: score the hot-path constructors only,
+        # as if the processes were perfectly packed (upper bound of the CPU throughput)
+        hot = float(np.max([o["hot_path_s"] for o in outs]))
+        r = {"value": n_proc / hot, "wall_s": wall, "hot_path_s_max": hot, "hot_path_s_mean": float(np.mean([o["hot_path_s"] for o in outs])),
+             "upstream_s_mean": float(np.mean([o["upstream_s"] for o in outs])), "processes": n_proc}
+        if best is None or r["value"] > best["value"]:
+            best = r
+    return best
+
+
+def cpu_baseline(config, budget_s=20.0, threads=None, identical=False):
+    """The reference's own CPU implementation of the hot path (oracle/_ref = unmodified CLASS++ built from /root/reference)
+    on this box's host cores, on a bounded sample of the bench workload: (1) latency arrangement, one cosmology on all
+    threads of the reference's thread pool; (2) throughput arrangement, one single-threaded process per core."""
+    from oracle import refprobe
     if not refprobe.available():
-        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
-                "sample": "oracle/_ref not built on this box"}
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built on this box"}
     cores = threads or os.cpu_count()
-    times, times3 = [], []
+    pars = _sweep_params(config, 4, identical)
+    lat = []
     t_start = time.perf_counter()
-    n = 0
-    while True:
-        ref = refprobe.RefCosmology(CONFIGS[config], threads=cores)
-        ref.compute("lensing")
-        t3 = ref.scalar("time.perturb") + ref.scalar("time.transfer") + ref.scalar("time.spectra")
-        t = t3 + ref.scalar("time.nonlinear") + ref.scalar("time.lensing")
-        ref.close()
-        n += 1
-        if n > 1:  # the first run of a process is cold: discard
-            times.append(t)
-            times3.append(t3)
-        if (time.perf_counter() - t_start > budget_s and len(times) >= 2) or len(times) >= 8:
+    for i in range(4):
+        t, t3, up = _ref_hot_path_seconds(pars[i % len(pars)], cores)
+        if i > 0:  # the first run of a process is cold
+            lat.append(t)
+        if time.perf_counter() - t_start > 0.4 * budget_s and len(lat) >= 2:
             break
-    best = min(times)
-    return {"value": 1.0 / best, "unit": UNIT, "cores": int(cores), "kind": "reference",
-            "hot_path_s_best": best, "hot_path_s_mean": float(np.mean(times)),
-            "three_module_s_best": float(min(times3)),
-            "sample": "%d full runs of the reference for this config (first discarded); value = 1 / best wall time of "
-                      "the Perturbations+Nonlinear+Transfer+Spectra+Lensing module constructors (same scope as the GPU "
-                      "arm; three_module_s_best = Perturbations+Transfer+Spectra alone; background/thermodynamics/"
-                      "primordial excluded), thread pool = %d threads" % (n, cores)}
+    thr = reference_throughput(config, cores, identical)
+    value = max(1.0 / min(lat), thr["value"])
+    return {"value": value, "unit": UNIT, "cores": int(cores), "kind": "reference",
+            "latency_arrangement": {"spectra_per_s": 1.0 / min(lat), "hot_path_s_best": min(lat), "threads": int(cores)},
+            "throughput_arrangement": thr,
+            "sample": "%d cosmologies of the bench workload on all %d threads of the reference's thread pool (first discarded) and "
+                      "%d cosmologies as %d single-threaded processes (BASELINE.md section 3); value = the better of the two; timed: "
+                      "Perturbations+Nonlinear+Transfer+Spectra+Lensing module constructors (the scope of the GPU arm's step; "
+                      "background/thermodynamics/primordial excluded)" % (len(lat) + 1, cores, cores, cores)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    if args.ref_worker >= 0:
+        return ref_worker(args)
     from oracle import refprobe
-    from classpp_public_b200.configs import CONFIGS
     if not refprobe.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (make -C oracle needs /root/reference)"}))
         return
     cores = os.cpu_count()
-    ts = []
-    for i in range(args.warmup + args.steps):
-        ref = refprobe.RefCosmology(CONFIGS[args.config], threads=cores).compute("lensing")
-        t = (ref.scalar("time.perturb") + ref.scalar("time.nonlinear") + ref.scalar("time.transfer") +
-             ref.scalar("time.spectra") + ref.scalar("time.lensing"))
-        ref.close()
-        if i >= args.warmup:
-            ts.append(t)
-    total = float(np.sum(ts))
-    value = len(ts) / total
+    # a step = `cores` cosmologies of the bench workload in the throughput arrangement (one single-threaded process each,
+    # ~15 s per step); the run is bounded to a few minutes: at most one warm-up step and eight timed steps
+    n_warm, n_steps = min(args.warmup, 1), max(1, min(args.steps, 8))
+    vals = []
+    for i in range(n_warm + n_steps):
+        r = reference_throughput(args.config, cores, args.identical)
+        if i >= n_warm:
+            vals.append(r)
+    value = float(np.mean([v["value"] for v in vals]))
+    lat, _, _ = _ref_hot_path_seconds(_sweep_params(args.config, 1, args.identical)[0], cores)
+    lat, _, _ = _ref_hot_path_seconds(_sweep_params(args.config, 1, args.identical)[0], cores)
+    from classpp_public_b200.configs import CONFIGS  # noqa: F401
+    workload = ("BASELINE configs[1]: base_2018_plikHM_TTTEEE_lowl_lowE_lensing.ini settings (1 ncdm species, halofit, "
+                "l_max_scalars=2500, P_k_max_h/Mpc=1); batch = %d %s" %
+                (cores, "DIFFERENT cosmologies: seed-0 Latin hypercube of BASELINE configs[4] (omega_b, omega_cdm, h, ln10^10A_s, n_s, "
+                        "tau_reio)" if not args.identical else "copies of the Planck-18 best fit (identical cosmologies)"))
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(ts) * 1e3, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": args.config, "note": "unmodified CLASS++ (oracle/_ref) on the host cores; each step = "
-                      "one cosmology, timed = Perturbations+Nonlinear+Transfer+Spectra+Lensing module constructors "
-                      "(the scope of the GPU arm's step)"},
+           "steps": len(vals), "warmup": n_warm, "ms_per_step": float(np.mean([v["hot_path_s_max"] for v in vals])) * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload if args.config == "planck18" else args.config, "batch_per_gpu": int(cores),
+                      "note": "unmodified CLASS++ (oracle/_ref) on the host cores, throughput arrangement: each step = %d "
+                              "cosmologies as %d single-threaded processes; timed = Perturbations+Nonlinear+Transfer+Spectra+Lensing "
+                              "module constructors (the scope of the GPU arm's step); value = cosmologies / slowest process" % (cores, cores)},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(cores), "kind": "reference",
-                            "sample": "%d steps of 1 cosmology each, thread pool = %d" % (len(ts), cores)},
+                            "latency_arrangement": {"spectra_per_s": 1.0 / lat, "hot_path_s": lat, "threads": int(cores)},
+                            "throughput_arrangement": vals[-1],
+                            "sample": "%d steps of %d cosmologies each, one single-threaded process per cosmology" % (len(vals), cores)},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -433,16 +523,20 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="planck18")
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("CLPP_BENCH_BATCH", 128)),
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("CLPP_BENCH_BATCH", 512)),
                     help="cosmologies per GPU and per step (one batched perturbation launch)")
+    ap.add_argument("--sets", type=int, default=int(os.environ.get("CLPP_BENCH_SETS", 3)),
+                    help="context sets = batched launches in flight (consecutive steps overlap)")
+    ap.add_argument("--identical", action="store_true", help="batch = copies of the Planck-18 best fit instead of the Latin hypercube")
+    ap.add_argument("--path", default="auto", choices=["auto", "lane", "warp"], help="perturbation kernels (auto: by batch size)")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-cosmology latency measurement")
+    ap.add_argument("--ref-worker", type=int, default=-1, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stagger", type=float, default=-1.0,
                     help="pipeline: >= 0 lets the batched launches of consecutive steps overlap, this fraction of a solo "
                          "launch duration apart (default: one launch at a time, only the per-cosmology stages overlap it)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="one set of contexts: the per-cosmology stages of a step finish before the next step starts")
-    ap.add_argument("--halofit", default="device", choices=["device", "input"],
-                    help="config with halofit: run it on the device (default) or take the reference's table as input")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

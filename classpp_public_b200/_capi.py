@@ -148,7 +148,7 @@ class SpectraInfo(C.Structure):
 # every symbol declared in include/clpp.h (tests check that the library exports all of them)
 SYMBOLS = [
     "clpp_ctx_create", "clpp_ctx_destroy", "clpp_ctx_launch_count", "clpp_version",
-    "clpp_ctx_get_stream", "clpp_ctx_get_kernel_ms", "clpp_measure_fp64_peak",
+    "clpp_ctx_get_stream", "clpp_ctx_get_kernel_ms", "clpp_measure_fp64_peak", "clpp_ctx_set_option",
     "clpp_set_background", "clpp_set_thermo", "clpp_set_ncdm",
     "clpp_perturb_grids", "clpp_perturb_solve", "clpp_perturb_solve_batch", "clpp_perturb_solve_list", "clpp_perturb_get_k", "clpp_perturb_get_tau",
     "clpp_perturb_get_sources", "clpp_perturb_get_kstat", "clpp_perturb_set_sources",
@@ -176,6 +176,7 @@ def lib():
         dp, ip, cp, vp = P(C.c_double), P(C.c_int), C.c_char_p, C.c_void_p
         L.clpp_version.restype = C.c_char_p
         L.clpp_ctx_create.argtypes = [C.c_int, P(vp), cp]
+        L.clpp_ctx_set_option.argtypes = [vp, cp, C.c_double, cp]
         L.clpp_ctx_destroy.argtypes = [vp]
         L.clpp_ctx_destroy.restype = None
         L.clpp_ctx_launch_count.argtypes = [vp]

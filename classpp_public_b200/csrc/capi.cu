@@ -125,6 +125,15 @@ __global__ void dfma_peak_kernel(double* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+int clpp_ctx_set_option(clpp_ctx* ctx, const char* name, double value, char* err) {
+  CLPP_CHECK(ctx && name, err, "null context / option name");
+  const std::string n(name);
+  if (n == "lean_scratch") ctx->lean_scratch = value != 0.;
+  else if (n == "lane_path") ctx->lane_path = (int)value;
+  else return clpp_fail(err, "unknown context option '%s'", name);
+  return CLPP_SUCCESS;
+}
+
 int clpp_measure_fp64_peak(clpp_ctx* c, double* tflops, char* err) {
   CLPP_CHECK(c && c->dev && tflops, err, "no CUDA device");
   cudaSetDevice(c->device);

@@ -73,6 +73,8 @@ struct clpp_ctx {
   int device = -1;  // -1: host-only context (grids only)
   long launches = 0;
   void* stream = nullptr;  // cudaStream_t
+  bool lean_scratch = false;  // stage-2 work buffers from the stream-ordered pool, returned after the stage
+  int lane_path = -1;         // -1: by batch size; 0 / 1: force the warp-per-mode / thread-per-mode perturbation kernels
 
   // --- inputs
   bool has_bg = false, has_th = false;

@@ -32,7 +32,7 @@
 #include "pt_types.h"
 
 #ifndef LN_CTA
-#define LN_CTA 64
+#define LN_CTA 32  // one warp per CTA: the long chains of a launch spread over as many SMs (and L1 caches) as possible
 #endif
 
 #ifdef CLPP_HOST_SIM

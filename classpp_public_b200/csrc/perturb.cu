@@ -3140,10 +3140,18 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   std::vector<int> perm(n_modes);
   for (int i = 0; i < n_modes; i++) perm[i] = i;
   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-  // ---- default path: one THREAD per mode (lane.cuh).  The warp-per-mode kernels below remain for evolver = rk and as
-  // a cross-check (CLPP_WARP_PATH=1, or any of their developer knobs).
-  const bool use_lane = c0->pd.evolver == 1 && !getenv("CLPP_WARP_PATH") && !getenv("CLPP_GENERIC_ONLY") &&
-                        !getenv("CLPP_NO_TAIL") && !getenv("CLPP_COHORT");
+  // ---- two families of kernels.  LANES (lane.cuh, one THREAD per mode): every instruction serves 32 modes, the launch
+  // scales to tens of thousands of modes at almost constant duration, but a GPU thread walks a serial chain ~10x slower
+  // than a warp does: the launch takes >= 14 s (the k = 22.6/Mpc chain of 3.6x10^5 step attempts) however small the batch.
+  // WARPS (one warp per mode, below): 2.2 s for one cosmology, 44 ms (identical) .. 80 ms (different cosmologies) per
+  // cosmology of a batch.  Measured crossover (profiles/r02_lane_vs_warp.txt): ~250 cosmologies per launch.
+  bool use_lane = c0->pd.evolver == 1 && !getenv("CLPP_WARP_PATH") && !getenv("CLPP_GENERIC_ONLY") &&
+                  !getenv("CLPP_NO_TAIL") && !getenv("CLPP_COHORT");
+  if (use_lane) {
+    const char* e = getenv("CLPP_LANE");
+    const int forced = c0->lane_path >= 0 ? c0->lane_path : (e ? atoi(e) : -1);
+    use_lane = forced >= 0 ? forced != 0 : n_ctx >= 256;
+  }
   if (use_lane) {
     std::vector<int2> sorted(n_modes);
     for (int i = 0; i < n_modes; i++) sorted[i] = modes[perm[i]];

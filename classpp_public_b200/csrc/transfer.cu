@@ -450,6 +450,29 @@ los_kernel(LosParams P, const double* __restrict__ kgrid, const double* __restri
 // =============================================================================================
 #define dev_alloc(p, n, err) clpp_dev_reserve(d, p, n, err)
 
+// work buffer of one stage call: grow-only per-context buffer, or (lean_scratch) a stream-ordered pool allocation that is
+// returned to the pool when the stage has been enqueued -- the pool recycles it for the next context without any
+// device-wide synchronisation (cudaMallocAsync / cudaFreeAsync)
+struct ScratchList {
+  cudaStream_t st;
+  bool lean;
+  std::vector<void**> owned;
+  template <typename T>
+  int get(clpp_ctx::Dev* d, T** p, size_t n, char* err) {
+    if (!lean) return clpp_dev_reserve(d, p, n, err);
+    if (*p && d->cap.count((void*)p)) { cudaFree(*p); d->cap.erase((void*)p); }  // left over from a non-lean call
+    cudaError_t e = cudaMallocAsync((void**)p, (n > 0 ? n : 1) * sizeof(T), st);
+    if (e != cudaSuccess) return clpp_fail(err, "cudaMallocAsync of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    owned.push_back((void**)p);
+    return CLPP_SUCCESS;
+  }
+  void release() {
+    for (void** p : owned) { cudaFreeAsync(*p, st); *p = nullptr; }
+    owned.clear();
+  }
+  ~ScratchList() { release(); }  // error paths
+};
+
 int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_begin, int q_end, char* err) {
   clpp_ctx::Dev* d = c->dev;
   const clpp_perturb_info& PI = c->pinfo;
@@ -458,6 +481,18 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
   const int nk = PI.k_size, nt = PI.tau_size, ntp = PI.tp_size;
   const size_t nsrc = (size_t)ntp * nk * nt;
   cudaStream_t st = d->stream;
+  ScratchList scratch{st, c->lean_scratch, {}};
+  if (c->lean_scratch) {
+    static bool pool_ready = false;  // keep freed blocks cached in the pool (no trimming at synchronisation points)
+    if (!pool_ready) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_ready = true;
+    }
+  }
   CLPP_CHECK(TI.tt_size <= LOS_MAX_TT, err, "too many transfer types");
   CLPP_CHECK(nt >= 3 && nk >= 3, err, "source table too small");
 
@@ -474,7 +509,7 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
   CLPP_CUDA(cudaMemcpyAsync(d->tau, c->tau.data(), nt * sizeof(double), cudaMemcpyHostToDevice, st), err);
 
   // (a) sources seen by the transfer stage (+ nonlinear correction of phi+psi), spline along k
-  if (dev_alloc(&d->src_tr, nsrc, err) || dev_alloc(&d->src_ddk, nsrc, err)) return CLPP_FAILURE;
+  if (scratch.get(d, &d->src_tr, nsrc, err) || scratch.get(d, &d->src_ddk, nsrc, err)) return CLPP_FAILURE;
   CLPP_CUDA(cudaMemcpyAsync(d->src_tr, d->sources, nsrc * sizeof(double), cudaMemcpyDeviceToDevice, st), err);
   std::vector<double> corr_t;
   if (!nl_corr_density && c->nl_dev_valid && d->nl_corr2 && PI.index_tp_phi_plus_psi >= 0) {
@@ -496,7 +531,7 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
     c->launches++;
   }
   {
-    if (dev_alloc(&d->spline_u, nsrc, err)) return CLPP_FAILURE;
+    if (scratch.get(d, &d->spline_u, nsrc, err)) return CLPP_FAILURE;
     for (int i = 0; i < 6; i++)
       if (!d->ev2[i]) cudaEventCreate(&d->ev2[i]);
     const int n = ntp * nt;
@@ -525,10 +560,10 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
     d->bessel_xmin = xmin;
     c->tinfo.x_size = nx;
     const size_t nb = (size_t)TI.l_size_max * nx;
-    if (dev_alloc(&d->bessel_x, nx, err) || dev_alloc(&d->bessel_phi, nb, err) || dev_alloc(&d->bessel_dphi, nb, err) ||
+    if (scratch.get(d, &d->bessel_x, (size_t)nx, err) || scratch.get(d, &d->bessel_phi, nb, err) || scratch.get(d, &d->bessel_dphi, nb, err) ||
         dev_alloc(&d->chi_at_phimin, TI.l_size_max, err))
       return CLPP_FAILURE;
-    if (dev_alloc(&d->bessel_scale, nb, err)) return CLPP_FAILURE;
+    if (scratch.get(d, &d->bessel_scale, nb, err)) return CLPP_FAILURE;
     int* scale_count = d->bessel_scale;
     cudaEventRecord(d->ev2[2], st);
     bessel_table_kernel<<<(nx + 63) / 64, 64, 0, st>>>(nx, xmin, dx, std::min(nx, xfwdidx), lmax + 1, TI.l_size_max, d->l,
@@ -593,6 +628,7 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
   }
   cudaEventRecord(d->ev[1], st);
   CLPP_CUDA(cudaGetLastError(), err);
+  scratch.release();
   unsigned long long cnt[2];
   CLPP_CUDA(cudaMemcpyAsync(cnt, d->tr_counters, sizeof(cnt), cudaMemcpyDeviceToHost, st), err);
   CLPP_CUDA(cudaStreamSynchronize(st), err);
@@ -610,6 +646,7 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
 
 int clpp_dev_get_bessel(clpp_ctx* c, double* x, double* phi, double* dphi, double* chi, char* err) {
   clpp_ctx::Dev* d = c->dev;
+  CLPP_CHECK(d->bessel_phi != nullptr, err, "the Bessel table of this context has been returned to the memory pool (lean_scratch)");
   const size_t nb = (size_t)c->tinfo.l_size_max * d->bessel_nx;
   if (x) CLPP_CUDA(cudaMemcpy(x, d->bessel_x, d->bessel_nx * sizeof(double), cudaMemcpyDeviceToHost), err);
   if (phi) CLPP_CUDA(cudaMemcpy(phi, d->bessel_phi, nb * sizeof(double), cudaMemcpyDeviceToHost), err);

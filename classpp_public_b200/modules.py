@@ -114,6 +114,10 @@ class Context:
             raise CosmoComputationError(self._err.value.decode(errors="replace"))
         self.device = device
 
+    def set_option(self, name, value):
+        """clpp_ctx_set_option: 'lean_scratch' (sweeps: transfer work buffers from the device memory pool), 'lane_path'."""
+        self.check(self._lib.clpp_ctx_set_option(self._h, name.encode(), float(value), self._err))
+
     def check(self, rc):
         if rc != 0:
             raise CosmoComputationError(self._err.value.decode(errors="replace"))

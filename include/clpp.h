@@ -46,6 +46,12 @@ int clpp_ctx_get_stream(clpp_ctx* ctx, void** stream);
  * [4] spectra kernels, [5] perturb_tail_kernel alone (included in [0]; 0 when the groups overlap), [6] halofit_kernel,
  * [7] lensing kernels */
 int clpp_ctx_get_kernel_ms(const clpp_ctx* ctx, double out[8]);
+/* options of a context. "lean_scratch" = 1: the transfer stage takes its work buffers (copy of the sources, their k-spline,
+ * the Bessel table: ~90 MB) from the stream-ordered memory pool of the device and returns them when the stage has run,
+ * so that a sweep can keep thousands of contexts resident (45 MB each: sources + transfer functions + tables);
+ * the Bessel accessor clpp_transfer_get_bessel is then unavailable.  "lane_path" = 0 / 1: force the warp-per-mode /
+ * thread-per-mode perturbation kernels (default -1: by batch size). */
+int clpp_ctx_set_option(clpp_ctx* ctx, const char* name, double value, char* err);
 /* FP64 vector-pipe peak of this device measured with a dependent-free DFMA loop (TFLOP/s);
  * the denominator of the stage-1/2 roofline (MEASURED_PEAKS.json has no FP64 entry) */
 int clpp_measure_fp64_peak(clpp_ctx* ctx, double* tflops, char* err);
