@@ -130,6 +130,7 @@ int clpp_ctx_set_option(clpp_ctx* ctx, const char* name, double value, char* err
   const std::string n(name);
   if (n == "lean_scratch") ctx->lean_scratch = value != 0.;
   else if (n == "lane_path") ctx->lane_path = (int)value;
+  else if (n == "use_device_nl") ctx->use_device_nl = value != 0.;
   else return clpp_fail(err, "unknown context option '%s'", name);
   return CLPP_SUCCESS;
 }
@@ -225,6 +226,7 @@ int clpp_perturb_grids(clpp_ctx* c, const clpp_perturb_desc* desc, clpp_perturb_
   CLPP_CHECK(c && desc, err, "null argument");
   c->pd = *desc;
   c->has_sources = false;
+  c->nl_dev_valid = false;  // a device-resident halofit table belongs to the previous sources
   if (clpp_host_perturb_grids(c, err)) return CLPP_FAILURE;
   if (info) *info = c->pinfo;
   return CLPP_SUCCESS;
@@ -302,6 +304,7 @@ int clpp_perturb_set_sources(clpp_ctx* c, const clpp_perturb_info* info, const d
   c->k.assign(k, k + info->k_size);
   c->tau.assign(tau, tau + info->tau_size);
   c->has_pgrids = true;
+  c->nl_dev_valid = false;
   const int nk = info->k_size, nt = info->tau_size, ntp = info->tp_size;
   std::vector<double> tmp((size_t)ntp * nk * nt);
   for (int tp = 0; tp < ntp; tp++)

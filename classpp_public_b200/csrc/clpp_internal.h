@@ -95,6 +95,8 @@ struct clpp_ctx {
   // --- stage 2
   bool has_tgrids = false, has_transfer = false;
   bool nl_dev_valid = false;  // a device-resident halofit correction matches the current sources
+  int nl_dev_nk = 0, nl_dev_nt = 0;  // grid the device-resident correction was built for
+  bool use_device_nl = true;  // clpp_transfer_compute(nl_corr_density = NULL) applies it (option "use_device_nl")
   clpp_transfer_desc td{};
   clpp_transfer_info tinfo{};
   std::vector<int> l, l_size_tt;

@@ -71,6 +71,15 @@ struct clpp_ctx::Dev {
   double t_lensing_ms = 0.;
 };
 
+// Dynamic shared memory above 48 KB needs a per-function opt-in that is PROCESS-GLOBAL state: raise it to the device limit
+// (227 KB) once instead of setting the size of each call -- concurrent stage calls of different contexts (sweeps run one
+// host thread per cosmology) would otherwise lower each other's limit between the attribute call and the launch.
+#define CLPP_SMEM_OPT_IN_MAX (227 * 1024)
+template <typename K>
+inline cudaError_t clpp_allow_max_dynamic_smem(K kernel) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CLPP_SMEM_OPT_IN_MAX);
+}
+
 // grow-only device buffer: reallocates only when the requested size exceeds the capacity
 template <typename T>
 inline int clpp_dev_reserve(clpp_ctx::Dev* d, T** p, size_t n, char* err) {

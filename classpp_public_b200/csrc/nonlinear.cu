@@ -311,7 +311,7 @@ int clpp_dev_halofit(clpp_ctx* c, const clpp_halofit_desc* hd, const double* pri
   P.corr = d->nl_corr2; P.fail = d->hf_flags; P.status = d->hf_flags + 2 * nt;
   const size_t smem = (size_t)(3 * nk + 7 * P.ni + std::max(P.ni, nk)) * sizeof(double);
   CLPP_CHECK(smem <= 200 * 1024, err, "k grid too large for the shared-memory staging of halofit");
-  CLPP_CUDA(cudaFuncSetAttribute(halofit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
+  { static const cudaError_t once = clpp_allow_max_dynamic_smem(halofit_kernel); CLPP_CUDA(once, err); }
   cudaEventRecord(d->ev[0], st);
   halofit_kernel<<<P.n_spec * nt, 32, smem, st>>>(P);
   c->launches++;
@@ -345,5 +345,6 @@ int clpp_dev_halofit(clpp_ctx* c, const clpp_halofit_desc* hd, const double* pri
   CLPP_CUDA(cudaStreamSynchronize(st), err);
   { float ms = 0; cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); d->t_halofit_ms = ms; }
   c->nl_dev_valid = true;
+  c->nl_dev_nk = nk; c->nl_dev_nt = nt;
   return CLPP_SUCCESS;
 }

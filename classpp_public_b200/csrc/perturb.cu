@@ -3259,12 +3259,12 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     size_t smem_pad = 0;
     if (wpc > 1 && P.neq_max >= 100 && smem * wpc <= 114 * 1024) smem_pad = 115 * 1024 - smem * wpc;
     if (getenv("CLPP_SMEM_PAD_KB")) smem_pad = (size_t)atoi(getenv("CLPP_SMEM_PAD_KB")) * 1024;  // developer knob
-    CLPP_CUDA(cudaFuncSetAttribute(perturb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * wpc + smem_pad)), err);
+    { static const cudaError_t once = clpp_allow_max_dynamic_smem(perturb_kernel); CLPP_CUDA(once, err); }
     P.wpc = wpc;
     PtParams Pt = P;  // geometry of the tail kernel: at most 16 equations, all hub
     set_geometry(Pt, 16, 16, c0->pd);
     const size_t smem_tail = perturb_smem_bytes(Pt);
-    CLPP_CUDA(cudaFuncSetAttribute(perturb_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_tail * wpc_tail)), err);
+    { static const cudaError_t once = clpp_allow_max_dynamic_smem(perturb_tail_kernel); CLPP_CUDA(once, err); }
     Pt.wpc = wpc_tail;
     if (getenv("CLPP_VERBOSE"))
       fprintf(stderr, "[clpp] perturb: %d modes, shared memory per mode %zu B (tail %zu B), sizeof(Mode) %zu, neq_max %d, hub %d, "
@@ -3330,9 +3330,15 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     for (int b = 0; b < n_ctx; b++) { cs[b]->dev->t_perturb_ms = 0.; cs[b]->dev->t_perturb_tail_ms = 0.; }
     d0->t_perturb_ms = ms;
   }
+  // per-cosmology outcome: a failing mode only invalidates ITS cosmology (the reference fails only the offending
+  // Cosmology object); the call reports the first failure and how many cosmologies of the batch failed
+  int n_failed = 0;
+  char first[CLPP_ERRLEN];
+  first[0] = 0;
   for (int b = 0; b < n_ctx; b++) {
     clpp_ctx* c = cs[b];
-    for (int i = 0; i < n_sel(b); i++) {
+    bool ok = true;
+    for (int i = 0; i < n_sel(b) && ok; i++) {
       const int ik = sel(b, i);
       const int s = c->kstat[ik].status;
       if (s != 0) {
@@ -3345,12 +3351,17 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
                          : s == 9 ? "Too many integration steps needed within one interval (rk evolver), the system of equations is probably buggy or featuring a discontinuity"
                          : s == 8 ? "scalar initial conditions assume tight coupling on and all other approximations off"
                                   : "unknown device error";
-        return clpp_fail(err, "perturb_solve failed for k=%e (index %d, cosmology %d of the batch): %s", c->k[ik], ik, b, what);
+        if (n_failed == 0)
+          snprintf(first, sizeof(first), "perturb_solve failed for k=%e (index %d, cosmology %d of the batch): %s", c->k[ik], ik, b, what);
+        ok = false;
       }
     }
-    c->has_sources = true;
+    c->has_sources = ok;
     c->nl_dev_valid = false;
+    if (!ok) n_failed++;
   }
+  if (n_failed > 0)
+    return clpp_fail(err, "%s%s", first, n_failed > 1 ? " (and further cosmologies of the batch failed: check clpp_perturb_get_kstat)" : "");
   return CLPP_SUCCESS;
 }
 

@@ -512,7 +512,8 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
   if (scratch.get(d, &d->src_tr, nsrc, err) || scratch.get(d, &d->src_ddk, nsrc, err)) return CLPP_FAILURE;
   CLPP_CUDA(cudaMemcpyAsync(d->src_tr, d->sources, nsrc * sizeof(double), cudaMemcpyDeviceToDevice, st), err);
   std::vector<double> corr_t;
-  if (!nl_corr_density && c->nl_dev_valid && d->nl_corr2 && PI.index_tp_phi_plus_psi >= 0) {
+  if (!nl_corr_density && c->use_device_nl && c->nl_dev_valid && c->nl_dev_nk == nk && c->nl_dev_nt == nt && d->nl_corr2 &&
+      PI.index_tp_phi_plus_psi >= 0) {
     // halofit ran on the device (clpp_nonlinear_halofit): total-matter correction, already in the [k][tau] layout
     const size_t n = (size_t)nk * nt;
     nl_correction_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d->src_tr + (size_t)PI.index_tp_phi_plus_psi * n,
@@ -618,7 +619,7 @@ int clpp_dev_transfer_compute(clpp_ctx* c, const double* nl_corr_density, int q_
   CLPP_CUDA(cudaMemsetAsync(d->tr_counters, 0, 2 * sizeof(unsigned long long), st), err);
   const size_t smem = (size_t)(3 + TI.tt_size) * nt * sizeof(double);
   CLPP_CHECK(smem <= 200 * 1024, err, "tau_size=%d too large for the shared-memory staging of the LOS kernel", nt);
-  CLPP_CUDA(cudaFuncSetAttribute(los_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
+  { static const cudaError_t once = clpp_allow_max_dynamic_smem(los_kernel); CLPP_CUDA(once, err); }
   cudaEventRecord(d->ev[0], st);
   if (q_end > q_begin) {
     los_kernel<<<q_end - q_begin, LOS_THREADS, smem, st>>>(P, d->k, d->tau, d->q, d->kq, d->l, d->chi_at_phimin, d->src_tr,

@@ -366,6 +366,9 @@ class TransferModule:
             if nonlinear_module is not None and getattr(nonlinear_module, "nl_corr_density_m", None) is not None:
                 nl = np.ascontiguousarray(nonlinear_module.nl_corr_density_m, dtype=np.float64)
             lo, hi = q_range if q_range is not None else (0, i.q_size)
+            # the halofit table a device NonlinearModule left on this context is applied only when THAT module is passed
+            # (the reference: no nonlinear module / method none means linear transfers)
+            ctx.set_option("use_device_nl", 1 if (nonlinear_module is not None and getattr(nonlinear_module, "on_device", False)) else 0)
             ctx.check(L.clpp_transfer_compute(ctx.handle, capi.dptr(nl), int(lo), int(hi), ctx.err))
             # refresh counters
             self.n_integrals_, self.n_points_ = None, None
