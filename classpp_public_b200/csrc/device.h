@@ -74,10 +74,15 @@ struct clpp_ctx::Dev {
 // Dynamic shared memory above 48 KB needs a per-function opt-in that is PROCESS-GLOBAL state: raise it to the device limit
 // (227 KB) once instead of setting the size of each call -- concurrent stage calls of different contexts (sweeps run one
 // host thread per cosmology) would otherwise lower each other's limit between the attribute call and the launch.
-#define CLPP_SMEM_OPT_IN_MAX (227 * 1024)
 template <typename K>
 inline cudaError_t clpp_allow_max_dynamic_smem(K kernel) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CLPP_SMEM_OPT_IN_MAX);
+  int dev = 0, optin = 0;
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, kernel);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
 }
 
 // grow-only device buffer: reallocates only when the requested size exceeds the capacity
