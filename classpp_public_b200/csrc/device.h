@@ -31,7 +31,10 @@ struct clpp_ctx::Dev {
   int* queue_head = nullptr;  // atomic cursor into k_order
   double* jac_scratch = nullptr;  // per-CTA global workspace: hub block of the Jacobian
   double* ncdm = nullptr;         // [3][nq_tot]: q, w, dlnf0/dlnq
-  double* lane_scratch = nullptr; // per-thread slabs of the lane kernel (lane.cuh)
+  double* lane_scratch = nullptr; // per-thread slabs of the lane kernel (lane.cuh), global-memory fallback only
+  unsigned char* ln_modes = nullptr;  // (cosmology, k) list of the lane kernel
+  cudaStream_t lane_stream = nullptr;
+  cudaEvent_t lane_done = nullptr, lane_go = nullptr;
   double* i2l1 = nullptr;         // 1/(2l+1)
   double* pt_tail = nullptr;      // hand-off records perturb_kernel -> perturb_tail_kernel
   size_t pt_tail_cap = 0;

@@ -2934,7 +2934,8 @@ __global__ void __launch_bounds__(32 * PT_TAIL_MAX_WPC, PT_TAIL_MIN_BLOCKS / PT_
 // W = doubles of per-thread state (compile-time size of the local-memory slab); W = 0: slab in global memory
 // (fallback for state vectors larger than the largest instantiation; correct but slow)
 #ifndef LN_MIN_CTAS
-#define LN_MIN_CTAS 1  // register budget of the lane kernel: 1 -> 255 registers per thread, 8 -> 128 (16 warps per SM)
+#define LN_MIN_CTAS 16  // register budget of the lane kernel (CTA = one warp): 16 CTAs per SM -> 128 registers per thread, so
+                        // that 8 lane warps still fit beside a resident CTA of the warp-per-mode kernel (252 registers x 128 threads)
 #endif
 template <int W>
 __global__ void __launch_bounds__(LN_CTA, LN_MIN_CTAS) perturb_lane_kernel(const __grid_constant__ PtParams P) {
@@ -3140,54 +3141,78 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   std::vector<int> perm(n_modes);
   for (int i = 0; i < n_modes; i++) perm[i] = i;
   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-  // ---- two families of kernels.  LANES (lane.cuh, one THREAD per mode): every instruction serves 32 modes, the launch
-  // scales to tens of thousands of modes at almost constant duration, but a GPU thread walks a serial chain ~10x slower
-  // than a warp does: the launch takes >= 14 s (the k = 22.6/Mpc chain of 3.6x10^5 step attempts) however small the batch.
-  // WARPS (one warp per mode, below): 2.2 s for one cosmology, 44 ms (identical) .. 80 ms (different cosmologies) per
-  // cosmology of a batch.  Measured crossover (profiles/r02_lane_vs_warp.txt): ~250 cosmologies per launch.
-  bool use_lane = c0->pd.evolver == 1 && !getenv("CLPP_WARP_PATH") && !getenv("CLPP_GENERIC_ONLY") &&
-                  !getenv("CLPP_NO_TAIL") && !getenv("CLPP_COHORT");
-  if (use_lane) {
+  // ---- two families of kernels.
+  // LANES (lane.cuh, one THREAD per mode): every instruction serves 32 modes, tens of thousands of modes run at once, but a
+  // GPU thread walks a serial chain ~10x slower than a warp does (a step attempt of the radiation-streaming tail takes 31 k
+  // cycles in a lane, 15 k in a warp; the k = 22.6/Mpc chain alone is 3.6x10^5 attempts = 14 s in a lane).
+  // WARPS (one warp per mode, below): good latency, poor throughput (one mode per warp, 4..12 warps per SM).
+  // HYBRID (default for batches): the long chains -- the modes with k >= kcut, which hold most of the radiation-streaming
+  // and fluid-phase steps -- go to the warp kernels, the bulk (k < kcut: short chains dominated by the full-hierarchy
+  // phases) to the lane kernel on its own low-priority stream; the two run concurrently.  Measured: profiles/r02_*.
+  int lane_mode = 0;  // 0: warps only, 1: lanes only, 2: hybrid
+  if (c0->pd.evolver == 1 && !getenv("CLPP_WARP_PATH") && !getenv("CLPP_GENERIC_ONLY") && !getenv("CLPP_NO_TAIL") &&
+      !getenv("CLPP_COHORT")) {
     const char* e = getenv("CLPP_LANE");
     const int forced = c0->lane_path >= 0 ? c0->lane_path : (e ? atoi(e) : -1);
-    use_lane = forced >= 0 ? forced != 0 : n_ctx >= 256;
+    lane_mode = forced >= 0 ? forced : (n_ctx >= 8 ? 2 : 0);
   }
-  if (use_lane) {
-    std::vector<int2> sorted(n_modes);
-    for (int i = 0; i < n_modes; i++) sorted[i] = modes[perm[i]];
-    if (clpp_dev_reserve(d0, &d0->pt_cosmo, n_ctx * sizeof(PtCosmo), err)) return CLPP_FAILURE;
-    if (clpp_dev_reserve(d0, &d0->pt_modes, (size_t)std::max(n_modes, 1) * sizeof(int2), err)) return CLPP_FAILURE;
-    CLPP_CUDA(cudaMemcpyAsync(d0->pt_cosmo, cosmo.data(), n_ctx * sizeof(PtCosmo), cudaMemcpyHostToDevice, st), err);
-    CLPP_CUDA(cudaMemcpyAsync(d0->pt_modes, sorted.data(), n_modes * sizeof(int2), cudaMemcpyHostToDevice, st), err);
+  const double lane_kcut = getenv("CLPP_LANE_KCUT") ? atof(getenv("CLPP_LANE_KCUT")) : 0.6;  // 1/Mpc
+  int n_lane = 0;  // the last n_lane modes of the cost-sorted order run in the lane kernel
+  if (lane_mode == 1) n_lane = n_modes;
+  else if (lane_mode == 2)
+    while (n_lane < n_modes && cost[perm[n_modes - 1 - n_lane]] < lane_kcut) n_lane++;
+  const int n_warp_modes = n_modes - n_lane;
+  if (clpp_dev_reserve(d0, &d0->pt_cosmo, n_ctx * sizeof(PtCosmo), err)) return CLPP_FAILURE;
+  CLPP_CUDA(cudaMemcpyAsync(d0->pt_cosmo, cosmo.data(), n_ctx * sizeof(PtCosmo), cudaMemcpyHostToDevice, st), err);
+  P.cosmo = (const PtCosmo*)d0->pt_cosmo;
+  cudaEventRecord(d0->ev[0], st);
+  if (n_lane > 0) {
+    std::vector<int2> lsorted(n_lane);
+    for (int i = 0; i < n_lane; i++) lsorted[i] = modes[perm[n_warp_modes + i]];
+    if (clpp_dev_reserve(d0, &d0->ln_modes, (size_t)n_lane * sizeof(int2), err)) return CLPP_FAILURE;
+    CLPP_CUDA(cudaMemcpyAsync(d0->ln_modes, lsorted.data(), n_lane * sizeof(int2), cudaMemcpyHostToDevice, st), err);
     std::vector<double> i2l1(P.n_i2l1);
     for (int l = 0; l < P.n_i2l1; l++) i2l1[l] = 1.0 / (2.0 * l + 1.0);
     if (clpp_dev_reserve(d0, &d0->i2l1, (size_t)P.n_i2l1, err)) return CLPP_FAILURE;
     CLPP_CUDA(cudaMemcpyAsync(d0->i2l1, i2l1.data(), P.n_i2l1 * sizeof(double), cudaMemcpyHostToDevice, st), err);
-    const int n_cta = (n_modes + LN_CTA - 1) / LN_CTA;
+    const int n_cta = (n_lane + LN_CTA - 1) / LN_CTA;
     static const int slab_sizes[] = {1536, 4608, 14336};
     int slab = 0;
     for (int w : slab_sizes)
       if (slab == 0 && P.ln_words <= w) slab = w;
-    if (slab == 0 && clpp_dev_reserve(d0, &d0->lane_scratch, (size_t)std::max(n_modes, 1) * P.ln_words, err)) return CLPP_FAILURE;
-    P.cosmo = (const PtCosmo*)d0->pt_cosmo;
-    P.modes = (const int2*)d0->pt_modes;
-    P.n_modes = n_modes;
-    P.lane_scratch = d0->lane_scratch;
-    P.i2l1 = d0->i2l1;
+    if (slab == 0 && clpp_dev_reserve(d0, &d0->lane_scratch, (size_t)n_lane * P.ln_words, err)) return CLPP_FAILURE;
+    PtParams PL = P;
+    PL.modes = (const int2*)d0->ln_modes;
+    PL.n_modes = n_lane;
+    PL.lane_scratch = d0->lane_scratch;
+    PL.i2l1 = d0->i2l1;
     if (getenv("CLPP_VERBOSE"))
-      fprintf(stderr, "[clpp] perturb (lane kernel): %d modes, %d CTAs of %d threads, %d doubles of state per mode (slab %d), neq_max %d, hub %d\n",
-              n_modes, n_cta, LN_CTA, P.ln_words, slab, P.neq_max, P.nh_max);
-    cudaEventRecord(d0->ev[0], st);
-    if (n_modes > 0) {
-      switch (slab) {
-        case 1536: perturb_lane_kernel<1536><<<n_cta, LN_CTA, 0, st>>>(P); break;
-        case 4608: perturb_lane_kernel<4608><<<n_cta, LN_CTA, 0, st>>>(P); break;
-        case 14336: perturb_lane_kernel<14336><<<n_cta, LN_CTA, 0, st>>>(P); break;
-        default: perturb_lane_kernel<0><<<n_cta, LN_CTA, 0, st>>>(P); break;
-      }
-      c0->launches++;
+      fprintf(stderr, "[clpp] perturb (lane kernel): %d of %d modes (k < %g/Mpc), %d CTAs of %d threads, %d doubles of state per mode "
+              "(slab %d), neq_max %d, hub %d\n", n_lane, n_modes, lane_mode == 2 ? lane_kcut : 1e30, n_cta, LN_CTA, P.ln_words, slab,
+              P.neq_max, P.nh_max);
+    if (!d0->lane_stream) {
+      int prio_lo = 0, prio_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+      CLPP_CUDA(cudaStreamCreateWithPriority(&d0->lane_stream, cudaStreamNonBlocking, prio_lo), err);
+      CLPP_CUDA(cudaEventCreateWithFlags(&d0->lane_done, cudaEventDisableTiming), err);
+      CLPP_CUDA(cudaEventCreateWithFlags(&d0->lane_go, cudaEventDisableTiming), err);
     }
-  } else {
+    cudaStream_t sl = n_warp_modes > 0 ? d0->lane_stream : st;  // lanes only: the context stream itself
+    if (sl != st) {
+      cudaEventRecord(d0->lane_go, st);  // uploads on st are complete
+      cudaStreamWaitEvent(sl, d0->lane_go, 0);
+    }
+    switch (slab) {
+      case 1536: perturb_lane_kernel<1536><<<n_cta, LN_CTA, 0, sl>>>(PL); break;
+      case 4608: perturb_lane_kernel<4608><<<n_cta, LN_CTA, 0, sl>>>(PL); break;
+      case 14336: perturb_lane_kernel<14336><<<n_cta, LN_CTA, 0, sl>>>(PL); break;
+      default: perturb_lane_kernel<0><<<n_cta, LN_CTA, 0, sl>>>(PL); break;
+    }
+    c0->launches++;
+    if (sl != st) cudaEventRecord(d0->lane_done, sl);
+  }
+  if (n_warp_modes > 0) {
+    const int n_modes = n_warp_modes;  // (shadows the total: this block launches the first n_warp_modes of the sorted order)
     // Launch groups.  Group L: the modes with long radiation-streaming tails (k >= 3 % of k_max: measured optimum), high-priority
     // stream, issued first: they finish their early phases quickly and run their tails -- the serial critical
     // path -- while the bulk is still in the generic kernel.  The bulk is dealt round-robin into chunks, one
@@ -3230,13 +3255,10 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
       chunk_first[n_chunks] = pos;
     }
   
-    if (clpp_dev_reserve(d0, &d0->pt_cosmo, n_ctx * sizeof(PtCosmo), err)) return CLPP_FAILURE;
     if (clpp_dev_reserve(d0, &d0->pt_modes, (size_t)std::max(n_modes, 1) * sizeof(int2), err)) return CLPP_FAILURE;
     if (clpp_dev_reserve(d0, &d0->jac_scratch, (size_t)std::max(n_modes, 1) * P.scr_stride, err))
       return CLPP_FAILURE;
-    CLPP_CUDA(cudaMemcpyAsync(d0->pt_cosmo, cosmo.data(), n_ctx * sizeof(PtCosmo), cudaMemcpyHostToDevice, st), err);
     CLPP_CUDA(cudaMemcpyAsync(d0->pt_modes, sorted.data(), n_modes * sizeof(int2), cudaMemcpyHostToDevice, st), err);
-    P.cosmo = (const PtCosmo*)d0->pt_cosmo;
     P.modes = (const int2*)d0->pt_modes;
     P.n_modes = n_modes;
     P.hub_jac = d0->jac_scratch;
@@ -3297,7 +3319,6 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
         c0->launches++;
       }
     };
-    cudaEventRecord(d0->ev[0], st);
     if (n_modes > 0) {
       cudaEventRecord(d0->ev2[4], st);        // uploads on st are complete before the other streams start
       if (n_long > 0) {
@@ -3315,6 +3336,7 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
       }
     }
 }
+  if (n_lane > 0 && n_warp_modes > 0) cudaStreamWaitEvent(st, d0->lane_done, 0);
   cudaEventRecord(d0->ev[1], st);
   CLPP_CUDA(cudaGetLastError(), err);
   for (int b = 0; b < n_ctx; b++) {
