@@ -748,20 +748,20 @@ def test_hybrid_launch_of_a_batch_vs_single_solves(golden, monkeypatch):
     cl_single = sp.cl_[0].copy()
     ctx.close()
     monkeypatch.setenv("CLPP_LANE_KCUT", "0.05")  # coarse grid: 69 modes, both kernels get a share
-    ctxs, pts = [], []
+    ctxs, pts, tabs = [], [], []
     for _ in range(8):
         c = M.Context(0)
         b = M.BackgroundModule(inp, c)
         t = M.ThermodynamicsModule(inp, b)
         ctxs.append(c)
+        tabs.append((b, t))
         pts.append(M.PerturbationsModule(inp, b, t, solve=False))
     M.PerturbationsModule.solve_batch(pts)
     a = inp.arrays
-    for c, p in zip(ctxs, pts):
+    for (bg, th), p in zip(tabs, pts):
         ks = p.kstat_
         assert np.all(ks[:, 7] == 0) and np.all(ks[:, 0] > 0)
-        bg = M.BackgroundModule(inp, c)
-        tr = M.TransferModule(inp, bg, M.ThermodynamicsModule(inp, bg), p, None)
+        tr = M.TransferModule(inp, bg, th, p, None)
         cl = M.SpectraModule(inp, p, M.TabulatedPrimordial(a["pm.pk_at_transfer_k"]), None, tr).cl_[0]
         nz = cl_single != 0
         assert np.max(np.abs(cl[nz] / cl_single[nz] - 1.0)) < 3e-4
