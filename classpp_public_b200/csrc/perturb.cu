@@ -3202,11 +3202,16 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
       cudaEventRecord(d0->lane_go, st);  // uploads on st are complete
       cudaStreamWaitEvent(sl, d0->lane_go, 0);
     }
+    // Hybrid: the lane warps must leave room for the warp-per-mode kernels launched next (one 128-thread CTA of 252
+    // registers and 115 KB of shared memory per SM): an (unused) dynamic shared-memory request of 14 KB caps the lane kernel
+    // at 8 of its 16 possible warps per SM, i.e. half of the register file and 112 KB of shared memory.
+    size_t lane_smem = (n_warp_modes > 0) ? 14 * 1024 : 0;
+    if (getenv("CLPP_LANE_SMEM_KB")) lane_smem = (size_t)atoi(getenv("CLPP_LANE_SMEM_KB")) * 1024;  // developer knob
     switch (slab) {
-      case 1536: perturb_lane_kernel<1536><<<n_cta, LN_CTA, 0, sl>>>(PL); break;
-      case 4608: perturb_lane_kernel<4608><<<n_cta, LN_CTA, 0, sl>>>(PL); break;
-      case 14336: perturb_lane_kernel<14336><<<n_cta, LN_CTA, 0, sl>>>(PL); break;
-      default: perturb_lane_kernel<0><<<n_cta, LN_CTA, 0, sl>>>(PL); break;
+      case 1536: perturb_lane_kernel<1536><<<n_cta, LN_CTA, lane_smem, sl>>>(PL); break;
+      case 4608: perturb_lane_kernel<4608><<<n_cta, LN_CTA, lane_smem, sl>>>(PL); break;
+      case 14336: perturb_lane_kernel<14336><<<n_cta, LN_CTA, lane_smem, sl>>>(PL); break;
+      default: perturb_lane_kernel<0><<<n_cta, LN_CTA, lane_smem, sl>>>(PL); break;
     }
     c0->launches++;
     if (sl != st) cudaEventRecord(d0->lane_done, sl);
