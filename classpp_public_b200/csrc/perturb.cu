@@ -3142,33 +3142,42 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   for (int i = 0; i < n_modes; i++) perm[i] = i;
   std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cost[a] > cost[b]; });
   // ---- two families of kernels.
-  // LANES (lane.cuh, one THREAD per mode): every instruction serves 32 modes, tens of thousands of modes run at once, but a
-  // GPU thread walks a serial chain ~10x slower than a warp does (a step attempt of the radiation-streaming tail takes 31 k
-  // cycles in a lane, 15 k in a warp; the k = 22.6/Mpc chain alone is 3.6x10^5 attempts = 14 s in a lane).
-  // WARPS (one warp per mode, below): good latency, poor throughput (one mode per warp, 4..12 warps per SM).
-  // HYBRID (default for batches): the long chains -- the modes with k >= kcut, which hold most of the radiation-streaming
-  // and fluid-phase steps -- go to the warp kernels, the bulk (k < kcut: short chains dominated by the full-hierarchy
-  // phases) to the lane kernel on its own low-priority stream; the two run concurrently.  Measured: profiles/r02_*.
+  // WARPS (one warp per mode, below; the default): 2.2 s for one Planck-18 cosmology, 66 ms per cosmology in a batch of 128
+  // different ones.
+  // LANES (lane.cuh, one THREAD per mode; opt-in: context option "lane_path" or CLPP_LANE = 1): every instruction serves 32
+  // modes and tens of thousands of modes run at once, but a GPU thread walks a serial chain ~10x slower than a warp does
+  // (a step attempt of the 7-equation tail: 31 k cycles in a lane, 15 k in a warp; of the 136-equation system: 3-5 M cycles,
+  // its 35 KB of state stream from L2), so a launch lasts >= 14 s (identical cosmologies) .. 43 s (different ones: some lane
+  // of a warp refactorises / outputs at almost every attempt) whatever the batch; beyond ~500 cosmologies per launch the
+  // cost per cosmology (9 ms identical) undercuts the warp kernels.
+  // HYBRID (lane_path / CLPP_LANE = 2): modes with k >= kcut in the warp kernels, the bulk in the lane kernel on its own
+  // stream.  Measured on 128 different cosmologies (profiles/r02_lane_vs_warp.txt): the halves take 4.4 s + 5.6 s alone and
+  // 9.7 s together -- both fill the register file, so they run one after the other -- against 8.5 s for the warp kernels alone.
   int lane_mode = 0;  // 0: warps only, 1: lanes only, 2: hybrid
   if (c0->pd.evolver == 1 && !getenv("CLPP_WARP_PATH") && !getenv("CLPP_GENERIC_ONLY") && !getenv("CLPP_NO_TAIL") &&
       !getenv("CLPP_COHORT")) {
     const char* e = getenv("CLPP_LANE");
     const int forced = c0->lane_path >= 0 ? c0->lane_path : (e ? atoi(e) : -1);
-    lane_mode = forced >= 0 ? forced : (n_ctx >= 8 ? 2 : 0);
+    lane_mode = forced >= 0 ? forced : 0;
   }
   const double lane_kcut = getenv("CLPP_LANE_KCUT") ? atof(getenv("CLPP_LANE_KCUT")) : 0.6;  // 1/Mpc
   int n_lane = 0;  // the last n_lane modes of the cost-sorted order run in the lane kernel
   if (lane_mode == 1) n_lane = n_modes;
   else if (lane_mode == 2)
     while (n_lane < n_modes && cost[perm[n_modes - 1 - n_lane]] < lane_kcut) n_lane++;
-  const int n_warp_modes = n_modes - n_lane;
+  int n_warp_modes = n_modes - n_lane;
+  // developer knob (timing the two halves of a hybrid launch separately; the skipped modes are simply not integrated)
+  if (getenv("CLPP_HYBRID_SKIP")) {
+    if (!strcmp(getenv("CLPP_HYBRID_SKIP"), "warp")) n_warp_modes = 0;
+    else n_lane = 0;
+  }
   if (clpp_dev_reserve(d0, &d0->pt_cosmo, n_ctx * sizeof(PtCosmo), err)) return CLPP_FAILURE;
   CLPP_CUDA(cudaMemcpyAsync(d0->pt_cosmo, cosmo.data(), n_ctx * sizeof(PtCosmo), cudaMemcpyHostToDevice, st), err);
   P.cosmo = (const PtCosmo*)d0->pt_cosmo;
   cudaEventRecord(d0->ev[0], st);
   if (n_lane > 0) {
     std::vector<int2> lsorted(n_lane);
-    for (int i = 0; i < n_lane; i++) lsorted[i] = modes[perm[n_warp_modes + i]];
+    for (int i = 0; i < n_lane; i++) lsorted[i] = modes[perm[n_modes - n_lane + i]];
     if (clpp_dev_reserve(d0, &d0->ln_modes, (size_t)n_lane * sizeof(int2), err)) return CLPP_FAILURE;
     CLPP_CUDA(cudaMemcpyAsync(d0->ln_modes, lsorted.data(), n_lane * sizeof(int2), cudaMemcpyHostToDevice, st), err);
     std::vector<double> i2l1(P.n_i2l1);
@@ -3283,8 +3292,10 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     // Two unsynchronised cohorts on one SM share the instruction cache again: measured (bench.py --batch 64) the large
     // Planck-18 system (136 equations) runs 4 % faster with ONE 4-mode cohort per SM, the small LCDM one (46 equations,
     // smaller hot code) 1.7x faster with two. Large systems therefore claim more than half of the SM's shared memory.
+    // (measured, scripts/time_varied.py: for 128 DIFFERENT cosmologies two cohorts per SM are 13 % faster again -- their
+    // warps are out of step anyway -- so the padding only applies to small batches, where identical settings are likely)
     size_t smem_pad = 0;
-    if (wpc > 1 && P.neq_max >= 100 && smem * wpc <= 114 * 1024) smem_pad = 115 * 1024 - smem * wpc;
+    if (wpc > 1 && n_ctx < 8 && P.neq_max >= 100 && smem * wpc <= 114 * 1024) smem_pad = 115 * 1024 - smem * wpc;
     if (getenv("CLPP_SMEM_PAD_KB")) smem_pad = (size_t)atoi(getenv("CLPP_SMEM_PAD_KB")) * 1024;  // developer knob
     { static const cudaError_t once = clpp_allow_max_dynamic_smem(perturb_kernel); CLPP_CUDA(once, err); }
     P.wpc = wpc;

@@ -72,9 +72,35 @@ def make_pk(names):
     print("pk ->", path, "%.2f MB" % (os.path.getsize(path) / 1e6))
 
 
+def make_lhs(n):
+    """BASELINE config 5 in miniature: the first n points of the seed-0 Latin hypercube (Planck-18 settings, full default
+    grids) through the unmodified reference: C_l table, lensed C_l, linear and non-linear P_m(k, z=0) per cosmology."""
+    import json
+    from classpp_public_b200.upstream import latin_hypercube_sweep
+    pars = latin_hypercube_sweep(n, CONFIGS["planck18"], seed=0)
+    out = {"params": np.array(json.dumps(pars))}
+    for i, par in enumerate(pars):
+        ref = RefCosmology(par, threads=os.cpu_count()).compute("lensing")
+        out["%d__l" % i] = ref.get("tr.l")
+        out["%d__cl" % i] = ref.get("sp.cl")
+        out["%d__cl_lensed" % i] = ref.get("le.cl_lensed")
+        out["%d__k" % i] = ref.get("pt.k")
+        out["%d__pk_lin_m" % i] = ref.get("nl.pk_lin_m_at_pt_k")
+        out["%d__pk_nl_m" % i] = ref.get("nl.pk_nl_m_at_pt_k")
+        out["%d__sizes" % i] = np.array([ref.iscalar("pt.k_size"), ref.iscalar("pt.tau_size"), ref.iscalar("tr.q_size"),
+                                         ref.iscalar("sp.ct_size"), ref.iscalar("le.lt_size")], dtype=np.float64)
+        ref.close()
+        print("lhs", i, par["h"], par["omega_cdm"], flush=True)
+    path = os.path.join(HERE, "lhs%d.npz" % n)
+    np.savez_compressed(path, **out)
+    print("lhs ->", path, "%.2f MB" % (os.path.getsize(path) / 1e6))
+
+
 if __name__ == "__main__":
     args = sys.argv[1:]
-    if args and args[0] == "pk":
+    if args and args[0] == "lhs":
+        make_lhs(int(args[1]) if len(args) > 1 else 16)
+    elif args and args[0] == "pk":
         make_pk(args[1:] or ["lcdm_coarse", "lcdm", "planck18", "ncdm3_deg", "lcdm_dense"])
     else:
         for name in (args or ["lcdm_coarse", "lcdm", "planck18"]):

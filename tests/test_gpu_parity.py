@@ -740,13 +740,14 @@ def test_lane_kernel_full_pipeline_vs_golden(golden, monkeypatch, name):
 
 
 def test_hybrid_launch_of_a_batch_vs_single_solves(golden, monkeypatch):
-    """Default for batches (>= 8 cosmologies): modes with k >= kcut in the warp-per-mode kernels, the bulk in the lane kernel
-    on a second stream (CLPP_LANE=2).  Every cosmology of the batch gets the C_l of its single-cosmology solve to the level
+    """Hybrid launch (opt-in, CLPP_LANE=2): modes with k >= kcut in the warp-per-mode kernels, the bulk in the lane kernel
+    on a second stream.  Every cosmology of the batch gets the C_l of its single-cosmology solve to the level
     the two integrator families agree at (3e-4 on these coarse grids), every mode is integrated exactly once."""
     inp = golden("lcdm_coarse")
     ctx, pt, tr, sp = run_pipeline(inp)
     cl_single = sp.cl_[0].copy()
     ctx.close()
+    monkeypatch.setenv("CLPP_LANE", "2")
     monkeypatch.setenv("CLPP_LANE_KCUT", "0.05")  # coarse grid: 69 modes, both kernels get a share
     ctxs, pts, tabs = [], [], []
     for _ in range(8):
@@ -768,4 +769,56 @@ def test_hybrid_launch_of_a_batch_vs_single_solves(golden, monkeypatch):
     # the lane share and the warp share of one cosmology are both populated
     assert np.array_equal(pts[0].kstat_[:, 0], pts[5].kstat_[:, 0])
     for c in ctxs:
+        c.close()
+
+
+def test_latin_hypercube_batch_at_full_resolution_vs_golden():
+    """BASELINE config 5 in miniature, at FULL resolution and the north-star tolerance: the first 16 points of the seed-0
+    Latin hypercube (Planck-18 settings: 1 ncdm species, halofit; omega_b, omega_cdm, h, A_s, n_s, tau_reio varied over the
+    config-5 ranges) in ONE batched perturbation launch, upstream tables from the drop-in library.  Against the unmodified
+    reference (tests/golden/lhs16.npz, make_golden.py lhs): unlensed C_l^{TT,EE,TE,pp}, lensed TT/EE/TE/BB, linear and
+    non-linear P_m(k, z=0) of every cosmology."""
+    import json
+    from classpp_public_b200 import upstream
+    if not upstream.available():
+        pytest.skip("shim/_build/libclass_b200.so not built")
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "lhs16.npz"))
+    pars = json.loads(str(z["params"]))
+    inps = [upstream.inputs_for(p) for p in pars]
+    tabs, pts = [], []
+    for inp in inps:
+        c = M.Context(0)
+        c.set_option("lean_scratch", 1)
+        b = M.BackgroundModule(inp, c)
+        t = M.ThermodynamicsModule(inp, b)
+        tabs.append((c, b, t))
+        pts.append(M.PerturbationsModule(inp, b, t, solve=False))
+    M.PerturbationsModule.solve_batch(pts)
+    worst = {}
+    for i, (inp, (c, bg, th), pt, par) in enumerate(zip(inps, tabs, pts, pars)):
+        assert np.array_equal(pt.k_[0], z["%d__k" % i])  # grids bit-exact for every point of the sweep
+        prim = M.AnalyticPrimordial(par["A_s"], par["n_s"])
+        nl = M.NonlinearModule(inp, bg, pt, prim, fetch=True)
+        tr = M.TransferModule(inp, bg, th, pt, nl)
+        sp = M.SpectraModule(inp, pt, prim, nl, tr)
+        check_cl(sp, z["%d__cl" % i])
+        le = M.LensingModule(inp, sp)
+        lref = z["%d__cl_lensed" % i].reshape(-1, le.lt_size_)
+        ll = np.arange(2, le.l_lensed_max_ + 1)
+        mine = np.array([le.lensing_cl_at_l(int(l)) for l in ll[::7]])
+        ref = lref[ll[::7]]
+        tt, ee, te, bb = le.index_lt_tt_, le.index_lt_ee_, le.index_lt_te_, le.index_lt_bb_
+        e = {"lensed_tt": np.max(np.abs(mine[:, tt] / ref[:, tt] - 1)), "lensed_ee": np.max(np.abs(mine[:, ee] / ref[:, ee] - 1)),
+             "lensed_te": np.max(np.abs(mine[:, te] - ref[:, te]) / np.sqrt(ref[:, tt] * ref[:, ee])),
+             "lensed_bb": np.max(np.abs(mine[:, bb] / ref[:, bb] - 1))}
+        pk = pt.pk_linear(prim.pk_at_k(pt.k_[0]))
+        e["pk_lin"] = np.max(np.abs(pk / z["%d__pk_lin_m" % i] - 1))
+        r_nl = nl.nl_corr_density_[0].reshape(pt.info.tau_size, pt.info.k_size)[-1]
+        e["pk_nl"] = np.max(np.abs(pk * r_nl ** 2 / z["%d__pk_nl_m" % i] - 1))
+        for k_, v in e.items():
+            worst[k_] = max(worst.get(k_, 0.0), float(v))
+        assert e["lensed_tt"] < CL_RTOL and e["lensed_ee"] < CL_RTOL and e["lensed_te"] < CL_RTOL and e["lensed_bb"] < 2 * CL_RTOL, (i, e)
+        assert e["pk_lin"] < 1e-4 and e["pk_nl"] < 1e-4, (i, e)
+    print("worst relative errors over the 16 cosmologies:", worst)
+    for c, _, _ in tabs:
         c.close()
