@@ -222,8 +222,8 @@ def run_gpu(args):
     step()
     pipe.drain()
     solo_s = pipe.solve_seconds[-1]
-    if NSET > 1:
-        pipe.stagger = max(solo_s / NSET, 0.0) if args.stagger < 0 else args.stagger * solo_s
+    if NSET > 1 and args.stagger >= 0:  # default: one batched launch at a time, only the per-cosmology stages overlap it
+        pipe.stagger = args.stagger * solo_s
     for _ in range(max(args.warmup - 1, 0)):
         step()
     pipe.drain()
@@ -323,7 +323,7 @@ def run_gpu(args):
     sec_achieved = ALGO_FLOP_PER_LOS_POINT * float(info_tr.n_points) / t_los / 1e12
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     traffic = json.load(open(TRAFFIC_FILE)) if os.path.exists(TRAFFIC_FILE) else {}
-    kern = "perturb_lane_kernel" if (args.path == "lane" or (args.path == "auto" and B >= 256)) else "perturb_kernel + perturb_tail_kernel"
+    kern = "perturb_lane_kernel" if args.path == "lane" else "perturb_kernel + perturb_tail_kernel"
     roofline = {"kernel": kern, "bound": "fp64-vector (latency-bound in practice; neither hbm nor tensor)",
                 "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "peak_source": "DFMA microbenchmark run live in bench.py (MEASURED_PEAKS.json has no FP64 entry; "
@@ -369,13 +369,14 @@ def run_gpu(args):
                    "scope": "per cosmology: perturbations -> halofit -> transfer -> spectra -> lensing (fast mode) -> linear P(k)",
                    "k_modes": int(info_pt.k_size), "tau_samples": int(info_pt.tau_size),
                    "q_values": int(info_tr.q_size), "l_values": int(info_tr.l_size),
-                   "pipeline": ("%d context sets of %d cosmologies; batched perturbation launches of consecutive steps overlap, "
-                                "%.2f s apart (solo launch %.2f s); per-cosmology stages run under them; all drained before the "
-                                "clock stops" % (NSET, B, pipe.stagger or 0.0, solo_s)) if NSET > 1 else "off",
+                   "pipeline": ("%d context sets of %d cosmologies; %s (solo launch %.2f s); the per-cosmology stages of a step run "
+                                "under the launch of the next one; all drained before the clock stops" %
+                                (NSET, B, ("batched perturbation launches of consecutive steps overlap, %.2f s apart" % pipe.stagger)
+                                 if pipe.stagger is not None else "one batched perturbation launch at a time", solo_s)) if NSET > 1 else "off",
                    "launch_log_set_start_end_s": launch_log,
-                   "parallelism": "independent cosmologies per GPU (replicas, no data-path collective); per GPU every k mode of a "
-                                  "batch in one launch, one THREAD per mode (lane kernel) from 256 cosmologies per launch, one "
-                                  "warp per mode below",
+                   "parallelism": "independent cosmologies per GPU (replicas, no data-path collective); per GPU every k mode of the "
+                                  "batch in one batched launch, one warp per mode: long-tail modes on a high-priority stream, the "
+                                  "bulk in chunks on low-priority streams, generic kernel -> radiation-streaming tail kernel",
                    "l2_policy": "working set per step = batch x (tables 6 MB + sources 24 MB + per-mode state 35 KB x 617 + transfer "
                                 "work buffers 90 MB) >> 126 MB L2; every buffer is rewritten every step",
                    "timing": "torch.cuda.Event around K steps after device-wide synchronize, max over ranks; per-kernel "
@@ -523,9 +524,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="planck18")
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("CLPP_BENCH_BATCH", 512)),
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("CLPP_BENCH_BATCH", 128)),
                     help="cosmologies per GPU and per step (one batched perturbation launch)")
-    ap.add_argument("--sets", type=int, default=int(os.environ.get("CLPP_BENCH_SETS", 3)),
+    ap.add_argument("--sets", type=int, default=int(os.environ.get("CLPP_BENCH_SETS", 2)),
                     help="context sets = batched launches in flight (consecutive steps overlap)")
     ap.add_argument("--identical", action="store_true", help="batch = copies of the Planck-18 best fit instead of the Latin hypercube")
     ap.add_argument("--path", default="auto", choices=["auto", "lane", "warp"], help="perturbation kernels (auto: by batch size)")
@@ -534,7 +535,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stagger", type=float, default=-1.0,
                     help="pipeline: >= 0 lets the batched launches of consecutive steps overlap, this fraction of a solo "
-                         "launch duration apart (default: one launch at a time, only the per-cosmology stages overlap it)")
+                         "launch duration apart (useful with --path lane; default: one launch at a time, only the "
+                         "per-cosmology stages overlap it)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="one set of contexts: the per-cosmology stages of a step finish before the next step starts")
     args = ap.parse_args()
