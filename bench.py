@@ -111,7 +111,9 @@ def sweep_inputs(args, M):
             if not upstream.available():
                 raise ImportError("shim/_build/libclass_b200.so not found")
             from concurrent.futures import ThreadPoolExecutor
-            pars = upstream.latin_hypercube_sweep(args.batch, base, seed=0)
+            # weak scaling: every rank takes its own shard of one Latin hypercube of batch x world points
+            rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+            pars = upstream.latin_hypercube_sweep(args.batch * world, base, seed=0)[rank::world]
             t0 = time.perf_counter()
             with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
                 inps = list(ex.map(upstream.inputs_for, pars))
@@ -305,6 +307,24 @@ def run_gpu(args):
                "latency_note": "one cosmology alone on the GPU (warp-per-mode kernels: bounded by the k = 22.6/Mpc chain of 3.6e5 "
                                "step attempts); second of two runs"}
         c1.close()
+
+    # ---- the same cosmology over ALL ranks (north-star split: cost-balanced k lists -> NCCL all-gather of S(k,tau) ->
+    # q ranges -> all-reduce of the partial C_l); bounded by the one k = 22.6/Mpc chain, so it does not get faster with N
+    if world > 1 and not args.no_latency:
+        from classpp_public_b200 import multigpu
+        fixture = M.Inputs.load(os.path.join(ROOT, "tests", "golden", args.config + ".npz"))
+        from classpp_public_b200.configs import CONFIGS
+        prim_f = M.AnalyticPrimordial(CONFIGS[args.config].get("A_s", 2.215e-9), CONFIGS[args.config].get("n_s", 0.9619))
+        for rep in range(2):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t1 = time.perf_counter()
+            multigpu.compute_cl_distributed(fixture, prim_f, None, rank, world, local)
+            torch.cuda.synchronize()
+            dist.barrier()
+            t_dist = time.perf_counter() - t1
+        lat["latency_single_cosmology_distributed_s"] = t_dist
+        lat["latency_distributed_note"] = "the Planck-18 best fit split over %d GPUs (second of two runs)" % world
 
     if rank != 0:
         if world > 1:

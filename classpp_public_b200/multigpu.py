@@ -5,9 +5,9 @@ One process per GPU; `torch.distributed` (NCCL) is the plumbing, the device buff
 zero-copy as torch tensors.  The exchange step is a real one (stage 2 needs S at ALL k for the cubic spline in k,
 transfer_module.cpp:604), unlike the sweep path (sweep.py), which has no data-path collective.
 
-`Exchange` abstracts the two collectives so that the partition / merge logic can be exercised on ONE GPU
-(`LocalExchange`: the "ranks" are contexts of the same process; tests/test_gpu_parity.py) exactly as it runs
-under torchrun (`DistExchange`).
+`DistExchange` holds the two collectives (torch.distributed / NCCL).  The partition / merge logic around them is also
+exercised on ONE GPU with the "ranks" emulated as contexts of the same process and the collectives replaced by direct
+copies (tests/test_gpu_parity.py::test_one_cosmology_over_two_ranks_equals_single_gpu).
 """
 import ctypes as C
 
@@ -110,6 +110,9 @@ def compute_cl_distributed(inputs, primordial, nonlinear, rank, world, device, g
     solve_modes(pt, parts[rank])
     ex = DistExchange(rank, world, group)
     ex.allgather_columns(device_sources(pt), parts)
+    if nonlinear is None and int(inputs.meta.get("nl.method", 0)) != 0:
+        # `non linear = halofit`: every rank now holds delta_m at all k and runs the (3 ms) halofit step on its own device
+        nonlinear = M.NonlinearModule(inputs, bg, pt, primordial)
     tr, sp, cl = finish(inputs, bg, th, pt, primordial, nonlinear, rank, world, ex)
     ct = sp.ct_size_
     ctx.close()

@@ -75,16 +75,53 @@ def test_grids_bit_exact_for_a_latin_hypercube_sweep(reference):
     assert len(sizes) > 1  # the grids really differ from point to point
 
 
-def test_spline_tables_match_private_reference_tables(reference):
-    """Our rebuilt second-derivative tables equal the reference's private ones bit for bit; checked
-    indirectly (tau grid) above and directly here through the host interpolator."""
+def test_spline_tables_match_private_reference_tables(reference, tmp_path):
+    """csrc/host_tables.cpp rebuilds the second-derivative tables that the reference keeps private
+    (background_module.h:177, thermodynamics_module.h:122-124): clpp_spline_table_lines on the reference's public tables must
+    reproduce `d2background_dtau2_table_` and `d2thermodynamics_dz2_table_` BIT FOR BIT (same recurrences in the same order as
+    array_spline_table_lines(..., _SPLINE_EST_DERIV_), tools/arrays.c:514-660) -- the interpolated background / thermodynamics
+    of the device path, and through them the tau grid, hang on it."""
     if reference is None:
         pytest.skip("oracle/_ref not built")
-    ref = reference("lcdm_coarse", "thermodynamics")
-    # rebuild with numpy the same recurrences as tools/arrays.c:514-660 would be a restatement of a
-    # restatement; instead compare the grids that depend on every interpolated column (done above)
-    d2 = ref.get("bg.d2background_dtau2_table")
-    assert np.all(np.isfinite(d2))
+    import os
+    import subprocess
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(ROOT, "classpp_public_b200", "csrc")
+    src = tmp_path / "spl.cpp"
+    src.write_text("""
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "clpp_internal.h"
+int main(int argc, char** argv) {
+  const int n = atoi(argv[1]), m = atoi(argv[2]);
+  std::vector<double> x(n), y((size_t)n * m), dd((size_t)n * m);
+  FILE* f = fopen(argv[3], "rb");
+  if (fread(x.data(), 8, n, f) != (size_t)n || fread(y.data(), 8, (size_t)n * m, f) != (size_t)n * m) return 2;
+  fclose(f);
+  clpp_spline_table_lines(x.data(), n, y.data(), m, dd.data());
+  f = fopen(argv[4], "wb");
+  fwrite(dd.data(), 8, (size_t)n * m, f);
+  fclose(f);
+  return 0;
+}
+""")
+    exe = str(tmp_path / "spl")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-I", csrc,
+                           str(src), os.path.join(csrc, "host_tables.cpp"), "-o", exe])
+    ref = reference("planck18", "thermodynamics")
+    for x_key, y_key, d_key in (("bg.tau_table", "bg.background_table", "bg.d2background_dtau2_table"),
+                                ("th.z_table", "th.thermodynamics_table", "th.d2thermodynamics_dz2_table")):
+        x, y, d2 = ref.get(x_key), ref.get(y_key), ref.get(d_key)
+        n, m = len(x), len(y) // len(x)
+        fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+        with open(fin, "wb") as f:
+            f.write(x.tobytes())
+            f.write(y.tobytes())
+        subprocess.check_call([exe, str(n), str(m), fin, fout])
+        mine = np.fromfile(fout, dtype=np.float64)
+        assert mine.shape == d2.shape
+        assert np.array_equal(mine, d2), (d_key, float(np.max(np.abs(mine - d2))))
 
 
 def test_unsupported_inputs_fail_loudly(golden):
