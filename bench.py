@@ -93,6 +93,8 @@ class _NL:
         self.nl_corr_density_m = arr
 
 
+_RESULT_LINE = []  # the one JSON line of rank 0 (printed by main() after stdout has been restored)
+
 # DRAM bytes one batched perturbation launch moves per cosmology: measured with ncu (profiles/, see roofline.traffic_source)
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic.json")
 
@@ -416,7 +418,7 @@ def run_gpu(args):
     out.update(lat)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.config, budget_s=20.0, identical=(wl["kind"] != "lhs"))
-    print(json.dumps(out))
+    _RESULT_LINE.append(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -563,7 +565,19 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_gpu(args)
+        # the contract is ONE JSON line on stdout: libraries (NCCL's version banner) write to the stdout file descriptor
+        # directly, so everything but that line is sent to stderr at the descriptor level
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            run_gpu(args)
+        finally:
+            sys.stdout.flush()
+            os.dup2(real_stdout, 1)
+            os.close(real_stdout)
+            if _RESULT_LINE:
+                print(_RESULT_LINE[0], flush=True)
 
 
 if __name__ == "__main__":
