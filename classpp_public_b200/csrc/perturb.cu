@@ -3140,7 +3140,19 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
   const int n_modes = (int)modes.size();
   std::vector<int> perm(n_modes);
   for (int i = 0; i < n_modes; i++) perm[i] = i;
-  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  // (developer knob CLPP_SORT_BLOCK = n: cohorts of n ADJACENT k of the same cosmology instead of the same k of n neighbouring
+  //  cosmologies -- the warps of a cohort then walk through the same background / thermodynamics table rows)
+  const int sort_block = getenv("CLPP_SORT_BLOCK") ? std::max(1, atoi(getenv("CLPP_SORT_BLOCK"))) : 1;
+  if (sort_block > 1 && k_list == nullptr) {
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
+      const int ka = modes[a].y / sort_block, kb = modes[b].y / sort_block;
+      if (ka != kb) return ka > kb;
+      if (modes[a].x != modes[b].x) return modes[a].x < modes[b].x;
+      return modes[a].y > modes[b].y;
+    });
+  } else {
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  }
   // ---- two families of kernels.
   // WARPS (one warp per mode, below; the default): 2.2 s for one Planck-18 cosmology, 66 ms per cosmology in a batch of 128
   // different ones.
