@@ -298,6 +298,17 @@ long rp_get(void* h, const char* cname, double* out, long cap) {
     if (n.nonlinear_pk_at_z(linear, pk_nonlinear, 0., n.index_pk_m_, pk.data(), nullptr) != 0) return -1;
     return put(pk.data(), nk, out, cap);
   }
+  if (name.rfind("nl.pk_lin_m_at_z.", 0) == 0 || name.rfind("nl.pk_nl_m_at_z.", 0) == 0) {  // P_m(k, z) on the perturbation k grid
+    const bool nonlin = name.rfind("nl.pk_nl_m_at_z.", 0) == 0;
+    const double z = std::stod(name.substr(nonlin ? 16 : 17));
+    const NonlinearModule& n = *c.GetNonlinearModule();
+    const PerturbationsModule& m = *c.GetPerturbationsModule();
+    const int nk = m.k_size_[m.index_md_scalars_];
+    if (!n.has_pk_m_ || (nonlin && nl.method == nl_none)) return 0;
+    std::vector<double> pk(n.k_size_);
+    if (n.nonlinear_pk_at_z(linear, nonlin ? pk_nonlinear : pk_linear, z, n.index_pk_m_, pk.data(), nullptr) != 0) return -1;
+    return put(pk.data(), nk, out, cap);
+  }
   if (name == "nl.sigma8_m") {
     const NonlinearModule& n = *c.GetNonlinearModule();
     if (!n.has_pk_m_) return 0;

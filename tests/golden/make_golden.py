@@ -72,6 +72,20 @@ def make_pk(names):
     print("pk ->", path, "%.2f MB" % (os.path.getsize(path) / 1e6))
 
 
+def make_pk_z(z_list=(0.0, 0.5, 1.5)):
+    """P_m(k, z) at z > 0 (Planck-18 settings with z_max_pk = 2: the late-time source table and its spline in ln tau)."""
+    par = dict(CONFIGS["planck18"], z_max_pk=2.0)
+    ref = RefCosmology(par, threads=os.cpu_count()).compute("nonlinear")
+    out = {"k": ref.get("pt.k"), "z": np.array(z_list), "sigma8": ref.get("nl.sigma8_m")}
+    for z in z_list:
+        out["pk_lin_%g" % z] = ref.get("nl.pk_lin_m_at_z.%g" % z)
+        out["pk_nl_%g" % z] = ref.get("nl.pk_nl_m_at_z.%g" % z)
+    ref.close()
+    path = os.path.join(HERE, "pk_z.npz")
+    np.savez_compressed(path, **out)
+    print("pk(z) ->", path, "%.2f MB" % (os.path.getsize(path) / 1e6))
+
+
 def make_lhs(n):
     """BASELINE config 5 in miniature: the first n points of the seed-0 Latin hypercube (Planck-18 settings, full default
     grids) through the unmodified reference: C_l table, lensed C_l, linear and non-linear P_m(k, z=0) per cosmology."""
@@ -98,7 +112,9 @@ def make_lhs(n):
 
 if __name__ == "__main__":
     args = sys.argv[1:]
-    if args and args[0] == "lhs":
+    if args and args[0] == "pkz":
+        make_pk_z()
+    elif args and args[0] == "lhs":
         make_lhs(int(args[1]) if len(args) > 1 else 16)
     elif args and args[0] == "pk":
         make_pk(args[1:] or ["lcdm_coarse", "lcdm", "planck18", "ncdm3_deg", "lcdm_dense"])

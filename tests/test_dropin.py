@@ -121,3 +121,26 @@ def test_class_cli_through_the_dropin_writes_cl_files(tmp_path):
         assert os.path.exists(path), (suffix, os.listdir(tmp_path))
         data = np.loadtxt(path)
         assert data.shape[0] > 10 and np.all(np.isfinite(data))
+
+
+@needs_build
+@pytest.mark.gpu
+def test_pk_at_k_and_z_through_the_dropin_vs_golden():
+    """classy's pk(k, z), pk_lin(k, z) and sigma8() through the shimmed library with z_max_pk = 2: the reference's own
+    NonlinearModule (nonlinear_pk_at_k_and_z, halofit, sigma8) working on the device-computed sources, incl. the late-time
+    source table of the shim (ln tau spline, perturb_sources_at_tau) -- against the unmodified reference
+    (tests/golden/pk_z.npz, make_golden.py pkz) at z = 0, 0.5, 1.5 within 1e-4."""
+    classy = _classy()
+    z = np.load(os.path.join(ROOT, "tests", "golden", "pk_z.npz"))
+    p = _params("planck18")
+    p["z_max_pk"] = 2.0
+    c = classy.Class(p)
+    c.compute(level=["nonlinear"])
+    kk = z["k"]
+    sel = np.arange(5, len(kk) - 1, 9)  # interior nodes of the k grid
+    for zz in z["z"]:
+        lin = np.array([c.pk_lin(float(k), float(zz)) for k in kk[sel]])
+        nl = np.array([c.pk(float(k), float(zz)) for k in kk[sel]])
+        assert np.max(np.abs(lin / z["pk_lin_%g" % zz][sel] - 1.0)) < 1e-4, zz
+        assert np.max(np.abs(nl / z["pk_nl_%g" % zz][sel] - 1.0)) < 1e-4, zz
+    assert abs(c.sigma8() / float(z["sigma8"][0]) - 1.0) < 1e-4
