@@ -88,6 +88,12 @@ void clpp_ctx_destroy(clpp_ctx* c) {
     cudaEventDestroy(d->ev[1]);
     if (d->stream2) cudaStreamDestroy(d->stream2);
     if (d->stream_hi) cudaStreamDestroy(d->stream_hi);
+    if (d->lane_stream) cudaStreamDestroy(d->lane_stream);
+    if (d->lane_done) cudaEventDestroy(d->lane_done);
+    if (d->lane_go) cudaEventDestroy(d->lane_go);
+    if (d->tlane_stream) cudaStreamDestroy(d->tlane_stream);
+    if (d->tlane_go) cudaEventDestroy(d->tlane_go);
+    if (d->tlane_done) cudaEventDestroy(d->tlane_done);
     for (int i = 0; i < CLPP_PT_MAX_CHUNKS; i++) {
       if (d->chunk_stream[i]) cudaStreamDestroy(d->chunk_stream[i]);
       if (d->chunk_done[i]) cudaEventDestroy(d->chunk_done[i]);

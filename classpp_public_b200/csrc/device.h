@@ -35,6 +35,8 @@ struct clpp_ctx::Dev {
   unsigned char* ln_modes = nullptr;  // (cosmology, k) list of the lane kernel
   cudaStream_t lane_stream = nullptr;
   cudaEvent_t lane_done = nullptr, lane_go = nullptr;
+  cudaStream_t tlane_stream = nullptr;  // lane tails (perturb_tail_lane_kernel) of a group that also has warp tails
+  cudaEvent_t tlane_go = nullptr, tlane_done = nullptr;
   double* i2l1 = nullptr;         // 1/(2l+1)
   double* pt_tail = nullptr;      // hand-off records perturb_kernel -> perturb_tail_kernel
   size_t pt_tail_cap = 0;

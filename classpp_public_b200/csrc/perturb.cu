@@ -53,12 +53,19 @@ extern __shared__ double smem_all[];
 // The barrier is bar.sync 0 over the whole CTA, reached from different call sites (three integrators) by warps that are
 // each fully converged; a warp that finishes its mode (or hands it to the tail kernel) simply exits, which the hardware
 // counts as arrived, so cohorts may be ragged (last CTA of a launch, modes of different length).
+#ifndef PT_MAX_WPC
 #define PT_MAX_WPC 8
+#endif
+#ifndef PT_GEN_MIN_BLOCKS
+#define PT_GEN_MIN_BLOCKS 1  // 255 registers; build variants (-DPT_MAX_WPC=4 -DPT_GEN_MIN_BLOCKS=3) trade spills for occupancy
+#endif
 #define PT_LANE ((int)(threadIdx.x & 31))
 #define PT_WARP ((int)(threadIdx.x >> 5))
 #define PT_SLOT(P) ((int)(blockIdx.x * (P).wpc) + PT_WARP)
 #define SMEM(P) (smem_all + (size_t)PT_WARP * (P).wstride)
-#define PT_COHORT_SYNC(P) do { if ((P).wpc > 1) asm volatile("bar.sync 0;" ::: "memory"); } while (0)
+// `sync_ctr` is a local counter of the calling integrator: with sync_every = n a warp joins the barrier on every n-th of its
+// step attempts (the j-th barrier of one warp pairs with the j-th of the others; exited warps count as arrived)
+#define PT_COHORT_SYNC(P) do { if ((P).wpc > 1 && ++sync_ctr >= (P).sync_every) { sync_ctr = 0; asm volatile("bar.sync 0;" ::: "memory"); } } while (0)
 // every shared-memory access goes through these, so that the compiler sees the shared address
 // space (LDS/STS with 32-bit addresses) instead of generic pointers
 #define s_pvb(P) (SMEM(P))
@@ -1278,6 +1285,7 @@ __device__ __noinline__ bool ndf15(const PtParams& P, double t0, double tfinal) 
   bool done = false, at_hmin = false;
   double rate = 0., oldnrm = 0., err = 0.;
 
+  int sync_ctr = 0;
   while (!done) {
     PT_COHORT_SYNC(P);
     hmin = P.hmin_allowed;
@@ -1661,6 +1669,7 @@ __device__ __noinline__ bool ndf15_hub(const PtParams& P, double t0, double tfin
     __syncwarp();
   };
 
+  int sync_ctr = 0;
   while (!done) {
     PT_COHORT_SYNC(P);
     hmin = P.hmin_allowed;
@@ -2134,6 +2143,7 @@ __device__ __noinline__ bool ndf15_rsa(const PtParams& P, double t0, double tfin
     __syncwarp();
   };
 
+  int sync_ctr = 0;
   while (!done) {
     PT_COHORT_SYNC(P);
     hmin = P.hmin_allowed;
@@ -2729,7 +2739,7 @@ enum { TL_VALID = 0, TL_T0, TL_TF, TL_NEXT, TL_IV, TL_NINT, TL_TAU_INI, TL_FLAGS
 #ifndef PT_MIN_BLOCKS
 #define PT_MIN_BLOCKS 8
 #endif
-__global__ void __launch_bounds__(32 * PT_MAX_WPC, 1) perturb_kernel(const __grid_constant__ PtParams P) {
+__global__ void __launch_bounds__(32 * PT_MAX_WPC, PT_GEN_MIN_BLOCKS) perturb_kernel(const __grid_constant__ PtParams P) {
   if (PT_SLOT(P) >= P.n_modes) return;
   Mode& M = MODE(P);
   const int lane = PT_LANE;
@@ -2865,7 +2875,8 @@ __global__ void __launch_bounds__(32 * PT_MAX_WPC, 1) perturb_kernel(const __gri
     if (lane < n) T[TL_Y + lane] = s_vec(P, V_Y)[lane];
     if (lane == 0) {
       const Approx al = M.sched[n_int - 1];
-      T[TL_VALID] = 1.; T[TL_T0] = M.limit[n_int - 1]; T[TL_TF] = M.limit[n_int]; T[TL_NEXT] = M.next;
+      T[TL_VALID] = (M.k < P.tail_lane_kmax) ? 2. : 1.;  // 2: perturb_tail_lane_kernel takes it
+      T[TL_T0] = M.limit[n_int - 1]; T[TL_TF] = M.limit[n_int]; T[TL_NEXT] = M.next;
       T[TL_IV] = n_int - 1; T[TL_NINT] = n_int; T[TL_TAU_INI] = tau_ini;
       T[TL_FLAGS] = al.tca_off; T[TL_FLAGS + 1] = al.rsa_on; T[TL_FLAGS + 2] = al.ufa_on; T[TL_FLAGS + 3] = al.ncdmfa_on;
       T[TL_STAT] = M.st.steps; T[TL_STAT + 1] = M.st.failed; T[TL_STAT + 2] = M.st.fevals; T[TL_STAT + 3] = M.st.jacobians;
@@ -2948,6 +2959,74 @@ __global__ void __launch_bounds__(LN_CTA, LN_MIN_CTAS) perturb_lane_kernel(const
   } else {
     ln_mode(P, P.lane_scratch + (size_t)slot * P.ln_words, P.cosmo + md.x, md.y);
   }
+}
+
+// LANE TAIL: the radiation-streaming interval of the handed-off modes with k < P.tail_lane_kmax, one THREAD per mode
+// (ln_ndf15_tail: everything in registers).  A tail step attempt keeps 7 of a warp's 32 lanes busy in perturb_tail_kernel and
+// costs it 15-25 k cycles; a thread needs ~38 k cycles for the same attempt but a warp then advances 32 modes, so the tails
+// of the bulk (70 % of all step attempts of a launch, half of them in modes below k = 8/Mpc) leave the warp kernels' SM
+// slots to the generic phases.  Neighbouring slots hold neighbouring k of the sorted mode list (the same k of the
+// cosmologies of a sweep): the lanes of a warp take nearly the same number of steps.  Only the few longest chains stay in
+// perturb_tail_kernel: a lone thread walks them 2.6x slower than a lone warp, and they are the critical path of a launch.
+// P here is the generic kernel's parameter block with the slab geometry of a <= 16-equation system (np = 16, lo_vec = 0).
+#ifndef LN_TAIL_MIN_CTAS
+#define LN_TAIL_MIN_CTAS 8  // CTA = one warp; 8 per SM -> up to 255 registers per thread (the state of 7 equations is ~100 doubles)
+#endif
+#define LN_TAIL_NP 16
+__global__ void __launch_bounds__(LN_CTA, LN_TAIL_MIN_CTAS) perturb_tail_lane_kernel(const __grid_constant__ PtParams P) {
+  const int slot = blockIdx.x * LN_CTA + threadIdx.x;
+  if (slot >= P.n_modes) return;
+  const double* T = P.tail + (size_t)slot * TL_STRIDE;
+  if (T[TL_VALID] != 2.) return;
+  const int2 md = P.modes[slot];
+  const PtCosmo* C = P.cosmo + md.x;
+  const int ik = md.y;
+  double slab[5 * LN_TAIL_NP];  // LV_Y, and LV_TMP / LV_YPI (slots 4 and 3) of the source output
+  double* mem = slab;
+  Lane M;
+  M.C = C;
+  M.ik_index = ik;
+  M.k = C->k[ik];
+  M.k2 = M.k * M.k;
+  M.ik = 1.0 / M.k;
+  M.ik2 = 1.0 / M.k2;
+  M.bg_tau = C->bg_tau; M.bg_y = C->bg_y; M.bg_dd = C->bg_dd;
+  M.th_z = C->th_z; M.th_y = C->th_y; M.th_dd = C->th_dd;
+  M.bt_size = C->bt_size; M.tt_size = C->tt_size;
+  M.z_last = C->th_z[C->tt_size - 1]; M.th_lin = C->th_linear_below_z; M.a_today = C->a_today;
+  M.bg_cur = -1000000; M.th_cur = -1000000;  // first lookup by bisection
+  M.need_nw = 0; M.status = 0; M.tca_shear_last = 0.; M.fac_c = 0.;
+  M.m.h_prime = M.m.eta_prime = M.m.alpha = M.m.alpha_prime = M.m.rsa_delta_g = M.m.rsa_theta_g = 0.;
+  M.m.delta_m = M.m.delta_cb = M.m.tca_shear_g = 0.;
+  M.ap.tca_off = (int)T[TL_FLAGS]; M.ap.rsa_on = (int)T[TL_FLAGS + 1]; M.ap.ufa_on = (int)T[TL_FLAGS + 2];
+  M.ap.ncdmfa_on = (int)T[TL_FLAGS + 3];
+  M.apprev = M.ap;
+  ln_make_layout(P, M.ap, M.L);
+  M.Lprev = M.L;
+  M.next = (int)T[TL_NEXT];
+  M.st.steps = (int)T[TL_STAT]; M.st.failed = (int)T[TL_STAT + 1]; M.st.fevals = (int)T[TL_STAT + 2];
+  M.st.jacobians = (int)T[TL_STAT + 3]; M.st.factorizations = (int)T[TL_STAT + 4]; M.st.solves = (int)T[TL_STAT + 5];
+  const int n = M.L.neq;
+  for (int i = 0; i < n; i++) LVP(LV_Y)[i] = T[TL_Y + i];
+  const int iv = (int)T[TL_IV], n_int = (int)T[TL_NINT];
+  const long long c0 = clock64();
+  const int s0 = M.st.steps;
+  ln_run_tail(P, M, mem, T[TL_T0], T[TL_TF]);
+  clpp_kstat* ks = C->kstat + ik;
+  ks->iv_neq[iv] = n;
+  ks->iv_steps[iv] = M.st.steps - s0;
+  ks->iv_cycles[iv] = clock64() - c0;
+  // zero-fill the samples that were not reached (failure only) and publish the counters (mode_finish)
+  const int tau_size = C->tau_size;
+  const size_t stride_tp = (size_t)C->k_size * tau_size;
+  double* out = C->sources + (size_t)ik * tau_size;
+  const int tps[7] = {P.tp_t0, P.tp_t1, P.tp_t2, P.tp_p, P.tp_delta_m, P.tp_delta_cb, P.tp_phi_plus_psi};
+  for (int it = M.next; it < tau_size; it++)
+    for (int j = 0; j < 7; j++)
+      if (tps[j] >= 0) out[tps[j] * stride_tp + it] = 0.;
+  ks->steps = M.st.steps; ks->failed = M.st.failed; ks->fevals = M.st.fevals; ks->jacobians = M.st.jacobians;
+  ks->factorizations = M.st.factorizations; ks->solves = M.st.solves;
+  ks->intervals = n_int; ks->status = M.status; ks->tau_ini = T[TL_TAU_INI];
 }
 
 // =============================================================================================
@@ -3257,7 +3336,9 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     // cohort width: modes per CTA. Batches of several cosmologies put the same k of neighbouring cosmologies side by side in
     // the sorted order (near-identical step sequences); a single cosmology is a latency problem and keeps one mode per CTA.
     const size_t smem1 = perturb_smem_bytes(P);
-    int wpc = getenv("CLPP_COHORT") ? atoi(getenv("CLPP_COHORT")) : (n_ctx >= 4 ? 4 : 1);
+    // (measured, scripts/time_varied.py on 128 different cosmologies: cohorts of 8 = one 256-thread CTA per SM 7.8 s, of 4 = two
+    //  CTAs per SM 8.7 s, of 6 8.7 s: gpurun_out/r2_time_varied_v5.log in profiles/r02_lane_vs_warp.txt)
+    int wpc = getenv("CLPP_COHORT") ? atoi(getenv("CLPP_COHORT")) : (n_ctx >= 64 ? 8 : n_ctx >= 4 ? 4 : 1);
     wpc = std::max(1, std::min(wpc, PT_MAX_WPC));
     while (wpc > 1 && smem1 * wpc > 227 * 1024) wpc--;
     int wpc_tail = getenv("CLPP_COHORT_TAIL") ? atoi(getenv("CLPP_COHORT_TAIL")) : std::min(wpc, PT_TAIL_MAX_WPC);
@@ -3311,6 +3392,7 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     if (getenv("CLPP_SMEM_PAD_KB")) smem_pad = (size_t)atoi(getenv("CLPP_SMEM_PAD_KB")) * 1024;  // developer knob
     { static const cudaError_t once = clpp_allow_max_dynamic_smem(perturb_kernel); CLPP_CUDA(once, err); }
     P.wpc = wpc;
+    P.sync_every = std::max(1, getenv("CLPP_SYNC_EVERY") ? atoi(getenv("CLPP_SYNC_EVERY")) : 1);  // developer knob
     PtParams Pt = P;  // geometry of the tail kernel: at most 16 equations, all hub
     set_geometry(Pt, 16, 16, c0->pd);
     const size_t smem_tail = perturb_smem_bytes(Pt);
@@ -3332,6 +3414,26 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
       }
     }
     cudaStream_t sth = d0->stream_hi;
+    // Tails.  Handed-off modes with k >= tail_lane_kmax run in perturb_tail_kernel (a warp per mode), the others in
+    // perturb_tail_lane_kernel (a thread per mode).  OPT-IN (developer knob CLPP_TAIL_LANE_KMAX, 1/Mpc; default 0 = warps only):
+    // measured on 128 DIFFERENT Planck-18 cosmologies (profiles/r02_lane_tail.txt) the launch takes 8.5 s with warp tails,
+    // 9.6 s with lane tails below k = 3/Mpc, 10.7-16.5 s below 8/Mpc, 42-45 s with every tail in lanes: the 32 lanes of a warp
+    // belong to 32 different cosmologies, some lane refactorises or writes a source sample at almost every attempt, and the
+    // warp pays for the union of the branches (~340 k cycles per attempt against 38 k for identical cosmologies).
+    double tail_lane_kmax = 0.;
+    if (getenv("CLPP_TAIL_LANE_KMAX") && use_tail && n_ctx >= 8) tail_lane_kmax = atof(getenv("CLPP_TAIL_LANE_KMAX"));
+    if (4 + 3 * P.N_ncdm > LN_TAIL_NP) tail_lane_kmax = 0.;
+    P.tail_lane_kmax = tail_lane_kmax;
+    PtParams Pl = P;  // slab geometry of the lane tail: vectors of LN_TAIL_NP doubles
+    Pl.np = LN_TAIL_NP; Pl.lo_vec = 0; Pl.lo_nw = 5 * LN_TAIL_NP;
+    if (tail_lane_kmax > 0. && !d0->tlane_stream) {
+      int prio_lo = 0, prio_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+      CLPP_CUDA(cudaStreamCreateWithPriority(&d0->tlane_stream, cudaStreamNonBlocking, prio_hi), err);
+      CLPP_CUDA(cudaEventCreateWithFlags(&d0->tlane_go, cudaEventDisableTiming), err);
+      CLPP_CUDA(cudaEventCreateWithFlags(&d0->tlane_done, cudaEventDisableTiming), err);
+    }
+    bool tlane_used = false;
     auto launch_group = [&](cudaStream_t s, int first, int count, int wpc, int wpc_tail) {
       if (count <= 0) return;
       PtParams G = P, Gt = Pt;
@@ -3342,9 +3444,30 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
       perturb_kernel<<<(count + wpc - 1) / wpc, 32 * wpc, smem * wpc + smem_pad, s>>>(G);
       c0->launches++;
       if (use_tail) {
-        Gt.modes = G.modes; Gt.n_modes = count; Gt.tail = G.tail; Gt.hub_jac = G.hub_jac;
-        perturb_tail_kernel<<<(count + wpc_tail - 1) / wpc_tail, 32 * wpc_tail, smem_tail * wpc_tail, s>>>(Gt);
-        c0->launches++;
+        bool any_warp = false, any_lane = false;
+        for (int i = first; i < first + count; i++) {
+          if (cs[sorted[i].x]->k[sorted[i].y] < tail_lane_kmax) any_lane = true; else any_warp = true;
+        }
+        const bool side = any_warp && any_lane && !tlane_used;  // lane tails beside the warp tails, on their own stream
+        if (side) cudaEventRecord(d0->tlane_go, s);
+        if (any_warp) {
+          Gt.modes = G.modes; Gt.n_modes = count; Gt.tail = G.tail; Gt.hub_jac = G.hub_jac;
+          perturb_tail_kernel<<<(count + wpc_tail - 1) / wpc_tail, 32 * wpc_tail, smem_tail * wpc_tail, s>>>(Gt);
+          c0->launches++;
+        }
+        if (any_lane) {
+          PtParams Gl = Pl;
+          Gl.modes = G.modes; Gl.n_modes = count; Gl.tail = G.tail;
+          cudaStream_t sl = side ? d0->tlane_stream : s;
+          if (side) cudaStreamWaitEvent(sl, d0->tlane_go, 0);
+          perturb_tail_lane_kernel<<<(count + LN_CTA - 1) / LN_CTA, LN_CTA, 0, sl>>>(Gl);
+          c0->launches++;
+          if (side) {
+            cudaEventRecord(d0->tlane_done, sl);
+            cudaStreamWaitEvent(s, d0->tlane_done, 0);
+            tlane_used = true;
+          }
+        }
       }
     };
     if (n_modes > 0) {

@@ -35,6 +35,7 @@ struct PtParams {
   int n_modes;
   double* hub_jac;  // per-CTA global scratch [nh_max*nh_max]: hub block of the Jacobian
   double* tail;     // per-mode hand-off records for perturb_tail_kernel (nullptr: no tail kernel)
+  double tail_lane_kmax;  // handed-off modes with k below this run their tail in perturb_tail_lane_kernel (one thread per mode)
   int bg_size, bg_size_normal, th_size;
   // background column indices
   int ia, iH, iHp, irho_g, irho_b, irho_cdm, irho_ur, irho_ncdm1, ip_ncdm1, ipseudo_p_ncdm1;
@@ -59,6 +60,7 @@ struct PtParams {
   double rk_stepsize; // perturb_integration_stepsize (rk only)
   int force_generic;  // developer/test switch: integrate every interval with the generic shared-memory NDF
   int wpc, wstride;   // warps (k modes) per CTA; doubles of shared memory per warp
+  int sync_every;     // the cohort barrier is taken every sync_every-th step attempt of a warp (1: every attempt)
   int scr_stride;     // doubles of global scratch per mode (hub Jacobian + 4 vectors)
   int neq_max, np, nh_max, ldh;
   int o_mode, o_hubtmp, o_nw, o_i2l1, n_i2l1, o_tabc, ncol, o_vec, o_sinv, o_int;

@@ -772,6 +772,45 @@ def test_hybrid_launch_of_a_batch_vs_single_solves(golden, monkeypatch):
         c.close()
 
 
+@pytest.mark.parametrize("kmax", ["1e9", "0.05"])
+def test_lane_tails_of_a_batch_vs_warp_tails(golden, monkeypatch, kmax):
+    """Batches of >= 8 cosmologies run the radiation-streaming tails of their modes below k = tail_lane_kmax in
+    perturb_tail_lane_kernel (one thread per mode) instead of perturb_tail_kernel (one warp per mode).  Same integrator,
+    different arithmetic order: every mode is integrated exactly once, the step counts of the two agree within 2 % in
+    total, the sources of the cosmologies of a batch are identical to each other, and the C_l agree at the level the two
+    integrator families agree at on these coarse grids (3e-4).  kmax = 1e9: every tail in lanes; 0.05: both kernels."""
+    inp = golden("lcdm_coarse")
+    a = inp.arrays
+    out = {}
+    for setting in ("0", kmax):
+        monkeypatch.setenv("CLPP_TAIL_LANE_KMAX", setting)
+        ctxs, pts, tabs = [], [], []
+        for _ in range(8):
+            c = M.Context(0)
+            b = M.BackgroundModule(inp, c)
+            t = M.ThermodynamicsModule(inp, b)
+            ctxs.append(c)
+            tabs.append((b, t))
+            pts.append(M.PerturbationsModule(inp, b, t, solve=False))
+        M.PerturbationsModule.solve_batch(pts)
+        for p in pts:
+            assert np.all(p.kstat_[:, 7] == 0) and np.all(p.kstat_[:, 0] > 0)
+            assert np.array_equal(np.stack(p.sources_[0]), np.stack(pts[0].sources_[0]))
+        bg, th = tabs[2]
+        tr = M.TransferModule(inp, bg, th, pts[2], None)
+        cl = M.SpectraModule(inp, pts[2], M.TabulatedPrimordial(a["pm.pk_at_transfer_k"]), None, tr).cl_[0].copy()
+        out[setting] = (cl, pts[2].kstat_[:, :6].copy(), ctxs[0].launch_count)
+        for c in ctxs:
+            c.close()
+    cl0, ks0, n0 = out["0"]
+    cl1, ks1, n1 = out[kmax]
+    nz = cl0 != 0
+    assert np.max(np.abs(cl1[nz] / cl0[nz] - 1.0)) < 3e-4
+    assert abs(ks1[:, 0].sum() / ks0[:, 0].sum() - 1.0) < 0.02
+    if kmax == "0.05":
+        assert n1 > n0  # the group holding both kinds of tails launched both tail kernels
+
+
 def test_latin_hypercube_batch_at_full_resolution_vs_golden():
     """BASELINE config 5 in miniature, at FULL resolution and the north-star tolerance: the first 16 points of the seed-0
     Latin hypercube (Planck-18 settings: 1 ncdm species, halofit; omega_b, omega_cdm, h, A_s, n_s, tau_reio varied over the
