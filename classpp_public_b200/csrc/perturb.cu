@@ -3343,9 +3343,11 @@ int clpp_dev_perturb_solve_batch(clpp_ctx** cs, int n_ctx, const int* k_begin, c
     while (wpc > 1 && smem1 * wpc > 227 * 1024) wpc--;
     int wpc_tail = getenv("CLPP_COHORT_TAIL") ? atoi(getenv("CLPP_COHORT_TAIL")) : std::min(wpc, PT_TAIL_MAX_WPC);
     wpc_tail = std::max(1, std::min(wpc_tail, PT_TAIL_MAX_WPC));
-    // the long-tail group is the latency-critical path: lockstep only pays for it once the batch is throughput-bound
-    // (measured, scripts/sweep_varied.py: 32 different cosmologies lose 15 % with cohorts there, 96 gain 4 %)
-    int wpc_long = getenv("CLPP_COHORT_LONG") ? atoi(getenv("CLPP_COHORT_LONG")) : (n_ctx >= 64 ? wpc : 1);
+    // the long-tail group is the latency-critical path and keeps one mode per CTA: lockstep with neighbours only delays it
+    // (measured, scripts/sweep_varied.py: 32 different cosmologies lose 15 % with cohorts there, 96 gain 4 % with cohorts of 4;
+    //  scripts/time_varied.py with bulk cohorts of 8 on 128 different cosmologies: long group in cohorts of 8 7.84 s, of 4
+    //  7.86 s, of 1 7.65 s -- profiles/r02_time_varied_v7.log)
+    int wpc_long = getenv("CLPP_COHORT_LONG") ? atoi(getenv("CLPP_COHORT_LONG")) : 1;
     wpc_long = std::max(1, std::min(wpc_long, wpc));
     const int chunk_modes = getenv("CLPP_CHUNK_MODES") ? atoi(getenv("CLPP_CHUNK_MODES")) : 4000;  // developer knob
     const int n_chunks = use_tail ? std::max(1, std::min(PT_MAX_CHUNKS, n_bulk / std::max(chunk_modes, 1))) : 1;
