@@ -5,7 +5,8 @@ One process per GPU; `torch.distributed` (NCCL) is the plumbing, the device buff
 zero-copy as torch tensors.  The exchange step is a real one (stage 2 needs S at ALL k for the cubic spline in k,
 transfer_module.cpp:604), unlike the sweep path (sweep.py), which has no data-path collective.
 
-`DistExchange` holds the two collectives (torch.distributed / NCCL).  The partition / merge logic around them is also
+`DistExchange` holds the two collectives (torch.distributed / NCCL; on host tensors over gloo in
+tests/test_sweep_gloo.py::test_source_exchange_of_one_cosmology_world2).  The partition / merge logic around them is also
 exercised on ONE GPU with the "ranks" emulated as contexts of the same process and the collectives replaced by direct
 copies (tests/test_gpu_parity.py::test_one_cosmology_over_two_ranks_equals_single_gpu).
 """
@@ -64,12 +65,16 @@ class DistExchange:
             if r != self.rank and len(p):
                 idx = torch.as_tensor(p, device=S.device, dtype=torch.long)
                 S.index_copy_(1, idx, recv[r][:, : len(p), :])
-        torch.cuda.synchronize(S.device)
+        if S.is_cuda:  # (host tensors: the gloo test of this logic, tests/test_sweep_gloo.py)
+            torch.cuda.synchronize(S.device)
 
     def allreduce_sum(self, cl, device):
+        """Sum of the partial C_l tables of all ranks; `device` None keeps the table on the host (gloo test)."""
         import torch
         import torch.distributed as dist
-        t = torch.from_numpy(np.ascontiguousarray(cl)).to("cuda:%d" % device)
+        t = torch.from_numpy(np.ascontiguousarray(cl).copy())
+        if device is not None:
+            t = t.to("cuda:%d" % device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
 

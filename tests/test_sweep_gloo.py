@@ -39,6 +39,41 @@ def _worker(rank, world, port, n_items, width, ret):
         dist.destroy_process_group()
 
 
+def _exchange_worker(rank, world, port, k, ret):
+    """The exchange step of the one-cosmology-over-N-GPUs path (multigpu.DistExchange) on host tensors over gloo:
+    ragged cost-balanced k partitions, all-gather of the source columns, all-reduce of the partial C_l."""
+    import torch
+    from classpp_public_b200 import multigpu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        parts = sweep.partition_modes_by_cost(k, world)
+        ntp, nt = 3, 11
+        full = torch.arange(ntp * len(k) * nt, dtype=torch.float64).reshape(ntp, len(k), nt) * 0.5 + 1.0
+        S = torch.zeros_like(full)
+        mine = torch.as_tensor(parts[rank], dtype=torch.long)
+        S[:, mine, :] = full[:, mine, :]  # what stage 1 of this rank produced
+        ex = multigpu.DistExchange(rank, world)
+        ex.allgather_columns(S, parts)
+        cl = ex.allreduce_sum(np.full((4, 7), float(rank + 1)), None)
+        ret[rank] = (bool(torch.equal(S, full)), bool(np.all(cl == sum(range(1, world + 1)))), [len(p) for p in parts])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_source_exchange_of_one_cosmology_world2(golden):
+    k = np.asarray(golden("lcdm_coarse").arrays["ref.k"], dtype=np.float64)[:-2]  # odd count: ragged partitions
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_exchange_worker, args=(world, port, k, ret), nprocs=world, join=True)
+        for r in range(world):
+            assert ret[r][0] and ret[r][1], ret[r]
+        assert sum(ret[0][2]) == len(k)
+
+
 @pytest.mark.parametrize("n_items", [5, 8])
 def test_sweep_shard_and_gather_world2(n_items):
     world, width = 2, 791  # 113 l values x 7 spectra
