@@ -508,29 +508,37 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (make -C oracle needs /root/reference)"}))
         return
     cores = os.cpu_count()
-    # a step = `cores` cosmologies of the bench workload in the throughput arrangement (one single-threaded process each,
-    # ~15 s per step); the run is bounded to a few minutes: at most one warm-up step and eight timed steps
-    n_warm, n_steps = min(args.warmup, 1), max(1, min(args.steps, 8))
+    # a step = a bounded sample of the bench workload: its first `cores` cosmologies in the throughput arrangement (one
+    # single-threaded process each, ~8 s per step).  W warm-up and K timed steps as asked; a wall-clock budget of 5 minutes
+    # cuts the run short if the box is slower than that (the line then says how many steps were timed).
+    n_warm, n_steps = max(0, args.warmup), max(1, args.steps)
     vals = []
+    t_begin = time.perf_counter()
     for i in range(n_warm + n_steps):
+        t_step = time.perf_counter()
         r = reference_throughput(args.config, cores, args.identical)
         if i >= n_warm:
             vals.append(r)
+        t_now = time.perf_counter()
+        if vals and (t_now - t_begin) + (t_now - t_step) > 300.0:
+            break
     value = float(np.mean([v["value"] for v in vals]))
     lat, _, _ = _ref_hot_path_seconds(_sweep_params(args.config, 1, args.identical)[0], cores)
     lat, _, _ = _ref_hot_path_seconds(_sweep_params(args.config, 1, args.identical)[0], cores)
     from classpp_public_b200.configs import CONFIGS  # noqa: F401
     workload = ("BASELINE configs[1]: base_2018_plikHM_TTTEEE_lowl_lowE_lensing.ini settings (1 ncdm species, halofit, "
                 "l_max_scalars=2500, P_k_max_h/Mpc=1); batch = %d %s" %
-                (cores, "DIFFERENT cosmologies: seed-0 Latin hypercube of BASELINE configs[4] (omega_b, omega_cdm, h, ln10^10A_s, n_s, "
-                        "tau_reio)" if not args.identical else "copies of the Planck-18 best fit (identical cosmologies)"))
+                (args.batch, "DIFFERENT cosmologies: seed-0 Latin hypercube of BASELINE configs[4] (omega_b, omega_cdm, h, ln10^10A_s, n_s, "
+                             "tau_reio)" if not args.identical else "copies of the Planck-18 best fit (identical cosmologies)"))
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
            "steps": len(vals), "warmup": n_warm, "ms_per_step": float(np.mean([v["hot_path_s_max"] for v in vals])) * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload if args.config == "planck18" else args.config, "batch_per_gpu": int(cores),
-                      "note": "unmodified CLASS++ (oracle/_ref) on the host cores, throughput arrangement: each step = %d "
-                              "cosmologies as %d single-threaded processes; timed = Perturbations+Nonlinear+Transfer+Spectra+Lensing "
-                              "module constructors (the scope of the GPU arm's step); value = cosmologies / slowest process" % (cores, cores)},
+           "config": {"workload": workload if args.config == "planck18" else args.config, "batch_per_gpu": int(args.batch),
+                      "sample_cosmologies_per_step": int(cores),
+                      "note": "unmodified CLASS++ (oracle/_ref) on the host cores, throughput arrangement: each step = a bounded "
+                              "sample of the workload, its first %d cosmologies as %d single-threaded processes; timed = "
+                              "Perturbations+Nonlinear+Transfer+Spectra+Lensing module constructors (the scope of the GPU arm's "
+                              "step); value = cosmologies / slowest process" % (cores, cores)},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(cores), "kind": "reference",
                             "latency_arrangement": {"spectra_per_s": 1.0 / lat, "hot_path_s": lat, "threads": int(cores)},
                             "throughput_arrangement": vals[-1],
