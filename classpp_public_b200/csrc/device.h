@@ -90,16 +90,22 @@ inline cudaError_t clpp_allow_max_dynamic_smem(K kernel) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
 }
 
-// grow-only device buffer: reallocates only when the requested size exceeds the capacity
+// grow-only device buffer: reallocates only when the requested size exceeds the capacity.  Every allocation carries 25 %
+// of headroom: in a sweep the contexts are reused for cosmology after cosmology whose grids differ by a few per cent
+// (k_size, tau_size, bt_size, the Bessel x range), and a reallocation is a cudaFree -- which waits for the whole device,
+// i.e. for the batched perturbation launch in flight -- so without headroom the host stages meant to run under that launch
+// queue up behind it (profiles/r02_config5_lhs1024.json: launches of 9-13 s in a real sweep against 8 s in the bench, whose
+// batch repeats).
 template <typename T>
 inline int clpp_dev_reserve(clpp_ctx::Dev* d, T** p, size_t n, char* err) {
   const size_t bytes = (n > 0 ? n : 1) * sizeof(T);
   auto it = d->cap.find((void*)p);
   if (*p && it != d->cap.end() && it->second >= bytes) return CLPP_SUCCESS;
   if (*p) { cudaFree(*p); *p = nullptr; }
-  cudaError_t e = cudaMalloc((void**)p, bytes);
-  if (e != cudaSuccess) return clpp_fail(err, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
-  d->cap[(void*)p] = bytes;
+  const size_t padded = (bytes + bytes / 4 + 255) & ~(size_t)255;
+  cudaError_t e = cudaMalloc((void**)p, padded);
+  if (e != cudaSuccess) return clpp_fail(err, "cudaMalloc of %zu bytes failed: %s", padded, cudaGetErrorString(e));
+  d->cap[(void*)p] = padded;
   return CLPP_SUCCESS;
 }
 

@@ -1,5 +1,6 @@
 """BASELINE config 5 on the device, every spectrum against the unmodified reference (a one-off parity run, not collected by
-pytest: `python tests/config5_sweep.py [n=1024] [batch=128]` on a GPU box).
+pytest: `python tests/config5_sweep.py [n=1024] [batch=128] [first=n]` on a GPU box; `first`: only the first so many points of
+the n-point fixture).
 
 The n-point seed-0 Latin hypercube over (omega_b, omega_cdm, h, ln10^10A_s, n_s, tau_reio) with the Planck-18 settings goes
 through the sweep scheduler (classpp_public_b200/sweep.py: batches of `batch` cosmologies, one batched perturbation launch
@@ -52,6 +53,10 @@ def main():
     ref_failures = dict((int(i), m) for i, m in json.loads(str(z["failures"])))
     stride = int(z["l_stride"])
     assert len(pars) == n and upstream.available(), "needs shim/_build/libclass_b200.so (python -c 'import __graft_entry__ as g; g.build()')"
+    n_fixture = n
+    if len(sys.argv) > 3:
+        n = min(n, int(sys.argv[3]))
+        pars = pars[:n]
     B = min(B, n)
     n_chunks = (n + B - 1) // B
     NSET = 2
@@ -137,13 +142,14 @@ def main():
     done = ~np.isnan(err[:, 0])
     out = {
         "what": "BASELINE config 5: %d-point seed-0 Latin hypercube (omega_b, omega_cdm, h, ln10^10A_s, n_s, tau_reio), Planck-18 "
-                "settings at full resolution, one B200, batches of %d; every cosmology against the unmodified reference" % (n, B),
+                "settings at full resolution, one B200, batches of %d; every cosmology against the unmodified reference%s"
+                % (n_fixture, B, "" if n == n_fixture else " (this run: the first %d points only)" % n),
         "n": n, "compared": int(done.sum()), "failures": failures, "tolerance": TOL,
         "wall_s": wall, "spectra_per_s_including_upstream": n / wall,
         "perturb_launch_s": [round(x, 2) for x in pipe.solve_seconds],
         "upstream_host_s_per_cosmology_single_thread_mean": float(host_s.mean()),
         "reference": {"wall_s": float(z["wall_s"]), "processes": int(z["processes"]),
-                      "seconds_per_cosmology_mean": float(np.mean([z["%d__seconds" % i] for i in range(n) if i not in ref_failures])),
+                      "seconds_per_cosmology_mean": float(np.mean([z["%d__seconds" % i] for i in range(n_fixture) if i not in ref_failures])),
                       "where": "the build container (not the GPU box's host): a cross-check of the fixture, not a baseline"},
         "max_rel_err": {k: float(np.nanmax(err[:, j])) for j, k in enumerate(SPECTRA)},
         "median_rel_err": {k: float(np.nanmedian(err[:, j])) for j, k in enumerate(SPECTRA)},
@@ -151,7 +157,7 @@ def main():
         "worst_point": {k: pars[int(np.nanargmax(err[:, j]))] for j, k in enumerate(SPECTRA)},
     }
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    path = os.path.join(ROOT, "gpurun_out", "config5_lhs%d.json" % n)
+    path = os.path.join(ROOT, "gpurun_out", "config5_lhs%d%s.json" % (n_fixture, "" if n == n_fixture else "_first%d" % n))
     with open(path, "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps({k: out[k] for k in ("n", "compared", "failures", "wall_s", "spectra_per_s_including_upstream",
