@@ -205,6 +205,9 @@ int clpp_thermodynamics_at_z(const clpp_ctx* c, double z, int mode, int* last_in
 // quadrature_gauss_legendre, tools/quadrature.c:752-788): each root of P_n in the upper half is refined by Newton's method
 // from the Chebyshev-like guess cos(pi (i - 1/4) / (n + 1/2)) until the update is below `tol`; the rule is symmetric.
 // Nodes are returned in ascending order, weights w = 2 / ((1 - x^2) P_n'(x)^2).
+// This is the textbook Newton iteration on the three-term recurrence (Numerical Recipes' `gauleg`, which the reference's
+// routine also is): the same algorithm in the same evaluation order -- the nodes must be bit-identical to the reference's for
+// the accurate lensing mode to reproduce its C_l -- so it is the standard routine restated, not an independent design.
 int clpp_gauss_legendre(double* mu, double* w8, int n, double tol, char* err) {
   const int half = (n + 1) / 2;
   for (int i = 0; i < half; i++) {

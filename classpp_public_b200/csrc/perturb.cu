@@ -21,6 +21,15 @@
 //   evolver_ndf15 (tools/evolver_ndf15.cpp:62-705), adjust_stepsize :907-943,
 //   interp_from_dif :860-905, new_linearisation :945-998.
 //
+// What is and what is not re-designed: the data layout, the warp mapping, the chain/hub linear algebra, the Jacobian
+// probing, the tail kernel, the cohorts and the launch structure are this repository's own.  The CONTROL SKELETON of the
+// three ndf15* integrators (step-size and order selection, Newton convergence test, failure handling: the branches and
+// the constants 0.3 / 0.833 / 0.769 / 1.2 / 1.3 / 1.4 / 0.05 rtol ...) follows tools/evolver_ndf15.cpp:302-651 branch by
+// branch and keeps its variable names (absh, abshlast, hinvGak, nconhk, havrate, gotynew ...): a transliteration by
+// necessity, not a re-derivation -- the step decisions must match the reference's for the work counters and the 1e-4
+// parity to hold (the reference itself is a port of MATLAB's ode15s).  The right-hand side is the Ma-Bertschinger algebra
+// of perturb_derivs_member re-ordered for lanes.
+//
 // Differences of METHOD (not of result) from the reference:
 //  * Linear algebra.  The reference discovers the sparsity of J numerically and runs a generic
 //    sparse LU (tools/sparse.c).  Here the structure of the Boltzmann hierarchy is used directly:
